@@ -1,0 +1,584 @@
+"""TEST ORACLE -- a NumPy execution backend with the reference's API.
+
+Test infrastructure only (see oracle/physics.py for who may import it).
+``make_backend(base)`` builds the backend classes on top of either the
+reference's own ``pyfr.backends.base`` package (when /root/reference is
+importable; used to pin this repo's host mirror against the reference's
+host code) or this repo's ``pyfr_b200.base`` mirror (everywhere else).
+
+It honours the real storage layout -- matrices live at their byte offset
+inside extents and kernels address them with the argument-dereference
+rules of ``pyfr/backends/base/generator.py:171-276`` -- so view
+``mapping``/``rstrides`` arrays are exercised exactly as a device backend
+would exercise them.  Kernel arithmetic comes from oracle/physics.py.
+"""
+
+import numpy as np
+from numpy.lib.stride_tricks import as_strided
+
+from oracle import physics as ph
+
+
+def _mat3(m, padto=1):
+    """Strided (nblocks, nrow, width) window onto a matrix or slice."""
+    it = m.itemsize
+    flat = m.basedata.view(m.dtype)
+    blocked = m.backend.blocks and not ({'xchg', 'noblock'} & set(m.tags))
+    width = m.leaddim if blocked else -(-m.ncol // padto)*padto
+    nblocks = m.nblocks if blocked else 1
+
+    return as_strided(flat[m.offset // it:],
+                      shape=(nblocks, m.nrow, width),
+                      strides=(m.blocksz*it, m.leaddim*it, it))
+
+
+def _stacked(m, nvar, nlead=None):
+    """View with the variable (and leading stack) axes in front:
+    ``[nlead,] nvar, nblocks, npts, nchunks, k``."""
+    k = m.backend.soasz
+    a = _mat3(m)
+    nb, nrow, w = a.shape
+    a = a.reshape(nb, nrow, w // (nvar*k), nvar, k)
+
+    if nlead is None:
+        return a.transpose(3, 0, 1, 2, 4)
+    else:
+        a = a.reshape(nb, nlead, nrow // nlead, w // (nvar*k), nvar, k)
+        return a.transpose(1, 4, 0, 2, 3, 5)
+
+
+def _plain(m):
+    """(nblocks, nrow, nchunks, k) window on a plain 2-D matrix."""
+    k = m.backend.soasz
+    a = _mat3(m, padto=k)
+    return a.reshape(a.shape[0], a.shape[1], a.shape[2] // k, k)
+
+
+class _ViewRef:
+    """Gather/scatter through a view: v[r][c] <-> base[map + rstr*r + k*c]"""
+
+    def __init__(self, view):
+        if hasattr(view, 'view'):
+            view = view.view
+
+        self.flat = view.basedata.view(view.refdtype)
+        self.map = view.mapping.get()[0].astype(np.int64)
+        self.k = view.mapping.backend.soasz
+        self.rstr = (view.rstrides.get()[0].astype(np.int64)
+                     if view.rstrides is not None else None)
+
+    def load(self, c, r=None):
+        ix = self.map + self.k*c
+        if r is not None:
+            ix = ix + self.rstr*r
+        return self.flat[ix]
+
+    def store(self, val, c, r=None):
+        ix = self.map + self.k*c
+        if r is not None:
+            ix = ix + self.rstr*r
+        self.flat[ix] = val
+
+
+def make_backend(base, name='oracle-numpy'):
+    class NPMatrixBase(base.MatrixBase):
+        def onalloc(self, basedata, offset):
+            self.basedata, self.offset = basedata, offset
+            self.data = basedata[offset:offset + self.nbytes].view(self.dtype)
+
+            if self._initval is not None:
+                self._set(self._initval)
+
+            del self._initval
+
+        def _get(self):
+            shp = (self.nblocks, self.nrow, self.leaddim)
+            return np.array(self._unpack(self.data.reshape(shp)))
+
+        def _set(self, ary):
+            self.data[:] = np.asarray(self._pack(ary)).reshape(-1)
+
+    class NPMatrix(NPMatrixBase, base.Matrix): pass
+    class NPConstMatrix(NPMatrixBase, base.ConstMatrix): pass
+    class NPMatrixSlice(base.MatrixSlice): pass
+    class NPView(base.View): pass
+    class NPXchgView(base.XchgView): pass
+
+    class NPXchgMatrix(NPMatrix, base.XchgMatrix):
+        def recvreq(self, comm, pid, tag):
+            return comm.recv_init(self, pid, tag)
+
+        def sendreq(self, comm, pid, tag):
+            return comm.send_init(self, pid, tag)
+
+    class NPKernel(base.Kernel):
+        def __init__(self, fn, rtnames=()):
+            super().__init__()
+            self._fn = fn
+            self._rt = {}
+
+            if rtnames:
+                self.rtnames = tuple(rtnames)
+                self.bind = self._bind
+
+        def _bind(self, **kw):
+            self._rt.update(kw)
+
+        def add_to_graph(self, graph, deps):
+            graph.program.append(('kernel', self))
+            return self
+
+        def run(self, *args):
+            with np.errstate(all='ignore'):
+                self._fn(**self._rt)
+
+    def _meta(cls):
+        class Meta(cls):
+            def add_to_graph(self, graph, deps):
+                graph.program.append(('kernel', self))
+                return self
+        return Meta
+
+    ordered_cls = getattr(base, 'OrderedMetaKernel', None) or \
+        base.BaseOrderedMetaKernel
+    unordered_cls = getattr(base, 'UnorderedMetaKernel', None) or \
+        base.BaseUnorderedMetaKernel
+
+    class NPGraph(base.Graph):
+        def __init__(self, backend):
+            self.program = []
+            super().__init__(backend)
+
+        def _add_mpi_req(self, req, deps):
+            super()._add_mpi_req(req, deps)
+            self.program.append(('send' if deps else 'recv', req))
+
+        def run(self, *args):
+            for what, obj in self.program:
+                if what == 'kernel':
+                    obj.run()
+                else:
+                    obj.start()
+
+        def get_wait_times(self):
+            return []
+
+    # -- providers -------------------------------------------------------
+    class BlasProvider:
+        def __init__(self, backend):
+            self.backend = backend
+
+        def mul(self, a, b, out, alpha=1.0, beta=0.0):
+            if a.nrow != out.nrow or a.ncol != b.nrow or b.ncol != out.ncol:
+                raise ValueError('Incompatible matrices for out = a*b')
+
+            A = a.get()
+
+            def run():
+                B, C = _mat3(b), _mat3(out)
+                r = alpha*np.einsum('mk,bkn->bmn', A, B)
+                C[:] = r + beta*C if beta else r
+
+            return NPKernel(run)
+
+        def copy(self, dst, src):
+            if dst.traits != src.traits:
+                raise ValueError('Incompatible matrix types')
+
+            def run():
+                _mat3(dst)[:] = _mat3(src)
+
+            return NPKernel(run)
+
+        def zero(self, m):
+            def run():
+                _mat3(m)[:] = 0
+
+            return NPKernel(run)
+
+        def axnpby(self, *arr, in_scale=(), in_scale_idxs=(), out_scale=()):
+            if any(arr[0].traits != x.traits for x in arr[1:]):
+                raise ValueError('Incompatible matrix types')
+            if in_scale or out_scale:
+                raise NotImplementedError('axnpby scaling not in oracle')
+
+            class AxnpbyKernel(NPKernel):
+                def bind(self, *consts):
+                    self._c = consts
+
+                def run(self, *args):
+                    c = self._c
+                    xs = [_mat3(x) for x in arr]
+                    acc = c[0]*xs[0] if c[0] != 0 else 0
+                    for ci, xi in zip(c[1:], xs[1:]):
+                        acc = acc + ci*xi
+                    xs[0][:] = acc
+
+            return AxnpbyKernel(None)
+
+        def pack(self, xv):
+            v = _ViewRef(xv.view)
+            nr, nc, n = xv.nvrow, xv.nvcol, xv.n
+            xm = xv.xchgmat
+
+            def run():
+                p = _mat3(xm)[0].reshape(nr*nc, n)
+                for r in range(nr):
+                    for c in range(nc):
+                        p[r*nc + c] = v.load(c, r if nr > 1 else None)
+
+            return NPKernel(run)
+
+        def unpack(self, xm):
+            # Received data is consumed in place as an 'mpi' array
+            return base.NullKernel()
+
+    class PointwiseProvider:
+        def __init__(self, backend):
+            self.backend = backend
+            self._mods = {}
+
+        def register(self, mod):
+            name = mod.rsplit('.', 1)[1]
+
+            if self._mods.setdefault(name, mod) != mod:
+                raise RuntimeError(f'Attempt to re-register {name!r} with a '
+                                   'different module')
+
+            impl = _pointwise_impls.get(mod)
+            if impl is not None and not hasattr(self, name):
+                setattr(self, name, lambda *a, **kw: impl(self.backend, *a,
+                                                          **kw))
+
+    class NPBackend(base.BaseBackend):
+        blocks = False
+
+        const_matrix_cls = NPConstMatrix
+        matrix_cls = NPMatrix
+        matrix_slice_cls = NPMatrixSlice
+        view_cls = NPView
+        xchg_matrix_cls = NPXchgMatrix
+        xchg_view_cls = NPXchgView
+        graph_cls = NPGraph
+        ordered_meta_kernel_cls = _meta(ordered_cls)
+        unordered_meta_kernel_cls = _meta(unordered_cls)
+
+        def __init__(self, cfg):
+            super().__init__(cfg)
+
+            self.alignb = cfg.getint('backend-oracle', 'alignb', 64)
+            self.soasz = cfg.getint('backend-oracle', 'soasz', 8)
+            self.csubsz = cfg.getint('backend-oracle', 'csubsz', self.soasz)
+            self.blocks = cfg.getbool('backend-oracle', 'blocks', False)
+
+            self.pointwise = PointwiseProvider(self)
+            self._providers = [BlasProvider(self), self.pointwise]
+
+        def _malloc_impl(self, nbytes):
+            return np.zeros(nbytes, dtype=np.uint8)
+
+        def run_kernels(self, kernels, wait=False):
+            for k in kernels:
+                k.run()
+
+        def run_graph(self, graph, wait=False):
+            graph.run()
+
+        def wait(self):
+            pass
+
+    NPBackend.name = name
+    NPBackend.kernel_cls = NPKernel
+    return NPBackend
+
+
+# -- pointwise kernel restatements (module path -> builder) -----------------
+def _geometry(be, tplargs, npts, smats, rcpdjac, verts, upts, need_rcp):
+    """Returns a callable giving (smats[i][j], rcpdjac) as arrays that
+    broadcast against (nblocks, npts, nchunks, k)."""
+    nd = tplargs['ndims']
+
+    if 'linear' in tplargs['ktype']:
+        x = [upts.get()[:, d].reshape(1, npts, 1, 1) for d in range(nd)]
+
+        def geo():
+            vv = _stacked(verts, nd)          # (nd, nb, nverts, nch, k)
+            V = [[vv[i][:, n:n + 1] for i in range(nd)]
+                 for n in range(tplargs['nverts'])]
+            s, d = ph.calc_smats_detj(tplargs['jac_exprs'], V, x, nd)
+            return s, (1/d if need_rcp else None)
+    else:
+        def geo():
+            sm = _stacked(smats, nd, nlead=nd)   # [i][j] -> (nb,npts,nch,k)
+            s = [[sm[i][j] for j in range(nd)] for i in range(nd)]
+            return s, (_plain(rcpdjac) if need_rcp else None)
+
+    return geo
+
+
+def _tflux_euler(be, tplargs, dims, extrns={}, u=None, f=None, smats=None,
+                 verts=None, upts=None, **kw):
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    geo = _geometry(be, tplargs, dims[0], smats, None, verts, upts, False)
+
+    def run():
+        uu, ff = _stacked(u, nv), _stacked(f, nv, nlead=nd)
+        s, _ = geo()
+        ft, p, v = ph.inviscid_flux(list(uu), nd, nv, c)
+        out = ph.transform_flux(ft, s, nd, nv)
+        for i in range(nd):
+            for j in range(nv):
+                ff[i][j][:] = out[i][j]
+
+    return be.kernel_cls(run)
+
+
+def _tflux_ns(be, tplargs, dims, extrns={}, u=None, f=None, gradu=None,
+              smats=None, rcpdjac=None, verts=None, upts=None,
+              artvisc_vtx=None, **kw):
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    fused = 'fused' in tplargs['ktype']
+    geo = _geometry(be, tplargs, dims[0], smats, rcpdjac, verts, upts, fused)
+
+    if tplargs.get('shock_capturing', 'none') != 'none':
+        raise NotImplementedError('shock capturing is out of scope')
+
+    def run():
+        uu, ff = _stacked(u, nv), _stacked(f, nv, nlead=nd)
+        s, rcp = geo()
+
+        if fused:
+            gg = _stacked(gradu, nv, nlead=nd)
+            g = ph.transform_grad([[gg[i][j] for j in range(nv)]
+                                   for i in range(nd)], s, rcp, nd, nv)
+            for i in range(nd):
+                for j in range(nv):
+                    gg[i][j][:] = g[i][j]
+        else:
+            g = [[ff[i][j].copy() for j in range(nv)] for i in range(nd)]
+
+        ft, p, v = ph.inviscid_flux(list(uu), nd, nv, c)
+        ph.viscous_flux_add(list(uu), g, ft, nd, nv, c, tplargs['visc_corr'])
+        out = ph.transform_flux(ft, s, nd, nv)
+
+        for i in range(nd):
+            for j in range(nv):
+                ff[i][j][:] = out[i][j]
+
+    return be.kernel_cls(run)
+
+
+def _gradcoru(be, tplargs, dims, extrns={}, gradu=None, smats=None,
+              rcpdjac=None, verts=None, upts=None, **kw):
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    geo = _geometry(be, tplargs, dims[0], smats, rcpdjac, verts, upts, True)
+
+    def run():
+        gg = _stacked(gradu, nv, nlead=nd)
+        s, rcp = geo()
+        g = ph.transform_grad([[gg[i][j] for j in range(nv)]
+                               for i in range(nd)], s, rcp, nd, nv)
+        for i in range(nd):
+            for j in range(nv):
+                gg[i][j][:] = g[i][j]
+
+    return be.kernel_cls(run)
+
+
+def _negdivconf(be, tplargs, dims, extrns={}, tdivtconf=None, rcpdjac=None,
+                ploc=None, u=None, **kw):
+    if tplargs['src_macros']:
+        raise NotImplementedError('source terms are out of scope')
+
+    nv = tplargs['nvars']
+
+    def run(t=0.0):
+        tt, r = _stacked(tdivtconf, nv), _plain(rcpdjac)
+        for i in range(nv):
+            tt[i][:] = -r*tt[i]
+
+    return be.kernel_cls(run, rtnames=('t',))
+
+
+def _evalsrcmacros(be, tplargs, dims, extrns={}, ploc=None, u=None, **kw):
+    """baseadvec/kernels/evalsrcmacros.mako: u <- sum of source macros."""
+    if tplargs['src_macros']:
+        raise NotImplementedError('source terms are out of scope')
+
+    def run(t=0.0):
+        _mat3(u)[:] = 0
+
+    return be.kernel_cls(run, rtnames=('t',))
+
+
+def _mpi_rows(xm):
+    return _mat3(xm)[0]
+
+
+def _intcflux_euler(be, tplargs, dims, extrns={}, ul=None, ur=None, nl=None,
+                    **kw):
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    rs = tplargs['rsolver']
+    vl, vr, n = _ViewRef(ul), _ViewRef(ur), list(nl.get())
+
+    def run():
+        l = [vl.load(i) for i in range(nv)]
+        r = [vr.load(i) for i in range(nv)]
+        fn = ph.euler_common_flux(l, r, n, nd, nv, c, rs)
+        for i in range(nv):
+            vl.store(fn[i], i)
+            vr.store(-fn[i], i)
+
+    return be.kernel_cls(run)
+
+
+def _mpicflux_euler(be, tplargs, dims, extrns={}, ul=None, ur=None, nl=None,
+                    **kw):
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    rs = tplargs['rsolver']
+    vl, n = _ViewRef(ul), list(nl.get())
+
+    def run():
+        l = [vl.load(i) for i in range(nv)]
+        r = list(_mpi_rows(ur))
+        fn = ph.euler_common_flux(l, r, n, nd, nv, c, rs)
+        for i in range(nv):
+            vl.store(fn[i], i)
+
+    return be.kernel_cls(run)
+
+
+def _intconu(be, tplargs, dims, extrns={}, ulin=None, urin=None, ulout=None,
+             urout=None, **kw):
+    nv, beta = tplargs['nvars'], tplargs['c']['ldg-beta']
+    li, ri, lo, ro = map(_ViewRef, (ulin, urin, ulout, urout))
+
+    def run():
+        l = [li.load(i) for i in range(nv)]
+        r = [ri.load(i) for i in range(nv)]
+        ol, orr = ph.ldg_common_solution(l, r, beta)
+        for i in range(nv):
+            if ol is not None:
+                lo.store(ol[i], i)
+            if orr is not None:
+                ro.store(orr[i], i)
+
+    return be.kernel_cls(run)
+
+
+def _mpiconu(be, tplargs, dims, extrns={}, ulin=None, urin=None, ulout=None,
+             **kw):
+    nv, beta = tplargs['nvars'], tplargs['c']['ldg-beta']
+    li, lo = _ViewRef(ulin), _ViewRef(ulout)
+
+    def run():
+        l = [li.load(i) for i in range(nv)]
+        r = list(_mpi_rows(urin))
+
+        # mpiconu.mako:9-18: beta = -1/2 keeps our own trace
+        if beta == -0.5:
+            out = l
+        elif beta == 0.5:
+            out = r
+        else:
+            out = [b*(0.5 + beta) + a*(0.5 - beta) for a, b in zip(l, r)]
+
+        for i in range(nv):
+            lo.store(out[i], i)
+
+    return be.kernel_cls(run)
+
+
+def _cflux_ns(mpi):
+    def build(be, tplargs, dims, extrns={}, ul=None, ur=None, gradul=None,
+              gradur=None, artvisc=None, nl=None, **kw):
+        nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+        rs, vc = tplargs['rsolver'], tplargs['visc_corr']
+        beta = c['ldg-beta']
+        vl, gl, n = _ViewRef(ul), _ViewRef(gradul), list(nl.get())
+
+        if not mpi:
+            vr, gr = _ViewRef(ur), _ViewRef(gradur)
+
+        def run():
+            l = [vl.load(i) for i in range(nv)]
+            gL = gR = None
+
+            if mpi:
+                r = list(_mpi_rows(ur))
+                if beta != 0.5:
+                    rows = _mpi_rows(gradur)
+                    gR = [[rows[nv*d + j] for j in range(nv)]
+                          for d in range(nd)]
+            else:
+                r = [vr.load(i) for i in range(nv)]
+                if beta != 0.5:
+                    gR = [[gr.load(j, d) for j in range(nv)]
+                          for d in range(nd)]
+
+            if beta != -0.5:
+                gL = [[gl.load(j, d) for j in range(nv)] for d in range(nd)]
+
+            fn = ph.ns_common_flux(l, r, gL, gR, n, nd, nv, c, rs, vc)
+
+            for i in range(nv):
+                vl.store(fn[i], i)
+                if not mpi:
+                    vr.store(-fn[i], i)
+
+        return be.kernel_cls(run)
+
+    return build
+
+
+_pointwise_impls = {
+    'pyfr.solvers.euler.kernels.tflux': _tflux_euler,
+    'pyfr.solvers.navstokes.kernels.tflux': _tflux_ns,
+    'pyfr.solvers.baseadvecdiff.kernels.gradcoru': _gradcoru,
+    'pyfr.solvers.baseadvec.kernels.negdivconf': _negdivconf,
+    'pyfr.solvers.baseadvec.kernels.evalsrcmacros': _evalsrcmacros,
+    'pyfr.solvers.euler.kernels.intcflux': _intcflux_euler,
+    'pyfr.solvers.euler.kernels.mpicflux': _mpicflux_euler,
+    'pyfr.solvers.navstokes.kernels.intconu': _intconu,
+    'pyfr.solvers.navstokes.kernels.mpiconu': _mpiconu,
+    'pyfr.solvers.navstokes.kernels.intcflux': _cflux_ns(False),
+    'pyfr.solvers.navstokes.kernels.mpicflux': _cflux_ns(True),
+}
+
+
+class LocalComm:
+    """All ranks live in one process; a send parks a copy of the buffer in
+    a shared mailbox and the matching receive (started at the top of the
+    same graph stage on the peer) collects it when the stage is closed by
+    ``deliver()``.  Drives multi-partition oracle runs without MPI."""
+
+    def __init__(self, rank, size, world=None):
+        self.rank, self.size = rank, size
+        self.world = world if world is not None else {'box': {}, 'recv': []}
+
+    def peer(self, rank):
+        return LocalComm(rank, self.size, self.world)
+
+    def send_init(self, xm, pid, tag):
+        comm = self
+
+        class Send:
+            def start(self):
+                comm.world['box'][comm.rank, pid, tag] = _mat3(xm).copy()
+
+        return Send()
+
+    def recv_init(self, xm, pid, tag):
+        comm = self
+
+        class Recv:
+            def start(self):
+                comm.world['recv'].append(((pid, comm.rank, tag), xm))
+
+        return Recv()
+
+    def deliver(self):
+        for key, xm in self.world['recv']:
+            _mat3(xm)[:] = self.world['box'].pop(key)
+
+        self.world['recv'].clear()

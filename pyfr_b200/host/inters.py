@@ -1,0 +1,261 @@
+"""Interface (interior / inter-partition) kernel declarations.
+
+Host-side counterpart of ``pyfr/solvers/base/inters.py:6-119``,
+``pyfr/solvers/baseadvec/inters.py:9-58``,
+``pyfr/solvers/baseadvecdiff/inters.py:7-66``,
+``pyfr/solvers/euler/inters.py:12-49`` and
+``pyfr/solvers/navstokes/inters.py:9-67``: builds the gather/scatter views
+over the element buffers for each side of each interface, the scaled
+normals, the memory-order permutation of interior interfaces, and declares
+the ``intconu/intcflux/mpiconu/mpicflux`` kernels with the reference's
+keyword arguments.  Boundary conditions are not part of this round's path.
+"""
+
+import itertools as it
+
+import numpy as np
+
+
+def _side_arrays(side, elemap, getter):
+    """Evaluate ``elemap[etype].<getter>(eidxs, fidx)`` for every face
+    group of one interface side and lay the per-flux-point results out in
+    interface order."""
+    nfp = np.empty(len(side), dtype=np.int64)
+    chunks = []
+
+    for etype, fidx, eidxs, where in side.foreach():
+        nfp[where] = elemap[etype].nfacefpts[fidx]
+        chunks.append((where, getattr(elemap[etype], getter)(eidxs, fidx)))
+
+    start = np.concatenate(([0], np.cumsum(nfp)))
+    return start, nfp, chunks
+
+
+def side_view_maps(side, elemap, getter):
+    """(matmap, rmap, cmap, rstridemap) arrays for a view over one side."""
+    start, nfp, chunks = _side_arrays(side, elemap, getter)
+    n = int(start[-1])
+
+    matmap = np.empty(n, dtype=np.int64)
+    rmap = np.empty(n, dtype=np.int64)
+    cmap = np.empty(n, dtype=np.int64)
+    rsmap = np.ones(n, dtype=np.int64)
+
+    for etype, fidx, eidxs, where in side.foreach():
+        mid, rows, rstride = getattr(elemap[etype], getter)(eidxs, fidx)
+        k = rows.shape[1]
+        dst = (start[where][:, None] + np.arange(k)).ravel()
+
+        matmap[dst] = mid
+        rmap[dst] = rows.ravel()
+        cmap[dst] = np.repeat(eidxs, k)
+        if rstride is not None:
+            rsmap[dst] = rstride
+
+    return matmap, rmap, cmap, rsmap
+
+
+def side_const(side, elemap, getter, ndims):
+    start, nfp, chunks = _side_arrays(side, elemap, getter)
+    out = np.empty((int(start[-1]), ndims))
+
+    for where, vals in chunks:
+        k = len(vals) // max(len(where), 1)
+        dst = (start[where][:, None] + np.arange(k)).ravel()
+        out[dst] = vals
+
+    return out
+
+
+class BaseInters:
+    def __init__(self, be, lhs, elemap, cfg):
+        self._be = be
+        self.elemap = elemap
+        self.cfg = cfg
+        self.lhs = lhs
+
+        e0 = next(iter(elemap.values()))
+        self.ndims, self.nvars = e0.ndims, e0.nvars
+
+        self.ninters = len(lhs)
+        self.ninterfpts = sum(elemap[et].nfacefpts[fi]*len(ei)
+                              for et, fi, ei in lhs.items())
+
+        self._perm = Ellipsis
+        self.c = cfg.items_as('constants', float)
+        self.kernels = {}
+        self.mpireqs = {}
+
+    def _view(self, side, getter, vshape, xchg=False):
+        m, r, c, rs = (a[self._perm]
+                       for a in side_view_maps(side, self.elemap, getter))
+        mk = self._be.xchg_view if xchg else self._be.view
+
+        return mk(m, r, c, rs, vshape=vshape)
+
+    def _scal_view(self, side, getter, **kw):
+        return self._view(side, getter, (self.nvars,), **kw)
+
+    def _vect_view(self, side, getter, **kw):
+        return self._view(side, getter, (self.ndims, self.nvars), **kw)
+
+    def _memory_order_perm(self, side):
+        # Order interface points by the address of their scal_fpts entry
+        m, r, c, _ = side_view_maps(side, self.elemap,
+                                    'get_scal_fpts_for_inters')
+        return np.argsort(self._be.view(m, r, c, vshape=()).mapping.get()[0])
+
+    def _pnorms(self, side):
+        pn = side_const(side, self.elemap, 'get_pnorms_for_inters',
+                        self.ndims)[self._perm]
+        return self._be.const_matrix(np.atleast_2d(pn.T))
+
+    def _rsolver_tplargs(self):
+        be, cfg = self._be, self.cfg
+        return dict(
+            ndims=self.ndims, nvars=self.nvars, c=self.c,
+            rsolver=cfg.get('solver-interfaces', 'riemann-solver'),
+            p_min=cfg.getfloat('solver-interfaces', 'p-min',
+                               5*be.fpdtype_eps)
+        )
+
+
+class IntInters(BaseInters):
+    name = 'internal'
+
+    def __init__(self, be, lhs, rhs, elemap, cfg):
+        super().__init__(be, lhs, elemap, cfg)
+        self.rhs = rhs
+
+        self._perm = self._memory_order_perm(self._perm_side())
+        self._pnorm_lhs = self._pnorms(lhs)
+
+        g = 'get_scal_fpts_for_inters'
+        self.scal_lhs = self._scal_view(lhs, g)
+        self.scal_rhs = self._scal_view(rhs, g)
+
+    def _perm_side(self):
+        return self.lhs
+
+
+class MPIInters(BaseInters):
+    def __init__(self, be, lhs, rhsrank, rank, elemap, cfg):
+        super().__init__(be, lhs, elemap, cfg)
+        self.rhsrank, self.rank = rhsrank, rank
+        self.name = f'p{rhsrank}'
+        self._tags = it.count()
+
+        self._pnorm_lhs = self._pnorms(lhs)
+
+        self.scal_lhs = self._scal_view(lhs, 'get_scal_fpts_for_inters',
+                                        xchg=True)
+        self.scal_rhs = be.xchg_matrix_for_view(self.scal_lhs)
+
+    def next_mpi_tag(self):
+        return next(self._tags)
+
+
+class EulerIntInters(IntInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be = self._be
+        be.pointwise.register('pyfr.solvers.euler.kernels.intcflux')
+        tplargs = self._rsolver_tplargs()
+
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'intcflux', tplargs=tplargs, dims=[self.ninterfpts],
+            ul=self.scal_lhs, ur=self.scal_rhs, nl=self._pnorm_lhs
+        )
+
+
+class EulerMPIInters(MPIInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be = self._be
+        be.pointwise.register('pyfr.solvers.euler.kernels.mpicflux')
+        tplargs = self._rsolver_tplargs()
+
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'mpicflux', tplargs, dims=[self.ninterfpts],
+            ul=self.scal_lhs, ur=self.scal_rhs, nl=self._pnorm_lhs
+        )
+
+
+def _ns_tplargs(inter):
+    cfg = inter.cfg
+    return inter._rsolver_tplargs() | dict(
+        visc_corr=cfg.get('solver', 'viscosity-correction', 'none'),
+        shock_capturing=cfg.get('solver', 'shock-capturing', 'none')
+    )
+
+
+class NavierStokesIntInters(IntInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be, lhs, rhs = self._be, self.lhs, self.rhs
+
+        self._vect_lhs = self._vect_view(lhs, 'get_vect_fpts_for_inters')
+        self._vect_rhs = self._vect_view(rhs, 'get_vect_fpts_for_inters')
+        self._comm_lhs = self._scal_view(lhs, 'get_comm_fpts_for_inters')
+        self._comm_rhs = self._scal_view(rhs, 'get_comm_fpts_for_inters')
+
+        self.c |= self.cfg.items_as('solver-interfaces', float)
+        tplargs = _ns_tplargs(self)
+
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.intconu')
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.intcflux')
+
+        self.kernels['con_u'] = lambda: be.kernel(
+            'intconu', tplargs=tplargs, dims=[self.ninterfpts],
+            ulin=self.scal_lhs, urin=self.scal_rhs,
+            ulout=self._comm_lhs, urout=self._comm_rhs
+        )
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'intcflux', tplargs=tplargs, dims=[self.ninterfpts],
+            ul=self.scal_lhs, ur=self.scal_rhs,
+            gradul=self._vect_lhs, gradur=self._vect_rhs,
+            artvisc=None, nl=self._pnorm_lhs
+        )
+
+    def _perm_side(self):
+        beta = self.cfg.getfloat('solver-interfaces', 'ldg-beta')
+        return self.lhs if beta != -0.5 else self.rhs
+
+
+class NavierStokesMPIInters(MPIInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be, lhs, rank, rhsrank = self._be, self.lhs, self.rank, self.rhsrank
+
+        self._vect_lhs = self._vect_view(lhs, 'get_vect_fpts_for_inters',
+                                         xchg=True)
+        self._vect_rhs = be.xchg_matrix_for_view(self._vect_lhs)
+        self._comm_lhs = self._scal_view(lhs, 'get_comm_fpts_for_inters',
+                                         xchg=True)
+        self._comm_rhs = be.xchg_matrix_for_view(self._comm_lhs)
+
+        self.c |= self.cfg.items_as('solver-interfaces', float)
+
+        # One side of every partition boundary negates beta so the LDG
+        # switch is consistent across it (reference baseadvecdiff
+        # inters.py:47-58)
+        if (rank + rhsrank) % 2:
+            self.c['ldg-beta'] *= 1.0 if rank > rhsrank else -1.0
+        else:
+            self.c['ldg-beta'] *= 1.0 if rhsrank > rank else -1.0
+
+        tplargs = _ns_tplargs(self)
+
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.mpiconu')
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.mpicflux')
+
+        self.kernels['con_u'] = lambda: be.kernel(
+            'mpiconu', tplargs=tplargs, dims=[self.ninterfpts],
+            ulin=self.scal_lhs, urin=self.scal_rhs, ulout=self._comm_lhs
+        )
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'mpicflux', tplargs=tplargs, dims=[self.ninterfpts],
+            ul=self.scal_lhs, ur=self.scal_rhs,
+            gradul=self._vect_lhs, gradur=self._vect_rhs,
+            artvisc=None, nl=self._pnorm_lhs
+        )
