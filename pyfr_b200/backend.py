@@ -1,0 +1,111 @@
+"""The ``b200`` backend: PyFR's backend contract on one NVIDIA B200.
+
+Plays the role of ``CUDABackend`` (``pyfr/backends/cuda/base.py:9-144``)
+with a different design underneath: blocked AoSoA storage
+(``blocks = True``, so one element block is a contiguous tile that a single
+TMA bulk copy moves), operator constants baked into generated sm_100a
+kernels, CUDA-graph replay of each RHS graph and NCCL for the halo
+exchange.  Configuration keys (section ``[backend-b200]``): ``device-id``
+(``local-rank`` or an index), ``n-soa`` (SoA width, default 128 bytes worth
+of scalars), ``n-csub`` (columns per block, multiple of ``n-soa``),
+``graphs`` (replay through CUDA graphs, default on).
+"""
+
+import os
+
+import numpy as np
+
+from pyfr_b200 import base, providers, types
+from pyfr_b200.compiler import KernelCompiler
+from pyfr_b200.lib import load_runtime
+
+
+class B200Backend(base.BaseBackend):
+    name = 'b200'
+    blocks = True
+
+    const_matrix_cls = types.B200ConstMatrix
+    matrix_cls = types.B200Matrix
+    matrix_slice_cls = types.B200MatrixSlice
+    view_cls = types.B200View
+    xchg_matrix_cls = types.B200XchgMatrix
+    xchg_view_cls = types.B200XchgView
+    graph_cls = types.B200Graph
+    ordered_meta_kernel_cls = providers.B200OrderedMetaKernel
+    unordered_meta_kernel_cls = providers.B200UnorderedMetaKernel
+
+    def __init__(self, cfg, dry=False, comm=None):
+        super().__init__(cfg)
+        sect = 'backend-b200'
+
+        devid = cfg.get(sect, 'device-id', 'local-rank')
+        if devid == 'local-rank':
+            devid = int(os.environ.get('LOCAL_RANK', 0))
+
+        self.rt = rt = load_runtime(int(devid), dry=dry)
+        info = rt.device_info()
+
+        if not dry and info['cc'][0] != 10:
+            raise RuntimeError('The b200 backend targets sm_100a only; found '
+                               f'compute capability {info["cc"]}')
+
+        self.sm_count = info['sm_count']
+        self.smem_budget = min(info['smem_optin'], 227*1024) - 8*1024
+
+        # Storage layout: 128-byte SoA rows, one SoA group per block
+        isz = np.dtype(self.fpdtype).itemsize
+        self.alignb = 256
+        self.soasz = cfg.getint(sect, 'n-soa', 128 // isz)
+        self.csubsz = cfg.getint(sect, 'n-csub', self.soasz)
+        if self.csubsz % self.soasz:
+            raise ValueError('n-csub must be a multiple of n-soa')
+
+        self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
+        self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
+
+        self.compiler = KernelCompiler(rt)
+        self.nlaunches = 0
+
+        # Compute stream, communication stream and fork/join events
+        self.stream = rt.new_ptr(rt.stream_create)
+        self.comm_stream = rt.new_ptr(rt.stream_create)
+        self.fork_event = rt.new_ptr(rt.event_create)
+        self.join_event = rt.new_ptr(rt.event_create)
+
+        self.comm = comm
+        self.pointwise = providers.PointwiseProvider(self)
+        self._providers = [providers.OperatorProvider(self),
+                           providers.BlasExtProvider(self),
+                           providers.PackingProvider(self), self.pointwise]
+
+    def _malloc_impl(self, nbytes):
+        return types.DevAlloc(self.rt, nbytes)
+
+    def run_kernels(self, kernels, wait=False):
+        for k in kernels:
+            k.run(self.stream)
+
+        if wait:
+            self.wait()
+
+    def run_graph(self, graph, wait=False):
+        graph.run(self.stream)
+
+        if wait:
+            self.wait()
+
+    def wait(self):
+        self.rt.stream_sync(self.stream)
+
+    def exchange(self, reqs, stream):
+        """Issue all sends/receives of one graph as a single NCCL group."""
+        if self.comm is None:
+            raise RuntimeError('Inter-partition exchange requested but the '
+                               'backend has no communicator')
+
+        self.comm.exchange(reqs, stream)
+
+    def memory_info(self):
+        info = self.rt.device_info()
+        return base.MemoryInfo(self._mem_now(), self._mem_peak,
+                               info['free_mem'], info['total_mem'])

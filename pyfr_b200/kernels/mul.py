@@ -1,0 +1,257 @@
+"""Generator for the constant-operator multiply kernels.
+
+Replaces the reference's GiMMiK / cuBLASLt ``mul`` providers
+(``pyfr/backends/cuda/gimmik.py:23-121``, ``cublaslt.py:169-280``):
+``out = alpha*A @ b + beta*out`` with ``A`` a constant ``M x K`` operator
+(``M0``, ``M4 - M6*M0``, ``M6``, ``M1 - M3*M2``, ``M3``) and ``b``/``out``
+blocked AoSoA matrices whose block ``j`` holds rows of ``LD`` columns
+(``LD = nvars*csubsz``).
+
+Design (sm_100a):
+
+* ``A`` is baked into the instruction stream: only its non-zeros generate
+  code and each becomes one DFMA/FFMA with an immediate-constant operand.
+* persistent CTAs (one per SM) walk the element blocks; a block's input
+  rows are contiguous in HBM, so the whole ``K x LD`` tile is fetched with
+  a single TMA bulk copy (``cp.async.bulk``) into shared memory, double
+  buffered and tracked with mbarriers so the fetch of block ``j+1``
+  overlaps the arithmetic on block ``j``.
+* a thread owns one column of the block and a contiguous group of output
+  rows; shared-memory reads are conflict free (adjacent threads, adjacent
+  words) and every output row is written as whole 128-byte segments.
+* operators whose tile does not fit (``K = ndims*nupts``) are split into
+  row chunks that stream through the same pipeline, with the partial
+  sums held in registers.
+
+Algorithmic HBM traffic per block is ``(K + M [+ M if beta != 0])*LD``
+words: each input is read once, each output written once.
+"""
+
+import numpy as np
+
+from pyfr_b200.kernels import physics as ph
+
+_pipeline_src = r'''
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned n)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(n));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar,
+                                               unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar,
+                                          unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// One TMA bulk copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src,
+                                            unsigned bytes,
+                                            unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+'''
+
+
+def plan_chunks(K, LD, itemsize, smem_budget, hint=None):
+    """Split the K input rows into equal chunks whose double-buffered tile
+    fits the shared-memory budget.  ``hint`` (e.g. nupts) is preferred as
+    the chunk length when it divides K."""
+    per_stage = smem_budget // 2
+    maxrows = max(1, per_stage // (LD*itemsize))
+
+    if K <= maxrows:
+        return [(0, K)]
+
+    cands = [d for d in range(1, K + 1) if K % d == 0 and d <= maxrows]
+    rows = max(cands)
+    if hint and K % hint == 0 and hint <= maxrows:
+        rows = hint
+
+    return [(i, i + rows) for i in range(0, K, rows)]
+
+
+def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
+               chunk_hint=None):
+    """CUDA source for ``out = alpha*A@b + beta*out``.
+
+    Returns (source, name, launch meta dict)."""
+    A = alpha*np.asarray(A, dtype=float)
+    M, K = A.shape
+    isz = np.dtype(be.fpdtype).itemsize
+
+    if (LD*isz) % 16:
+        raise ValueError('Row size must be a multiple of 16 bytes')
+
+    chunks = plan_chunks(K, LD, isz, smem_budget, chunk_hint)
+    nchunks = len(chunks)
+    crows = chunks[0][1] - chunks[0][0]
+
+    wpr = -(-LD // 32)                       # warps covering one row
+    R = max(1, min(rowgroups, 32 // wpr, M))
+    nthreads = 32*wpr*R
+
+    # Output rows of each row group
+    bounds = np.linspace(0, M, R + 1).astype(int)
+    groups = [range(bounds[i], bounds[i + 1]) for i in range(R)]
+    maxrows = max(len(g) for g in groups)
+
+    def row_expr(m, k0, k1, acc=None):
+        terms = [(k, A[m, k]) for k in range(k0, k1) if A[m, k] != 0]
+        expr = acc
+
+        for k, a in terms:
+            t = f'sm[{(k - k0)*LD} + col]'
+            if expr is None:
+                expr = f'{ph.fpconst(a)}*{t}'
+            else:
+                expr = f'fma({ph.fpconst(a)}, {t}, {expr})'
+
+        return expr
+
+    def store(m, val):
+        ix = f'ob + {m*LD} + col'
+        if beta == 0:
+            return f'out[{ix}] = {val};'
+        elif beta == 1:
+            return f'out[{ix}] += {val};'
+        else:
+            return f'out[{ix}] = fma({ph.fpconst(beta)}, out[{ix}], {val});'
+
+    cases = []
+    for ci, (k0, k1) in enumerate(chunks):
+        first, last = ci == 0, ci == nchunks - 1
+        body = []
+
+        for rg, rows in enumerate(groups):
+            lines = []
+            for j, m in enumerate(rows):
+                if nchunks == 1:
+                    e = row_expr(m, k0, k1) or 'FP(0.0)'
+                    lines.append(store(m, e))
+                else:
+                    e = row_expr(m, k0, k1, None if first else f'acc[{j}]')
+                    if e is None:
+                        e = 'FP(0.0)'
+                    if last:
+                        lines.append(store(m, e))
+                    elif e != f'acc[{j}]':
+                        lines.append(f'acc[{j}] = {e};')
+
+            body.append(f'            case {rg}:\n                ' +
+                        '\n                '.join(lines) +
+                        '\n                break;')
+
+        cases.append(f'        case {ci}:\n            switch (rg)\n'
+                     '            {\n' + '\n'.join(body) +
+                     '\n            }\n            break;')
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz)}
+#define LD {LD}
+#define NCHUNKS {nchunks}
+#define CROWS {crows}
+#define TILE (CROWS*LD)
+#define NTHREADS {nthreads}
+{_pipeline_src}
+
+// out[{M} x LD] = A[{M} x {K}] @ b[{K} x LD] per element block;
+// {int(np.count_nonzero(A))} non-zeros, {nchunks} chunk(s) of {crows} rows
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
+      fpdtype_t* __restrict__ out, long long out_bsz)
+{{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    fpdtype_t *tiles = reinterpret_cast<fpdtype_t *>(smem_raw);
+    unsigned long long *full =
+        reinterpret_cast<unsigned long long *>(tiles + 2*TILE);
+
+    const int tid = threadIdx.x;
+    const int col = tid % {32*wpr}, rg = tid / {32*wpr};
+    const bool active = col < LD;
+
+    // Work items: (block, chunk) pairs owned by this CTA, in order
+    const long long myblocks = (nblocks - (long long) blockIdx.x
+                                + gridDim.x - 1) / gridDim.x;
+    const long long nitems = myblocks*NCHUNKS;
+
+    if (tid == 0)
+    {{
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    __syncthreads();
+
+    auto issue = [&](long long item)
+    {{
+        const long long blk = blockIdx.x + (item / NCHUNKS)*gridDim.x;
+        const int chunk = (int) (item % NCHUNKS), st = (int) (item & 1);
+        const fpdtype_t *src = b + blk*b_bsz + (long long) chunk*TILE;
+
+        mbar_expect_tx(&full[st], TILE*sizeof(fpdtype_t));
+        tma_load_1d(tiles + st*TILE, src, TILE*sizeof(fpdtype_t), &full[st]);
+    }};
+
+    if (tid == 0 && nitems > 0)
+        issue(0);
+
+    fpdtype_t acc[{maxrows if nchunks > 1 else 1}];
+
+    for (long long item = 0; item < nitems; item++)
+    {{
+        const int st = (int) (item & 1), chunk = (int) (item % NCHUNKS);
+        const long long blk = blockIdx.x + (item / NCHUNKS)*gridDim.x;
+
+        // Prefetch the next tile into the buffer released last iteration
+        if (tid == 0 && item + 1 < nitems)
+            issue(item + 1);
+
+        mbar_wait(&full[st], (unsigned) ((item >> 1) & 1));
+
+        const fpdtype_t *sm = tiles + st*TILE;
+        const long long ob = blk*out_bsz;
+
+        if (active)
+        {{
+        switch (chunk)
+        {{
+{chr(10).join(cases)}
+        }}
+        }}
+
+        __syncthreads();
+    }}
+}}
+'''
+
+    meta = dict(nthreads=nthreads,
+                smem=2*crows*LD*isz + 16, nnz=int(np.count_nonzero(A)),
+                nchunks=nchunks, crows=crows, M=M, K=K)
+
+    return src, 'opmul', meta

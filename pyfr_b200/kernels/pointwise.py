@@ -1,0 +1,218 @@
+"""CUDA source for the element-local pointwise kernels.
+
+``tflux`` (Euler: ``pyfr/solvers/euler/kernels/tflux.mako``; Navier-Stokes:
+``pyfr/solvers/navstokes/kernels/tflux.mako``), ``gradcoru``
+(``pyfr/solvers/baseadvecdiff/kernels/gradcoru.mako``) and ``negdivconf``
+(``pyfr/solvers/baseadvec/kernels/negdivconf.mako``).
+
+Work decomposition (blocked AoSoA, one block = ``C_SUB`` elements): a
+thread owns one (solution point, element) pair; consecutive threads walk
+the ``C_SUB`` elements of a row and then move to the next point, so every
+load/store instruction of a warp touches whole 128-byte row segments.  All
+``NVARS`` (and ``NDIMS x NVARS``) values of the point live in registers.
+Grids are sized in whole blocks; one launch covers every element of the
+region.
+"""
+
+from pyfr_b200.kernels import physics as ph
+
+# Thread <-> (block, point, element-in-block) decomposition shared by the
+# 2-D kernels; returns early for the padding columns of the last block
+_index_src = r'''
+    const long long gid = (long long) blockIdx.x*blockDim.x + threadIdx.x;
+    const int e = (int) (gid % C_SUB);
+    const int p = (int) ((gid / C_SUB) % NPTS);
+    const long long blk = gid / ((long long) C_SUB*NPTS);
+
+    if (blk*C_SUB + e >= neles)
+        return;
+'''
+
+_geom_linear_src = r'''
+    // Metric terms of a linear element, rebuilt from its vertices
+    fpdtype_t V[NVERTS][NDIMS], x[NDIMS], s[NDIMS][NDIMS], djac;
+    UNROLL for (int n = 0; n < NVERTS; n++)
+        UNROLL for (int i = 0; i < NDIMS; i++)
+            V[n][i] = __ldg(verts + blk*verts_bsz + n*(NDIMS*C_SUB)
+                            + COFF(e, i, NDIMS));
+    UNROLL for (int i = 0; i < NDIMS; i++)
+        x[i] = c_pts[p][i];
+
+    calc_smats_detj(V, x, s, djac);
+    const fpdtype_t rcpdjac_v = FP(1.0)/djac;
+    (void) rcpdjac_v;
+'''
+
+_geom_curved_src = r'''
+    // Stored metric terms of a curved element
+    fpdtype_t s[NDIMS][NDIMS];
+    UNROLL for (int i = 0; i < NDIMS; i++)
+        UNROLL for (int j = 0; j < NDIMS; j++)
+            s[i][j] = __ldg(smats + blk*smats_bsz
+                            + (long long) (i*NPTS + p)*(NDIMS*C_SUB)
+                            + COFF(e, j, NDIMS));
+#ifdef NEED_RCPDJAC
+    const fpdtype_t rcpdjac_v = __ldg(rcpdjac + blk*rcpdjac_bsz + p*C_SUB + e);
+#endif
+'''
+
+
+def _pts_table(pts):
+    rows = ', '.join('{' + ', '.join(ph.fpconst(v) for v in row) + '}'
+                     for row in pts)
+    return (f'__constant__ fpdtype_t c_pts[{len(pts)}][{len(pts[0])}] = '
+            f'{{{rows}}};\n')
+
+
+def _geom(tplargs, pts):
+    if 'linear' in tplargs['ktype']:
+        src = (_pts_table(pts) +
+               ph.linear_smats_src(tplargs['ndims'], tplargs['nverts'],
+                                   tplargs['jac_exprs']))
+        args = ['const fpdtype_t* __restrict__ verts', 'long long verts_bsz']
+        return src, args, _geom_linear_src
+    else:
+        args = ['const fpdtype_t* __restrict__ smats', 'long long smats_bsz',
+                'const fpdtype_t* __restrict__ rcpdjac',
+                'long long rcpdjac_bsz']
+        return '', args, _geom_curved_src
+
+
+def tflux_source(be, tplargs, npts, pts, viscous):
+    """Returns (source, kernel name, ordered argument names)."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    fused = 'fused' in tplargs['ktype']
+
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', npts),
+            ('NVERTS', tplargs.get('nverts', 0))]
+    defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
+                               viscous)
+    if fused:
+        defs.append(('NEED_RCPDJAC', 1))
+
+    gsrc, gargs, gbody = _geom(tplargs, pts)
+
+    args = ['int neles', 'const fpdtype_t* __restrict__ u', 'long long u_bsz',
+            'fpdtype_t* __restrict__ f', 'long long f_bsz']
+    if fused:
+        args += ['fpdtype_t* __restrict__ gradu', 'long long gradu_bsz']
+    args += gargs
+
+    if viscous and fused:
+        load_grad = '''
+    // Corrected transformed gradient -> physical gradient, written back
+    fpdtype_t g[NDIMS][NVARS];
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            g[d][v] = gradu[blk*gradu_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)];
+
+    transform_grad(g, s, rcpdjac_v);
+
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            gradu[blk*gradu_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)] = g[d][v];
+'''
+    elif viscous:
+        load_grad = '''
+    // The flux buffer holds the physical gradient on entry
+    fpdtype_t g[NDIMS][NVARS];
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            g[d][v] = f[blk*f_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)];
+'''
+    else:
+        load_grad = ''
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+#define LD (NVARS*C_SUB)
+{ph.flux_src}
+{ph.visc_src if viscous else ''}
+{ph.geom_src}
+{gsrc}
+
+extern "C" __global__ void __launch_bounds__(128)
+tflux({', '.join(args)})
+{{
+{_index_src}
+{gbody}
+
+    fpdtype_t us[NVARS];
+    UNROLL for (int v = 0; v < NVARS; v++)
+        us[v] = u[blk*u_bsz + (long long) p*LD + COFF(e, v, NVARS)];
+{load_grad}
+    // Physical flux F = Fi (+ Fv), then its contravariant transform
+    fpdtype_t ft[NDIMS][NVARS], fo[NDIMS][NVARS], pr, vel[NDIMS];
+    inviscid_flux(us, ft, pr, vel);
+    {'viscous_flux_add(us, g, ft);' if viscous else ''}
+    transform_flux(ft, s, fo);
+
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            f[blk*f_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)] = fo[d][v];
+}}
+'''
+    return src, 'tflux', [a.split()[-1].lstrip('*') for a in args]
+
+
+def gradcoru_source(be, tplargs, npts, pts):
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', npts),
+            ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1)]
+
+    gsrc, gargs, gbody = _geom(tplargs, pts)
+    args = ['int neles', 'fpdtype_t* __restrict__ gradu',
+            'long long gradu_bsz'] + gargs
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+#define LD (NVARS*C_SUB)
+{ph.geom_src}
+{gsrc}
+
+extern "C" __global__ void __launch_bounds__(128)
+gradcoru({', '.join(args)})
+{{
+{_index_src}
+{gbody}
+
+    fpdtype_t g[NDIMS][NVARS];
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            g[d][v] = gradu[blk*gradu_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)];
+
+    transform_grad(g, s, rcpdjac_v);
+
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        UNROLL for (int v = 0; v < NVARS; v++)
+            gradu[blk*gradu_bsz + (long long) (d*NPTS + p)*LD + COFF(e, v, NVARS)] = g[d][v];
+}}
+'''
+    return src, 'gradcoru', [a.split()[-1].lstrip('*') for a in args]
+
+
+def negdivconf_source(be, tplargs, npts):
+    defs = [('NDIMS', tplargs['ndims']), ('NVARS', tplargs['nvars']),
+            ('NPTS', npts)]
+    args = ['int neles', 'fpdtype_t* __restrict__ tdivtconf',
+            'long long tdivtconf_bsz', 'const fpdtype_t* __restrict__ rcpdjac',
+            'long long rcpdjac_bsz']
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+#define LD (NVARS*C_SUB)
+
+extern "C" __global__ void __launch_bounds__(128)
+negdivconf({', '.join(args)})
+{{
+{_index_src}
+    const fpdtype_t r = -__ldg(rcpdjac + blk*rcpdjac_bsz + p*C_SUB + e);
+
+    UNROLL for (int v = 0; v < NVARS; v++)
+    {{
+        const long long ix = blk*tdivtconf_bsz + (long long) p*LD + COFF(e, v, NVARS);
+        tdivtconf[ix] = r*tdivtconf[ix];
+    }}
+}}
+'''
+    return src, 'negdivconf', [a.split()[-1].lstrip('*') for a in args]

@@ -1,0 +1,86 @@
+"""GPU parity: the B200 backend against the NumPy oracle on identical
+inputs, through the backend API (every launch goes through the C ABI)."""
+
+import numpy as np
+import pytest
+
+from pyfr_b200 import cases
+from pyfr_b200.host.system import get_system
+
+from util import oracle_rhs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# fp64 per-point RHS tolerance stated by BASELINE.json's north_star,
+# normalised by the field's infinity norm
+TOL64 = 1e-12
+
+
+def b200_rhs(case, n, **kw):
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box = cases.make(case, n, **kw)
+    be = B200Backend(cfg)
+    sysm = get_system(be, box.local_mesh(), cfg, 2)
+    sysm.rhs(0.0, 0, 1)
+    be.wait()
+
+    return sysm, sysm.ele_scal_upts(1)[0]
+
+
+@pytest.mark.parametrize('kw', [
+    dict(order=2), dict(order=2, rsolver='hllc'), dict(order=2, beta=0.0),
+    dict(order=2, beta=-0.5), dict(order=3, rsolver='hllc'), dict(order=4),
+    dict(order=4, rsolver='hllc')
+], ids=str)
+def test_tgv_rhs_matches_oracle(built, kw):
+    n = (5, 4, 3)
+    _, ref = oracle_rhs('tgv', n, warp=0.1, **kw)
+    _, out = b200_rhs('tgv', n, warp=0.1, **kw)
+
+    assert out.shape == ref[0].shape
+    assert rel_err(out, ref[0]) < TOL64
+
+
+@pytest.mark.parametrize('kw', [dict(order=3), dict(order=3, rsolver='hllc')],
+                         ids=str)
+def test_vortex_rhs_matches_oracle(built, kw):
+    _, ref = oracle_rhs('vortex', 12, **kw)
+    _, out = b200_rhs('vortex', 12, **kw)
+
+    assert rel_err(out, ref[0]) < TOL64
+
+
+def test_matrix_roundtrip_and_layout(built):
+    from pyfr_b200.backend import B200Backend
+
+    cfg, _ = cases.make('tgv', 2)
+    be = B200Backend(cfg)
+    rng = np.random.default_rng(0)
+
+    for shape in [(7, 5, 37), (3, 4, 5, 19), (6, 50)]:
+        a = rng.standard_normal(shape)
+        m = be.matrix(shape, a, tags={'align'})
+        assert np.array_equal(m.get(), a)
+
+        b = rng.standard_normal(shape)
+        m.set(b)
+        assert np.array_equal(m.get(), b)
+
+
+def test_free_stream_preserved(built):
+    extra = ''
+    from pyfr_b200.backend import B200Backend
+    from pyfr_b200.host.config import Config
+
+    txt = cases.tgv_cfg(order=3)
+    txt = txt[:txt.index('[soln-ics]')] + (
+        '[soln-ics]\nrho = 1.2\nu = 0.3\nv = -0.2\nw = 0.1\np = 2.5\n'
+    )
+    cfg = Config(txt)
+    be = B200Backend(cfg)
+    box = cases.tgv_mesh((4, 3, 3), warp=0.15)
+    sysm = get_system(be, box.local_mesh(), cfg, 2)
+    sysm.rhs(0.0, 0, 1)
+
+    assert np.abs(sysm.ele_scal_upts(1)[0]).max() < 1e-11

@@ -1,0 +1,40 @@
+"""Shared helpers for the parity tests."""
+
+import numpy as np
+
+from oracle.npbackend import LocalComm, make_backend
+from pyfr_b200 import base, cases
+from pyfr_b200.host.system import get_system
+
+OracleBackend = make_backend(base)
+
+
+def oracle_rhs(case, n, nregs=2, vparts=None, nparts=1, **kw):
+    """RHS of bank 0 into bank 1 on the NumPy oracle; returns per-rank
+    (system, rhs array) lists."""
+    world = LocalComm(0, nparts)
+    systems = []
+
+    for r in range(nparts):
+        cfg, box = cases.make(case, n, **kw)
+        be = OracleBackend(cfg)
+        mesh = box.local_mesh(vparts, r)
+        systems.append(get_system(be, mesh, cfg, nregs, comm=world.peer(r)))
+
+    run_lockstep(systems, world, 0.0, 0, 1)
+    return systems, [s.ele_scal_upts(1)[0] for s in systems]
+
+
+def run_lockstep(systems, world, t, uin, fout):
+    """Advance all in-process ranks graph by graph, delivering the halo
+    messages between stages (what MPI/NCCL do between real ranks)."""
+    graphs = [s.rhs_graphs(uin, fout) for s in systems]
+
+    for stage in zip(*graphs):
+        for g in stage:
+            g.run()
+        world.deliver()
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max()/np.abs(b).max()
