@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""RHS throughput benchmark (BASELINE.json metric: GDoF-RHS/s, TGV hex p=4
+fp64).
+
+One *step* is one right-hand-side evaluation ``system.rhs(t, 0, 1)`` over
+the whole mesh (the metric the reference defines as ``rhs-gdof/s =
+gndofs*nrhsevals/wtime``, pyfr/integrators/base.py:348-349).  At N GPUs the
+mesh is N bricks of ``--n``^3 hexes (weak scaling), one rank per GPU, halo
+exchange over NCCL.
+
+Prints ONE JSON line (rank 0).  ``value`` is timed with CUDA events on the
+compute stream with all data resident in HBM; ``e2e`` repeats the
+measurement with the solution uploaded from / the RHS downloaded to pinned
+host memory inside the timed region; ``roofline`` describes the dominant
+kernel (per-launch CUDA-event times against its algorithmic bytes);
+``cpu_baseline`` is the NumPy oracle port timed on the host cores on a
+bounded sample.  ``--impl reference`` times only that CPU port.
+"""
+
+import argparse
+import ctypes as ct
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np                                       # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--n', type=int, default=64, help='hexes per direction '
+                    'per GPU')
+    ap.add_argument('--order', type=int, default=4)
+    ap.add_argument('--precision', default='double')
+    ap.add_argument('--rsolver', default='rusanov')
+    ap.add_argument('--cpu-n', type=int, default=12, help='mesh size of the '
+                    'bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--kernel-times', default=None, help='write the '
+                    'per-kernel event timings to this JSON file')
+    return ap.parse_args()
+
+
+# -- helpers ------------------------------------------------------------------
+def bricks(nparts):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[nparts]
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '100', '-i',
+                 str(self.gpu)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+
+        if not sm:
+            return None
+
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(smax),
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_baseline(args):
+    """The NumPy oracle port on the host cores, bounded sample."""
+    from oracle.npbackend import make_backend
+    from pyfr_b200 import base, cases
+    from pyfr_b200.host.system import get_system
+
+    n = args.cpu_n
+    cfg, box = cases.make('tgv', n, order=args.order, rsolver=args.rsolver)
+    be = make_backend(base)(cfg)
+    sysm = get_system(be, box.local_mesh(), cfg, 2)
+    ndof = sum(sysm.ele_ndofs)
+
+    sysm.rhs(0.0, 0, 1)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 2 or time.perf_counter() - t0 < 10.0:
+        sysm.rhs(0.0, 0, 1)
+        reps += 1
+    dt = (time.perf_counter() - t0)/reps
+
+    return {
+        'value': ndof/dt/1e9, 'unit': 'GDoF/s', 'cores': 1, 'kind': 'port',
+        'sample': f'{reps} RHS evaluations of TGV NS hex p={args.order} '
+                  f'fp64 on {n}^3 elements ({ndof} DoF), NumPy oracle '
+                  '(restatement of the reference kernels; the reference '
+                  'OpenMP/libxsmm backend cannot run offline)'
+    }, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+
+    vals = []
+    base_info = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base_info, dt = cpu_baseline(args)
+        vals.append(base_info['value'])
+
+    v = statistics.median(vals)
+    base_info['value'] = v
+    line = {
+        'impl': 'reference', 'metric': 'GDoF-RHS/s', 'value': v,
+        'unit': 'GDoF/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': None,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64' if args.precision == 'double' else 'f32',
+        'data': 'synthetic',
+        'config': workload_config(args), 'cpu_baseline': base_info,
+        'e2e': {'value': v, 'unit': 'GDoF/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0}
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        'workload': f'TGV compressible Navier-Stokes, {args.n}^3 periodic '
+                    f'hexes per GPU, p={args.order}, '
+                    f'{"fp64" if args.precision == "double" else "fp32"}, '
+                    f'{args.rsolver}, LDG beta=0.5 tau=0.1, one RHS '
+                    'evaluation per step',
+        'mesh': f'{args.n}^3 per GPU, brick partition',
+        'l2': 'inputs larger than L2 (solution bank alone is '
+              f'{args.n**3*(args.order + 1)**3*5*8/1e6:.0f} MB per GPU)',
+        'parallelism': f'domain decomposition, {args.gpus} rank(s), NCCL '
+                       'send/recv halo exchange'
+    }
+
+
+# -- main benchmark -----------------------------------------------------------
+def main():
+    args = parse()
+
+    if args.impl == 'reference':
+        reference_arm(args)
+        return
+
+    from pyfr_b200 import cases
+    from pyfr_b200.backend import B200Backend
+    from pyfr_b200.comm import NCCLComm
+    from pyfr_b200.host.system import get_system
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    lrank = int(os.environ.get('LOCAL_RANK', 0))
+
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}; launch '
+                         'with torch.distributed.run for N > 1')
+
+    # Mesh: `world` bricks of n^3 hexes
+    parts = bricks(world)
+    cfg, box = cases.make('tgv', tuple(args.n*p for p in parts),
+                          order=args.order, precision=args.precision,
+                          rsolver=args.rsolver)
+    cfg.set('backend-b200', 'device-id', lrank)
+    if args.no_graphs:
+        cfg.set('backend-b200', 'graphs', 'false')
+
+    be = B200Backend(cfg)
+    rt = be.rt
+
+    comm = None
+    if world > 1:
+        comm = be.comm = NCCLComm(rt, rank, world)
+    else:
+        comm = type('Serial', (), {'rank': 0, 'size': 1})()
+
+    vparts = box.brick_partition(parts) if world > 1 else None
+    t0 = time.time()
+    sysm = get_system(be, box.local_mesh(vparts, rank), cfg, 2, comm=comm)
+    setup_s = time.time() - t0
+    ndof_local = sum(sysm.ele_ndofs)
+    ndof = ndof_local*world
+    isz = 8 if args.precision == 'double' else 4
+
+    # Scalar used for barriers / max-over-ranks
+    red = be.matrix((1, 4), tags={'noblock'})
+
+    def barrier():
+        if world > 1:
+            comm.allreduce(red.data, 1, 1 if isz == 8 else 0, 2, be.stream)
+        rt.stream_sync(be.stream)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        red.set(np.full((1, 4), x))
+        comm.allreduce(red.data, 1, 1 if isz == 8 else 0, 2, be.stream)
+        rt.stream_sync(be.stream)
+        return float(red.get()[0, 0])
+
+    ev0, ev1 = rt.new_ptr(rt.event_create), rt.new_ptr(rt.event_create)
+
+    def timed(fn, steps):
+        barrier()
+        rt.device_sync()
+        rt.event_record(ev0, be.stream)
+        for _ in range(steps):
+            fn()
+        rt.event_record(ev1, be.stream)
+        rt.event_sync(ev1)
+        rt.device_sync()
+        ms = rt.elapsed_ms(ev0, ev1)
+        barrier()
+        return max_over_ranks(ms)
+
+    step = lambda: sysm.rhs(0.0, 0, 1)
+
+    # ---- device-resident throughput --------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    rt.device_sync()
+
+    sampler = ClockSampler(lrank)
+    if rank == 0:
+        sampler.start()
+
+    l0 = be.nlaunches
+    ms = timed(step, args.steps)
+    graphs = sysm.rhs_graphs(0, 1)
+    nkern = sum(1 for g in graphs for w, k in g.plan if w == 'kernel')
+    launches = (be.nlaunches - l0) if not be.use_graphs else nkern*args.steps
+
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms/args.steps
+    value = ndof/(ms_per_step*1e-3)/1e9
+
+    # ---- per-kernel event timing (dominant kernel + roofline) -------------
+    kt = {}
+    kernels = [(gi, i, k) for gi, g in enumerate(graphs)
+               for i, (w, k) in enumerate(g.plan) if w == 'kernel']
+    evs = [(rt.new_ptr(rt.event_create), rt.new_ptr(rt.event_create))
+           for _ in kernels]
+    nrep = min(args.steps, 10)
+    acc = [0.0]*len(kernels)
+
+    if world == 1:
+        for _ in range(nrep):
+            for (a, b), (gi, i, k) in zip(evs, kernels):
+                rt.event_record(a, be.stream)
+                k.run(be.stream)
+                rt.event_record(b, be.stream)
+            rt.device_sync()
+            for j, (a, b) in enumerate(evs):
+                acc[j] += rt.elapsed_ms(a, b)
+
+        for j, (gi, i, k) in enumerate(kernels):
+            name = getattr(getattr(k, 'fn', None), 'name',
+                           type(k).__name__)
+            meta = (k.misc[0] if getattr(k, 'misc', None) and
+                    isinstance(k.misc[0], dict) else {})
+            label = f'g{gi}.{i}:{name}' + (
+                f'[{meta["M"]}x{meta["K"]}]' if meta else '')
+            kt[label] = {'ms': acc[j]/nrep,
+                         'bytes': getattr(k, 'traffic', 0)}
+
+    roof = None
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak_gbs = peaks.get('hbm_gbs', 6650.0)
+    peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+
+    if kt:
+        dom = max(kt, key=lambda n: kt[n]['ms'])
+        d = kt[dom]
+        ach = d['bytes']/(d['ms']*1e-3)/1e9
+        ksum = sum(v['ms'] for v in kt.values())
+        roof = {
+            'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak_gbs,
+            'unit': 'GB/s', 'frac': ach/peak_gbs, 'traffic': None,
+            'peak_source': peak_src, 'kernel_ms': d['ms'],
+            'kernel_share_of_step': d['ms']/ksum,
+            'sum_kernel_ms': ksum
+        }
+
+    # Whole-RHS figure against the 3-pass algorithmic model
+    nu, nf = (args.order + 1)**3, 6*(args.order + 1)**2
+    balg = (5*nu*5 + 5*nf*5 + 3*3*nf*5)*isz/(nu*5)
+    rhs_model = {
+        'bytes_per_dof_3pass': balg,
+        'achieved_gbs_3pass': value*balg,
+        'frac_of_hbm_3pass': value*balg/peak_gbs,
+        'peak_source': peak_src
+    }
+
+    # ---- end to end: host buffers in, host buffers out ---------------------
+    e2e = None
+    if not args.no_e2e:
+        bank_in = sysm.ele_banks[0][0]
+        bank_out = sysm.ele_banks[0][1]
+        nb = bank_in.nbytes
+        hin = rt.new_ptr(rt.malloc_host, nb)
+        hout = rt.new_ptr(rt.malloc_host, nb)
+        rt.memcpy(hin, bank_in.data, nb)
+
+        def step_e2e():
+            bank_in.upload_packed(hin)
+            sysm.rhs(0.0, 0, 1)
+            bank_out.download_packed(hout)
+
+        for _ in range(2):
+            step_e2e()
+        rt.device_sync()
+
+        esteps = max(3, min(args.steps, 10))
+        ems = timed(step_e2e, esteps)/esteps
+        e2e = {'value': ndof/(ems*1e-3)/1e9, 'unit': 'GDoF/s',
+               'h2d_bytes_per_step': nb*world, 'd2h_bytes_per_step': nb*world,
+               'ms_per_step': ems,
+               'api': 'Matrix.upload_packed -> system.rhs -> '
+                      'Matrix.download_packed, pinned host memory'}
+        rt.free_host(hin)
+        rt.free_host(hout)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            'metric': 'GDoF-RHS/s', 'value': value, 'unit': 'GDoF/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64' if isz == 8 else 'f32', 'data': 'synthetic',
+            'config': workload_config(args), 'gpu_launches': launches,
+            'launches_per_step': nkern, 'cuda_graphs': be.use_graphs,
+            'dof': ndof, 'setup_s': setup_s, 'clocks': clocks,
+            'roofline': roof, 'rhs_model': rhs_model, 'e2e': e2e,
+            'cpu_baseline': cpu,
+            'compiler': be.compiler.stats
+        }
+        print(json.dumps(line))
+
+        if args.kernel_times:
+            with open(args.kernel_times, 'w') as f:
+                json.dump({'ms_per_step': ms_per_step, 'kernels': kt}, f,
+                          indent=1)
+
+    if world > 1:
+        barrier()
+        be.comm.close()
+
+
+if __name__ == '__main__':
+    main()

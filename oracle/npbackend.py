@@ -173,11 +173,21 @@ def make_backend(base, name='oracle-numpy'):
                 raise ValueError('Incompatible matrices for out = a*b')
 
             A = a.get()
+            ext = self.backend.extended_mul
 
             def run():
                 B, C = _mat3(b), _mat3(out)
-                r = alpha*np.einsum('mk,bkn->bmn', A, B)
-                C[:] = r + beta*C if beta else r
+
+                if ext:
+                    # Extended-precision accumulation: measures how much of
+                    # a discrepancy is plain fp64 summation-order noise
+                    r = alpha*np.einsum('mk,bkn->bmn',
+                                        A.astype(np.longdouble),
+                                        B.astype(np.longdouble))
+                    C[:] = (r + beta*C if beta else r).astype(C.dtype)
+                else:
+                    r = alpha*np.einsum('mk,bkn->bmn', A, B)
+                    C[:] = r + beta*C if beta else r
 
             return NPKernel(run)
 
@@ -270,6 +280,8 @@ def make_backend(base, name='oracle-numpy'):
             self.soasz = cfg.getint('backend-oracle', 'soasz', 8)
             self.csubsz = cfg.getint('backend-oracle', 'csubsz', self.soasz)
             self.blocks = cfg.getbool('backend-oracle', 'blocks', False)
+            self.extended_mul = cfg.getbool('backend-oracle', 'extended-mul',
+                                            False)
 
             self.pointwise = PointwiseProvider(self)
             self._providers = [BlasProvider(self), self.pointwise]

@@ -16,24 +16,20 @@ import itertools as it
 import numpy as np
 
 
-def _side_arrays(side, elemap, getter):
-    """Evaluate ``elemap[etype].<getter>(eidxs, fidx)`` for every face
-    group of one interface side and lay the per-flux-point results out in
-    interface order."""
+def _side_layout(side, elemap):
+    """Start offset of every interface's run of flux points."""
     nfp = np.empty(len(side), dtype=np.int64)
-    chunks = []
 
     for etype, fidx, eidxs, where in side.foreach():
         nfp[where] = elemap[etype].nfacefpts[fidx]
-        chunks.append((where, getattr(elemap[etype], getter)(eidxs, fidx)))
 
-    start = np.concatenate(([0], np.cumsum(nfp)))
-    return start, nfp, chunks
+    return np.concatenate(([0], np.cumsum(nfp)))
 
 
 def side_view_maps(side, elemap, getter):
-    """(matmap, rmap, cmap, rstridemap) arrays for a view over one side."""
-    start, nfp, chunks = _side_arrays(side, elemap, getter)
+    """(matmap, rmap, cmap, rstridemap) arrays for a view over one side,
+    one entry per flux point, in interface order."""
+    start = _side_layout(side, elemap)
     n = int(start[-1])
 
     matmap = np.empty(n, dtype=np.int64)
@@ -56,10 +52,11 @@ def side_view_maps(side, elemap, getter):
 
 
 def side_const(side, elemap, getter, ndims):
-    start, nfp, chunks = _side_arrays(side, elemap, getter)
+    start = _side_layout(side, elemap)
     out = np.empty((int(start[-1]), ndims))
 
-    for where, vals in chunks:
+    for etype, fidx, eidxs, where in side.foreach():
+        vals = getattr(elemap[etype], getter)(eidxs, fidx)
         k = len(vals) // max(len(where), 1)
         dst = (start[where][:, None] + np.arange(k)).ravel()
         out[dst] = vals

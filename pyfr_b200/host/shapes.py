@@ -103,16 +103,16 @@ def clean(arr, tol=1e-10):
     if arr.size > 1:
         mag = np.abs(arr).ravel()
         order = np.argsort(mag)
-        srt = mag[order]
+        srt = mag[order].tolist()
 
         # A run continues while values stay close to the run's first entry
-        start = 0
-        for j in range(1, len(srt) + 1):
-            if j == len(srt) or not np.isclose(srt[j], srt[start], rtol=tol,
-                                                atol=0.1*tol):
+        start, ref, n = 0, srt[0], len(srt)
+        for j in range(1, n + 1):
+            if j == n or abs(srt[j] - ref) > 0.1*tol + tol*abs(ref):
                 if j - start > 1:
                     mag[order[start:j]] = np.median(srt[start:j])
-                start = j
+                if j < n:
+                    start, ref = j, srt[j]
 
         arr = np.copysign(mag, arr.ravel()).reshape(arr.shape)
 

@@ -77,6 +77,19 @@ class B200MatrixBase(_Common, base.MatrixBase):
         rt.device_sync()
         rt.memcpy(self.data, buf.ctypes.data, self.nbytes)
 
+    # Raw transfers of the storage-order image (what the reference moves
+    # through its pinned bounce buffer, cuda/types.py:25-41), asynchronous
+    # on the backend's stream; ``hostptr`` should be pinned memory
+    def upload_packed(self, hostptr, stream=None):
+        be = self.backend
+        be.rt.memcpy_async(self.data, hostptr, self.nbytes,
+                           stream if stream is not None else be.stream)
+
+    def download_packed(self, hostptr, stream=None):
+        be = self.backend
+        be.rt.memcpy_async(hostptr, self.data, self.nbytes,
+                           stream if stream is not None else be.stream)
+
 
 class B200Matrix(B200MatrixBase, base.Matrix): pass
 
