@@ -6,9 +6,10 @@ with a different design underneath: blocked AoSoA storage
 TMA bulk copy moves), operator constants baked into generated sm_100a
 kernels, CUDA-graph replay of each RHS graph and NCCL for the halo
 exchange.  Configuration keys (section ``[backend-b200]``): ``device-id``
-(``local-rank`` or an index), ``n-soa`` (SoA width, default 128 bytes worth
+(``local-rank`` or an index), ``n-soa`` (SoA width, default 64 bytes worth
 of scalars), ``n-csub`` (columns per block, multiple of ``n-soa``),
-``graphs`` (replay through CUDA graphs, default on).
+``graphs`` (replay through CUDA graphs, default on), ``fusion`` (replace
+grouped kernel chains by fused single-launch kernels, default on).
 """
 
 import os
@@ -52,16 +53,19 @@ class B200Backend(base.BaseBackend):
         self.sm_count = info['sm_count']
         self.smem_budget = min(info['smem_optin'], 227*1024) - 8*1024
 
-        # Storage layout: 128-byte SoA rows, one SoA group per block
+        # Storage layout: 64-byte SoA rows (two 32-byte sectors), one SoA
+        # group per block; small enough that the fused element kernel can
+        # hold a whole block's gradients in shared memory at p = 4
         isz = np.dtype(self.fpdtype).itemsize
         self.alignb = 256
-        self.soasz = cfg.getint(sect, 'n-soa', 128 // isz)
+        self.soasz = cfg.getint(sect, 'n-soa', 64 // isz)
         self.csubsz = cfg.getint(sect, 'n-csub', self.soasz)
         if self.csubsz % self.soasz:
             raise ValueError('n-csub must be a multiple of n-soa')
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
+        self.fuse = cfg.getbool(sect, 'fusion', True)
 
         self.compiler = KernelCompiler(rt)
         self.nlaunches = 0

@@ -1,0 +1,292 @@
+"""Graph-level kernel fusion.
+
+The host code (the reference's system classes, or the mirror in
+``pyfr_b200.host``) builds each RHS graph from individual kernels and, for
+``blocks = True`` backends, marks the element-local chains that only
+communicate through block-private temporaries with ``Graph.group(kerns,
+subs)`` (``pyfr/solvers/baseadvecdiff/system.py:174-203,225-227``;
+``pyfr/solvers/baseadvec/system.py:126-134``).  The reference's OpenMP
+backend uses those hints to run a group block by block out of cache
+(``pyfr/backends/openmp/types.py:136-186``); here they select generated
+single-launch kernels that keep the temporaries in shared memory.
+
+Every rewrite is checked structurally against the kernels it replaces and
+silently declines when anything is unexpected -- the graph then simply runs
+the individual (still GPU) kernels.
+"""
+
+import numpy as np
+
+from pyfr_b200.kernels import fused as kfused
+from pyfr_b200.kernels import mul as kmul
+
+
+def leaves(k):
+    if hasattr(k, 'kernels'):
+        return [l for c in k.kernels for l in leaves(c)]
+    return [k]
+
+
+def _same(a, b):
+    """Do two matrix handles address the same storage window?"""
+    return (a is b or (a.data == b.data and a.nrow == b.nrow and
+                       a.ncol == b.ncol and a.blocksz == b.blocksz))
+
+
+def _block_off(m):
+    return getattr(m, 'ba', 0)
+
+
+def _root(m):
+    return getattr(m, 'parent', m)
+
+
+def _rows_of(m):
+    """(root matrix, first row, nrow) of a matrix or row/column slice."""
+    return _root(m), getattr(m, 'ra', 0), m.nrow
+
+
+def fuse_gradflux(be, kerns, subs):
+    """tgradpcoru .. tdivtpcorf of one element type -> ``gradflux``."""
+    from pyfr_b200.providers import B200Kernel
+
+    if len(kerns) != 6:
+        return None
+
+    k0, k1, k2, k3, k4, k5 = kerns
+    g2, g3, g4 = leaves(k2), leaves(k3), leaves(k4)
+
+    if not (getattr(k0, 'kind', None) == 'mul' and
+            getattr(k1, 'kind', None) == 'mul' and
+            getattr(k5, 'kind', None) == 'mul' and
+            all(k.kind == 'gradcoru' for k in g2) and
+            all(k.kind == 'mul' for k in g3) and
+            all(k.kind == 'tflux' for k in g4)):
+        return None
+
+    i0, i1, i5 = k0.info, k1.info, k5.info
+    U, G, C, FOUT = i0['b'], i0['out'], i1['b'], i5['out']
+
+    if (i0['beta'] != 0 or i0['alpha'] != 1 or i1['beta'] != 1 or
+        i1['alpha'] != 1 or i5['beta'] != 0 or i5['alpha'] != 1 or
+        not _same(i1['out'], G) or not _same(i5['b'], G)):
+        return None
+
+    tpl = g4[0].info['tplargs']
+    nd, nv = tpl['ndims'], tpl['nvars']
+    nu, nf = U.nrow, C.nrow
+    LD = U.leaddim
+
+    if (len(g3) != nd or G.nrow != nd*nu or len(g2) != len(g4) or
+        any(k.info['tplargs'].get('shock_capturing', 'none') != 'none' or
+            'fused' in k.info['tplargs']['ktype'] or not k.info['viscous']
+            for k in g4)):
+        return None
+
+    # gradcoru_fpts: ndims multiplies by M0 from G[d] into vect_fpts[d]
+    M0 = g3[0].info['A']
+    VF = _root(g3[0].info['out'])
+    for d, k in enumerate(g3):
+        i = k.info
+        if (i['beta'] != 0 or i['alpha'] != 1 or
+            not np.array_equal(i['A'], M0) or
+            _rows_of(i['b']) != (_root(G), d*nu, nu) or
+            _rows_of(i['out']) != (VF, d*nf, nf)):
+            return None
+
+    if VF.nrow != nd*nf or VF.leaddim != LD or FOUT.leaddim != LD:
+        return None
+
+    # Shared memory: u + ucomm + G
+    isz = U.itemsize
+    if (nu + nf + nd*nu)*LD*isz + 64 > be.smem_budget + 8*1024:
+        return None
+
+    ops = dict(A1=i0['A'], M6=i1['A'], M0=M0, A5=i5['A'])
+    out = []
+
+    # One launch per mesh region (curved / linear)
+    for kg, kt in zip(g2, g4):
+        ti, gi = kt.info, kg.info
+        ktype = ti['tplargs']['ktype']
+
+        if (gi['tplargs']['ktype'] != ktype or ti['dims'] != gi['dims'] or
+            _root(ti['f']) is not _root(G) or _root(ti['u']) is not _root(U)
+            or _root(gi['gradu']) is not _root(G)):
+            return None
+
+        npts, neles = ti['dims']
+        b0 = _block_off(ti['u'])
+        nblocks = -(-neles // be.csubsz)
+        pts = ti['upts'].get() if ti['upts'] is not None else None
+
+        src, name, meta = kfused.gradflux_source(be, ops, ti['tplargs'], pts,
+                                                 LD)
+        fn = be.pointwise._function(src, name)
+        fn.set_smem(meta['smem'])
+
+        off = lambda m: m.data + b0*m.blocksz*isz
+        args = [('i', nblocks), ('i', neles),
+                ('p', off(U)), ('l', U.blocksz),
+                ('p', off(C)), ('l', C.blocksz),
+                ('p', off(VF)), ('l', VF.blocksz),
+                ('p', off(FOUT)), ('l', FOUT.blocksz)]
+
+        if 'linear' in ktype:
+            v = ti['verts']
+            args += [('p', v.data), ('l', v.blocksz)]
+            geo = [v]
+        else:
+            s, r = ti['smats'], gi['rcpdjac']
+            args += [('p', s.data), ('l', s.blocksz), ('p', r.data),
+                     ('l', r.blocksz)]
+            geo = [s, r]
+
+        out.append(B200Kernel(
+            be, fn, (min(nblocks, be.sm_count), 1, 1),
+            (meta['nthreads'], 1, 1), meta['smem'], args,
+            mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
+            traffic=meta['words_per_block']*nblocks*isz, kind='gradflux',
+            info=dict(replaces=kerns)
+        ))
+
+    return out
+
+
+def fuse_tdivtconf_negdivconf(be, kerns, subs):
+    """tdivtconf (out += M3 @ scal_fpts) followed by negdivconf."""
+    from pyfr_b200.providers import B200Kernel
+
+    if len(kerns) != 2:
+        return None
+
+    km, kn = kerns
+    ln = leaves(kn)
+    if not (getattr(km, 'kind', None) == 'mul' and len(ln) == 1 and
+            ln[0].kind == 'negdivconf'):
+        return None
+
+    im, ineg = km.info, ln[0].info
+    out, b = im['out'], im['b']
+
+    if (not _same(ineg['tdivtconf'], out) or ineg['tplargs']['src_macros'] or
+        ineg['dims'][0] != out.nrow):
+        return None
+
+    LD, nv = b.leaddim, ineg['tplargs']['nvars']
+    nblocks = -(-b.ncol // LD)
+    r = ineg['rcpdjac']
+
+    src, name, meta = kmul.mul_source(
+        be, im['A'], LD, im['alpha'], im['beta'], smem_budget=be.smem_budget,
+        rowgroups=be.mul_rowgroups, negdiv_nvars=nv
+    )
+    fn = be.pointwise._function(src, name)
+    fn.set_smem(meta['smem'])
+
+    isz = b.itemsize
+    traffic = ((b.nrow + out.nrow*(2 if im['beta'] else 1))*LD +
+               out.nrow*be.csubsz)*nblocks*isz
+
+    k = B200Kernel(
+        be, fn, (min(nblocks, be.sm_count), 1, 1), (meta['nthreads'], 1, 1),
+        meta['smem'],
+        [('i', nblocks), ('p', b.data), ('l', b.blocksz), ('p', out.data),
+         ('l', out.blocksz), ('p', r.data), ('l', r.blocksz)],
+        mats=[b, out, r], misc=[meta], traffic=traffic, kind='mul+negdivconf',
+        info=dict(replaces=kerns)
+    )
+
+    # negdivconf carries the (unused here) run-time argument t
+    k.rtnames = ()
+    return [k]
+
+
+_group_fusers = [fuse_gradflux, fuse_tdivtconf_negdivconf]
+
+
+def fuse_group(be, kerns, subs):
+    for f in _group_fusers:
+        try:
+            new = f(be, kerns, subs)
+        except (KeyError, AttributeError, AssertionError):
+            new = None
+
+        if new:
+            return new
+
+    return None
+
+
+def elide_copy_fpts(be, program):
+    """Drop ``copy_fpts`` when the common-solution kernels that follow it
+    can store every flux point themselves.
+
+    With |ldg-beta| = 1/2 the reference seeds the common solution with a
+    full copy of the interpolated solution and lets ``intconu`` overwrite
+    one side only (``pyfr/solvers/baseadvecdiff/elements.py:42-46``,
+    ``navstokes/kernels/intconu.mako``).  Every flux point belongs to exactly
+    one interface side, so when the con_u kernels of the graph cover the
+    whole array the copy is a wasted pass; ``intconu`` is regenerated to
+    store both sides."""
+    kerns = [k for w, k in program if w == 'kernel']
+    copies = [k for k in kerns if getattr(k, 'kind', None) == 'copy']
+    conus = [k for k in kerns if getattr(k, 'kind', None) in
+             ('intconu', 'mpiconu')]
+
+    if len(copies) != 1 or not conus:
+        return program
+
+    cp = copies[0]
+    dst, src = cp.info['dst'], cp.info['src']
+
+    if any(kerns.index(k) < kerns.index(cp) for k in conus):
+        return program
+
+    def where(view, mat):
+        # (block, offset in block) of every view point inside ``mat``
+        m = view.mapping.get()[0].astype(np.int64) - mat.offset//mat.itemsize
+        return m // mat.blocksz, m % mat.blocksz
+
+    # Coverage: interior kernels touch 2n points, partition-boundary ones n
+    npts = 0
+    for k in conus:
+        i = k.info
+        sides = [(i['ulin'], i['ulout'])]
+        if k.kind == 'intconu':
+            sides.append((i['urin'], i['urout']))
+
+        for vin, vout in sides:
+            vin, vout = getattr(vin, 'view', vin), getattr(vout, 'view', vout)
+
+            # The trace and the common solution must be addressed alike
+            if (int(vout.basedata) != int(dst.basedata) or
+                int(vin.basedata) != int(src.basedata)):
+                return program
+
+            (bi, oi), (bo, oo) = where(vin, src), where(vout, dst)
+            if not (np.array_equal(bi, bo) and np.array_equal(oi, oo)):
+                return program
+
+            npts += vin.n
+
+    nele = src.ioshape[-1] if hasattr(src, 'ioshape') else None
+    if nele is None or npts != src.nrow*nele:
+        return program
+
+    # Regenerate intconu with both-side stores
+    repl = {}
+    for k in conus:
+        if k.kind == 'intconu' and not k.info['both']:
+            i = k.info
+            repl[k] = be.pointwise._conu(False, i['tplargs'], i['dims'],
+                                         i['ulin'], i['urin'], i['ulout'],
+                                         i['urout'], both=True)
+
+    out = []
+    for w, k in program:
+        if k is cp:
+            continue
+        out.append((w, repl.get(k, k)))
+
+    return out

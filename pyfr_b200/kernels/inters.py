@@ -181,7 +181,10 @@ extern "C" __global__ void __launch_bounds__(128)
     return src, name, _names(args)
 
 
-def conu_source(be, tplargs, mpi):
+def conu_source(be, tplargs, mpi, both=False):
+    """``both``: also store each side's own trace where the reference
+    kernel leaves it untouched (|beta| = 1/2), which makes the preceding
+    ``copy_fpts`` pass over the whole flux-point array redundant."""
     nv, beta = tplargs['nvars'], tplargs['c']['ldg-beta']
     name = 'mpiconu' if mpi else 'intconu'
 
@@ -205,7 +208,15 @@ def conu_source(be, tplargs, mpi):
                     f'{ldr}*{ph.fpconst(0.5 + beta)} + '
                     f'{ldl}*{ph.fpconst(0.5 - beta)};')
     else:
-        if beta == -0.5:
+        if beta == -0.5 and both:
+            stmt = (f'const fpdtype_t com = {ldl};\n'
+                    '        ulout[ulout_map[i] + K_SOA*v] = com;\n'
+                    '        urout[urout_map[i] + K_SOA*v] = com;')
+        elif beta == 0.5 and both:
+            stmt = (f'const fpdtype_t com = {ldr};\n'
+                    '        ulout[ulout_map[i] + K_SOA*v] = com;\n'
+                    '        urout[urout_map[i] + K_SOA*v] = com;')
+        elif beta == -0.5:
             stmt = f'urout[urout_map[i] + K_SOA*v] = {ldl};'
         elif beta == 0.5:
             stmt = f'ulout[ulout_map[i] + K_SOA*v] = {ldr};'

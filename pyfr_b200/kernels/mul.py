@@ -97,8 +97,13 @@ def plan_chunks(K, LD, itemsize, smem_budget, hint=None):
 
 
 def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
-               chunk_hint=None):
+               chunk_hint=None, negdiv_nvars=None):
     """CUDA source for ``out = alpha*A@b + beta*out``.
+
+    With ``negdiv_nvars`` the ``negdivconf`` step that follows the last
+    operator of the RHS (``out = -rcpdjac*out``, pyfr/solvers/baseadvec/
+    kernels/negdivconf.mako) is applied in the epilogue, saving one full
+    read-modify-write pass over the result.
 
     Returns (source, name, launch meta dict)."""
     A = alpha*np.asarray(A, dtype=float)
@@ -136,6 +141,11 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
 
     def store(m, val):
         ix = f'ob + {m*LD} + col'
+        if negdiv_nvars:
+            old = f'out[{ix}] + ' if beta == 1 else (
+                f'{ph.fpconst(beta)}*out[{ix}] + ' if beta else '')
+            return (f'out[{ix}] = -__ldg(rcpdjac + rjb + {m}*C_SUB)*'
+                    f'({old}{val});')
         if beta == 0:
             return f'out[{ix}] = {val};'
         elif beta == 1:
@@ -171,6 +181,13 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
                      '            {\n' + '\n'.join(body) +
                      '\n            }\n            break;')
 
+    extra_args = extra_pre = ''
+    if negdiv_nvars:
+        extra_args = (', const fpdtype_t* __restrict__ rcpdjac, '
+                      'long long rcpdjac_bsz')
+        extra_pre = (f'        const long long rjb = blk*rcpdjac_bsz + '
+                     f'(col/(K_SOA*{negdiv_nvars}))*K_SOA + col % K_SOA;')
+
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz)}
 #define LD {LD}
@@ -184,7 +201,7 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
 // {int(np.count_nonzero(A))} non-zeros, {nchunks} chunk(s) of {crows} rows
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
 opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
-      fpdtype_t* __restrict__ out, long long out_bsz)
+      fpdtype_t* __restrict__ out, long long out_bsz{extra_args})
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *tiles = reinterpret_cast<fpdtype_t *>(smem_raw);
@@ -236,6 +253,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
 
         const fpdtype_t *sm = tiles + st*TILE;
         const long long ob = blk*out_bsz;
+{extra_pre}
 
         if (active)
         {{

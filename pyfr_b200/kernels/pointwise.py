@@ -36,7 +36,7 @@ _geom_linear_src = r'''
             V[n][i] = __ldg(verts + blk*verts_bsz + n*(NDIMS*C_SUB)
                             + COFF(e, i, NDIMS));
     UNROLL for (int i = 0; i < NDIMS; i++)
-        x[i] = c_pts[p][i];
+        x[i] = __ldg(&c_pts[p][i]);
 
     calc_smats_detj(V, x, s, djac);
     const fpdtype_t rcpdjac_v = FP(1.0)/djac;
@@ -60,8 +60,8 @@ _geom_curved_src = r'''
 def _pts_table(pts):
     rows = ', '.join('{' + ', '.join(ph.fpconst(v) for v in row) + '}'
                      for row in pts)
-    return (f'__constant__ fpdtype_t c_pts[{len(pts)}][{len(pts[0])}] = '
-            f'{{{rows}}};\n')
+    return (f'static __device__ const fpdtype_t c_pts[{len(pts)}]'
+            f'[{len(pts[0])}] = {{{rows}}};\n')
 
 
 def _geom(tplargs, pts):

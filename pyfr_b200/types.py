@@ -141,10 +141,37 @@ class B200Graph(base.Graph):
         return kern
 
     def _group(self, kerns, subs):
-        # Fusion hints: see pyfr_b200/providers/fused.py (later rounds)
-        pass
+        self._fgroups = getattr(self, '_fgroups', []) + [(kerns, subs)]
+
+    def _fuse(self):
+        from pyfr_b200 import fusion
+
+        be = self.backend
+        if not be.fuse:
+            return
+
+        for kerns, subs in getattr(self, '_fgroups', []):
+            new = fusion.fuse_group(be, kerns, subs)
+            if not new:
+                continue
+
+            old = {id(l) for k in kerns for l in fusion.leaves(k)}
+            prog, done = [], False
+            for what, obj in self.program:
+                if what == 'kernel' and id(obj) in old:
+                    if not done:
+                        prog.extend(('kernel', k) for k in new)
+                        done = True
+                else:
+                    prog.append((what, obj))
+
+            self.program = prog
+
+        self.program = fusion.elide_copy_fpts(be, self.program)
 
     def _commit(self):
+        self._fuse()
+
         # All exchanges of a graph go out as one NCCL group, issued once
         # the last pack kernel has been enqueued
         reqs = [r for what, r in self.program if what == 'xchg']

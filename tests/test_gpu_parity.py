@@ -16,10 +16,17 @@ pytestmark = pytest.mark.gpu
 TOL64 = 1e-12
 
 
-def b200_rhs(case, n, **kw):
+# Backend variants: default (64-byte SoA, fused kernels), the wide layout
+# (fused element kernel does not fit -> individual kernels) and fusion off
+VARIANTS = {'default': {}, 'soa16': {'n-soa': 16}, 'nofuse': {'fusion': 0}}
+
+
+def b200_rhs(case, n, opts={}, **kw):
     from pyfr_b200.backend import B200Backend
 
     cfg, box = cases.make(case, n, **kw)
+    for k, v in opts.items():
+        cfg.set('backend-b200', k, v)
     be = B200Backend(cfg)
     sysm = get_system(be, box.local_mesh(), cfg, 2)
     sysm.rhs(0.0, 0, 1)
@@ -33,14 +40,22 @@ def b200_rhs(case, n, **kw):
     dict(order=2, beta=-0.5), dict(order=3, rsolver='hllc'), dict(order=4),
     dict(order=4, rsolver='hllc')
 ], ids=str)
-def test_tgv_rhs_matches_oracle(built, kw):
+@pytest.mark.parametrize('variant', list(VARIANTS))
+def test_tgv_rhs_matches_oracle(built, kw, variant):
     n = (5, 4, 3)
     _, ref = oracle_rhs('tgv', n, warp=0.1, **kw)
     _, ext = oracle_rhs('tgv', n, warp=0.1, extended=True, **kw)
-    _, out = b200_rhs('tgv', n, warp=0.1, **kw)
+    sysm, out = b200_rhs('tgv', n, VARIANTS[variant], warp=0.1, **kw)
 
     assert out.shape == ref[0].shape
     assert_parity(out, ref[0], ext[0], TOL64)
+
+    kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
+             for w, k in g.plan if w == 'kernel']
+    if variant == 'default':
+        assert 'gradflux' in kinds and 'mul+negdivconf' in kinds
+    else:
+        assert 'gradflux' not in kinds
 
 
 @pytest.mark.parametrize('kw', [dict(order=3), dict(order=3, rsolver='hllc')],
@@ -48,7 +63,7 @@ def test_tgv_rhs_matches_oracle(built, kw):
 def test_vortex_rhs_matches_oracle(built, kw):
     _, ref = oracle_rhs('vortex', 12, **kw)
     _, ext = oracle_rhs('vortex', 12, extended=True, **kw)
-    _, out = b200_rhs('vortex', 12, **kw)
+    _, out = b200_rhs('vortex', 12, {}, **kw)
 
     assert_parity(out, ref[0], ext[0], TOL64)
 
