@@ -310,8 +310,8 @@ def main():
                            type(k).__name__)
             meta = (k.misc[0] if getattr(k, 'misc', None) and
                     isinstance(k.misc[0], dict) else {})
-            label = f'g{gi}.{i}:{name}' + (
-                f'[{meta["M"]}x{meta["K"]}]' if meta else '')
+            label = f'g{gi}.{i}:{getattr(k, "kind", None) or name}' + (
+                f'[{meta["M"]}x{meta["K"]}]' if 'M' in meta else '')
             kt[label] = {'ms': acc[j]/nrep,
                          'bytes': getattr(k, 'traffic', 0)}
 
