@@ -12,24 +12,36 @@ hands to ``Graph.group`` at ``:174-203``):
     tdivtpcorf        fout = (M1 - M3*M2) @ G
 
 ``G`` (``ndims*nupts`` rows) never leaves the SM: per element block the
-kernel reads ``u`` and the common solution, and writes only the gradients
-at the flux points and the partial divergence -- ``(2 nupts + nfpts +
+kernel reads ``u`` and the common solution and writes only the gradients at
+the flux points and the partial divergence -- ``(2 nupts + nfpts +
 ndims nfpts)*LD`` words instead of the ``~35 nupts*LD`` the unfused chain
 moves.
 
-Per block (sm_100a):
+How the operators are applied (sm_100a, FP64/FP32 FMA pipes):
 
-* ``u`` and ``ucomm`` arrive by TMA bulk copy; the copy of the *next*
-  block's ``ucomm`` is issued as soon as phase 1 has consumed the current
-  one and the next ``u`` as soon as the flux has been formed, so HBM reads
-  overlap the remaining phases;
-* operator phases: a thread owns one column and a set of output rows; rows
-  that read the same inputs (the points of one tensor-product line) are
-  produced together from registers, which cuts shared-memory reads ~3x;
-  operator constants are immediates;
-* pointwise phases: a thread owns one (point, element) pair, exactly the
+* The operators of tensor-product elements are unions of small dense
+  blocks: the rows belonging to one line of solution points read the same
+  few inputs with the *same* coefficients as every other line.  The
+  generator discovers this from the matrices alone: rows with identical
+  column support form a *group*; groups whose coefficient blocks agree (up
+  to a row/column permutation) form a *class*.  Each class becomes one
+  short loop whose coefficients are immediates and whose row indices come
+  from a small table, so the instruction footprint is a few KB instead of
+  the hundreds of KB of a fully unrolled product, every lane is busy
+  (lanes run over (group, column) pairs) and each input is read from
+  shared memory once per group instead of once per row.
+* ``(M1 - M3*M2)`` is block diagonal over lines in every direction, so the
+  divergence is formed by in-place line transforms of the flux followed by
+  one pass that sums the directions and streams the result to HBM.
+* ``u`` and ``ucomm`` arrive by TMA bulk copy.  Both buffers are dead once
+  phase 1 has run (each thread keeps the few ``u`` values its flux points
+  need in registers), so the copies for the *next* block are issued right
+  then and overlap phases 2-5.
+* pointwise phases: a thread owns (point, element) pairs -- exactly the
   arithmetic of the stand-alone ``gradcoru``/``tflux`` kernels.
 """
+
+import itertools as it
 
 import numpy as np
 
@@ -37,40 +49,102 @@ from pyfr_b200.kernels import physics as ph
 from pyfr_b200.kernels.mul import _pipeline_src
 
 
+class NotFusable(Exception):
+    pass
+
+
 def _support(A, m):
     return tuple(np.flatnonzero(A[m]))
 
 
-def _row_groups(terms, rows, smax=10):
-    """Partition ``rows`` into groups reading identical inputs (across all
-    terms); rows with a large or unique support stay on their own."""
-    groups = {}
+def _row_groups(terms, rows, smax=16):
+    """Partition ``rows`` into groups whose inputs are contained in one
+    common small input set (per term).  Rows are absorbed into the group
+    with the smallest covering support, so a row with a structurally zero
+    coefficient still joins its line."""
+    sups = {m: tuple(frozenset(_support(A, m)) for A in terms) for m in rows}
+    order = sorted(rows, key=lambda m: -sum(len(s) for s in sups[m]))
+    groups = []            # [support per term, rows]
 
-    for m in rows:
-        key = tuple(_support(A, m) for A, _ in terms)
-        nsup = sum(len(s) for s in key)
-        if nsup > smax:
-            key = ('solo', m)
-        groups.setdefault(key, []).append(m)
+    for m in order:
+        if sum(len(s) for s in sups[m]) > smax:
+            groups.append([sups[m], [m]])
+            continue
 
-    return list(groups.values())
+        fits = [g for g in groups
+                if all(a <= b for a, b in zip(sups[m], g[0]))]
+        if fits:
+            min(fits, key=lambda g: sum(len(s) for s in g[0]))[1].append(m)
+        else:
+            groups.append([sups[m], [m]])
+
+    return [sorted(g[1]) for g in groups]
 
 
-def _balance(groups, R, cost):
-    """Longest-processing-time assignment of groups to R bins."""
-    bins, load = [[] for _ in range(R)], [0]*R
+def _canonical(blocks):
+    """Canonical form of a group's coefficient blocks under a common row
+    permutation and independent column permutations.  Returns
+    (key, row order, [column order per block])."""
+    n = blocks[0].shape[0]
+    perms = it.permutations(range(n)) if n <= 6 else [tuple(range(n))]
+    best = None
 
-    for g in sorted(groups, key=cost, reverse=True):
-        i = load.index(min(load))
-        bins[i].append(g)
-        load[i] += cost(g)
+    for perm in perms:
+        cols, parts = [], []
+        for B in blocks:
+            Bp = B[list(perm)]
+            order = sorted(range(B.shape[1]), key=lambda j: tuple(Bp[:, j]))
+            cols.append(order)
+            parts.append(Bp[:, order])
 
-    return bins
+        key = tuple(tuple(P.ravel()) for P in parts)
+        if best is None or key < best[0]:
+            best = (key, perm, cols)
+
+    return best
+
+
+class OpClass:
+    """Groups sharing one coefficient pattern."""
+
+    def __init__(self, nout, nins, coefs):
+        self.nout, self.nins, self.coefs = nout, nins, coefs
+        self.members = []       # (out rows, [input rows per term])
+
+
+def build_classes(terms, max_classes=24):
+    """Decompose ``out = sum_t A_t @ src_t`` into line classes."""
+    M = terms[0].shape[0]
+    classes = {}
+
+    for g in _row_groups(terms, range(M)):
+        sups = [sorted(set().union(*[_support(A, m) for m in g]))
+                for A in terms]
+        blocks = [A[np.ix_(g, s)] for A, s in zip(terms, sups)]
+        key, perm, cols = _canonical(blocks)
+
+        rows = [g[i] for i in perm]
+        ins = [[s[j] for j in order] for s, order in zip(sups, cols)]
+
+        sig = (len(g), tuple(len(s) for s in sups), key)
+        if sig not in classes:
+            coefs = [B[list(perm)][:, order]
+                     for B, order in zip(blocks, cols)]
+            classes[sig] = OpClass(len(g), [len(s) for s in sups], coefs)
+
+        classes[sig].members.append((rows, ins))
+
+    if len(classes) > max_classes:
+        raise NotFusable(f'{len(classes)} operator classes')
+
+    return list(classes.values())
 
 
 def _fma_chain(pairs, acc=None):
     expr = acc
     for a, x in pairs:
+        if a == 0:
+            continue
         if expr is None:
             expr = f'{ph.fpconst(a)}*{x}'
         else:
@@ -78,86 +152,84 @@ def _fma_chain(pairs, acc=None):
     return expr or 'FP(0.0)'
 
 
-def emit_grouped(terms, R, store, LD):
-    """Single-pass operator phase: every output row is finished inside the
-    group that owns its inputs.  ``terms`` = [(A, smem array name)];
-    ``store(m, expr)`` renders the store of output row ``m``."""
-    M = terms[0][0].shape[0]
-    groups = _row_groups(terms, range(M))
-    cost = lambda g: sum(len(_support(A, g[0])) for A, _ in terms) + sum(
-        int(np.count_nonzero(A[m])) for A, _ in terms for m in g)
-    bins = _balance(groups, R, cost)
+class PhaseEmitter:
+    """Renders class loops and collects their index tables."""
 
-    cases = []
-    for rg, gl in enumerate(bins):
-        lines = []
-        for g in gl:
-            lines.append('{')
-            regs = {}
-            for ti, (A, src) in enumerate(terms):
-                sup = sorted(set().union(*[_support(A, m) for m in g]))
-                for k in sup:
-                    regs[ti, k] = f'x{ti}_{k}'
-                    lines.append(f'const fpdtype_t x{ti}_{k} = '
-                                 f'{src}[{k*LD} + col];')
-            for m in g:
-                pairs = [(A[m, k], regs[ti, k])
-                         for ti, (A, _) in enumerate(terms)
-                         for k in _support(A, m)]
-                lines.append(store(m, _fma_chain(pairs)))
-            lines.append('}')
+    def __init__(self, LD):
+        self.LD = LD
+        self.tables = []
 
-        cases.append(f'        case {rg}:\n            ' +
-                     '\n            '.join(lines) + '\n            break;')
+    def emit(self, tag, classes, srcs, store, inplace=False):
+        """``srcs[t]``: expression of the array term ``t`` reads;
+        ``store(ixexpr, val)``: renders a store at element offset
+        ``ixexpr + col``."""
+        LD, out = self.LD, []
 
-    return ('        switch (rg)\n        {\n' + '\n'.join(cases) +
-            '\n        }\n')
+        for ci, c in enumerate(classes):
+            nidx = (0 if inplace else c.nout) + sum(c.nins)
+            tab = []
+            for rows, ins in c.members:
+                ent = [] if inplace else [r*LD for r in rows]
+                for s in ins:
+                    ent += [k*LD for k in s]
+                tab.append(ent)
 
+                if inplace and not set(rows) <= set(ins[0]):
+                    raise NotFusable('in-place transform needs rows within '
+                                     'inputs')
 
-def emit_accum(blocks, R, store, LD):
-    """Operator phase whose rows gather from several column blocks
-    (``blocks`` = [(A_d, smem name, row offset)]); a thread owns a
-    contiguous run of rows, keeps their partial sums in registers and
-    shares the loads of rows lying on one line of a block."""
-    M = blocks[0][0].shape[0]
-    bounds = np.linspace(0, M, R + 1).astype(int)
+            name = f'tab_{tag}_{ci}'
+            flat = ', '.join(str(v) for e in tab for v in e)
+            self.tables.append(f'static __device__ const int '
+                               f'{name}[{len(tab)*nidx}] = {{{flat}}};')
 
-    cases = []
-    for rg in range(R):
-        rows = list(range(bounds[rg], bounds[rg + 1]))
-        lines = [f'fpdtype_t a{j} = FP(0.0);' for j in range(len(rows))]
+            L = [f'for (int item = tid; item < {len(tab)}*LD; '
+                 'item += NTHREADS)', '{',
+                 '    const int g = item / LD, col = item - g*LD;',
+                 f'    const int *ix = {name} + g*{nidx};']
 
-        for bi, (A, src, off) in enumerate(blocks):
-            for g in _row_groups([(A, src)], rows):
-                sup = sorted(set().union(*[_support(A, m) for m in g]))
-                if not sup:
-                    continue
-                lines.append('{')
-                for k in sup:
-                    lines.append(f'const fpdtype_t x{k} = '
-                                 f'{src}[{(off + k)*LD} + col];')
-                for m in g:
-                    j = rows.index(m)
-                    pairs = [(A[m, k], f'x{k}') for k in _support(A, m)]
-                    lines.append(f'a{j} = {_fma_chain(pairs, f"a{j}")};')
-                lines.append('}')
+            base = 0 if inplace else c.nout
+            regs, off = [], base
+            for t, n in enumerate(c.nins):
+                for j in range(n):
+                    L.append(f'    const int i{t}_{j} = __ldg(ix + {off + j})'
+                             ' + col;')
+                    L.append(f'    const fpdtype_t x{t}_{j} = '
+                             f'{srcs[t]}[i{t}_{j}];')
+                regs.append([f'x{t}_{j}' for j in range(n)])
+                off += n
 
-        lines += [store(m, f'a{j}') for j, m in enumerate(rows)]
-        cases.append(f'        case {rg}:\n            {{\n            ' +
-                     '\n            '.join(lines) +
-                     '\n            }\n            break;')
+            for i in range(c.nout):
+                pairs = [(c.coefs[t][i, j], regs[t][j])
+                         for t in range(len(c.nins))
+                         for j in range(c.nins[t])]
+                val = _fma_chain(pairs)
 
-    return ('        switch (rg)\n        {\n' + '\n'.join(cases) +
-            '\n        }\n')
+                if inplace:
+                    # Output row i lives where the same point's input was
+                    rows0, ins0 = c.members[0]
+                    j = ins0[0].index(rows0[i])
+                    if any(ins[0].index(rows[i]) != j
+                           for rows, ins in c.members):
+                        raise NotFusable('inconsistent in-place slots')
+                    L.append('    ' + store(f'i0_{j} - col', val))
+                else:
+                    L.append('    ' + store(f'__ldg(ix + {i})', val))
+
+            L.append('}')
+            out.append('\n        '.join(L))
+
+        return '\n        '.join(out)
 
 
-def gradflux_source(be, ops, tplargs, pts, LD, R=None):
+def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     """Source of the fused kernel.
 
     ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
     ``M6`` (ndims*nupts x nfpts), ``M0`` (nfpts x nupts) and ``A5``
     (nupts x ndims*nupts); ``tplargs``: the tflux template arguments
-    (``ktype`` is 'linear' or 'curved')."""
+    (``ktype`` is 'linear' or 'curved').  Raises ``NotFusable`` when the
+    operators lack the line structure the kernel relies on."""
     nd, nv = tplargs['ndims'], tplargs['nvars']
     A1, M6, M0, A5 = (np.asarray(ops[k], dtype=float)
                       for k in ('A1', 'M6', 'M0', 'A5'))
@@ -165,35 +237,42 @@ def gradflux_source(be, ops, tplargs, pts, LD, R=None):
     isz = np.dtype(be.fpdtype).itemsize
     csub = be.csubsz
 
-    assert A1.shape == (nd*nu, nu) and M6.shape == (nd*nu, nf)
-    assert A5.shape == (nu, nd*nu) and LD == nv*csub
+    if A1.shape != (nd*nu, nu) or M6.shape != (nd*nu, nf) or \
+       A5.shape != (nu, nd*nu) or LD != nv*csub:
+        raise NotFusable('unexpected operator shapes')
 
-    wpr = -(-LD // 32)
-    R = R or max(1, min(8, 16 // wpr))
-    nthreads = 32*wpr*R
     linear = 'linear' in tplargs['ktype']
+    npoints = nu*csub
+    nrounds = -(-npoints // nthreads)
 
     smem = (nu + nf + nd*nu)*LD*isz + 64
     defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
             ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
-            ('LD', LD), ('NTHREADS', nthreads)]
+            ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds)]
     defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
                                True)
 
+    em = PhaseEmitter(LD)
+
     # Phase 1: G = A1 @ U + M6 @ C
-    p1 = emit_grouped([(A1, 'U'), (M6, 'C')], R,
-                      lambda m, e: f'G[{m*LD} + col] = {e};', LD)
+    p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
+                 lambda ix, v: f'G[{ix} + col] = {v};')
 
     # Phase 3: vect_fpts[d] = M0 @ G[d]
     M0d = np.zeros((nd*nf, nd*nu))
     for d in range(nd):
         M0d[d*nf:(d + 1)*nf, d*nu:(d + 1)*nu] = M0
-    p3 = emit_grouped([(M0d, 'G')], R,
-                      lambda m, e: f'vf[vfb + {m*LD} + col] = {e};', LD)
+    p3 = em.emit('p3', build_classes([M0d]), ['G'],
+                 lambda ix, v: f'vf[vfb + {ix} + col] = {v};')
 
-    # Phase 5: fout = A5 @ G, one column block per direction
-    p5 = emit_accum([(A5[:, d*nu:(d + 1)*nu], 'G', d*nu) for d in range(nd)],
-                    R, lambda m, e: f'fout[fob + {m*LD} + col] = {e};', LD)
+    # Phase 5: in-place line transforms of the flux, direction by
+    # direction (block d of A5 acts on rows d*nu.. of G), then the sum
+    A5d = np.zeros((nd*nu, nd*nu))
+    for d in range(nd):
+        A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
+    p5 = em.emit('p5', build_classes([A5d]), ['G'],
+                 lambda ix, v: f'G[{ix} + col] = {v};', inplace=True)
+    psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
 
     if linear:
         gsrc = ph.linear_smats_src(nd, tplargs['nverts'],
@@ -230,6 +309,8 @@ def gradflux_source(be, ops, tplargs, pts, LD, R=None):
                                               + p*C_SUB + e);
 '''
 
+    tables = '\n'.join(em.tables)
+
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz, defs)}
 {_pipeline_src}
@@ -237,6 +318,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, R=None):
 {ph.visc_src}
 {ph.geom_src}
 {gsrc}
+{tables}
 
 #define U_WORDS (NPTS*LD)
 #define C_WORDS (NFPTS*LD)
@@ -258,27 +340,25 @@ gradflux(int nblocks, int neles,
         reinterpret_cast<unsigned long long *>(G + G_WORDS);
 
     const int tid = threadIdx.x;
-    const int col = tid % {32*wpr}, rg = tid / {32*wpr};
-    const bool active = col < LD;
 
     if (tid == 0)
     {{
         mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }}
     __syncthreads();
 
-    long long blk = blockIdx.x;
-
-    if (tid == 0 && blk < nblocks)
+    auto fetch = [&](long long b)
     {{
-        mbar_expect_tx(&bars[0], U_WORDS*sizeof(fpdtype_t));
-        tma_load_1d(U, u + blk*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
-        mbar_expect_tx(&bars[1], C_WORDS*sizeof(fpdtype_t));
-        tma_load_1d(C, ucomm + blk*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
-                    &bars[1]);
-    }}
+        mbar_expect_tx(&bars[0], (U_WORDS + C_WORDS)*sizeof(fpdtype_t));
+        tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
+        tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
+                    &bars[0]);
+    }};
+
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < nblocks)
+        fetch(blk);
 
     for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
     {{
@@ -286,22 +366,28 @@ gradflux(int nblocks, int neles,
         const long long vfb = blk*vf_bsz, fob = blk*fout_bsz;
 
         mbar_wait(&bars[0], it & 1);
-        mbar_wait(&bars[1], it & 1);
 
         // ---- phase 1: corrected transformed gradient ------------------
-        if (active)
+        {p1}
+
+        // Keep the solution at this thread's flux-evaluation points
+        fpdtype_t ureg[NROUNDS][NVARS];
+        UNROLL for (int r = 0; r < NROUNDS; r++)
         {{
-{p1}
+            const int item = tid + r*NTHREADS;
+            if (item < NPTS*C_SUB)
+            {{
+                const int e = item % C_SUB, p = item / C_SUB;
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    ureg[r][v] = U[p*LD + COFF(e, v, NVARS)];
+            }}
         }}
         __syncthreads();
 
-        // ucomm consumed: fetch the next block's while we carry on
+        // u and ucomm are consumed: fetch the next block's behind the
+        // remaining phases
         if (tid == 0 && nxt < nblocks)
-        {{
-            mbar_expect_tx(&bars[1], C_WORDS*sizeof(fpdtype_t));
-            tma_load_1d(C, ucomm + nxt*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
-                        &bars[1]);
-        }}
+            fetch(nxt);
 
         // ---- phase 2: physical gradient (in place) ---------------------
         for (int item = tid; item < NPTS*C_SUB; item += NTHREADS)
@@ -324,56 +410,46 @@ gradflux(int nblocks, int neles,
         __syncthreads();
 
         // ---- phase 3: gradients at the flux points -> HBM ---------------
-        if (active)
-        {{
-{p3}
-        }}
+        {p3}
         __syncthreads();
 
         // ---- phase 4: transformed flux (in place over the gradient) -----
-        for (int item = tid; item < NPTS*C_SUB; item += NTHREADS)
+        UNROLL for (int r = 0; r < NROUNDS; r++)
         {{
+            const int item = tid + r*NTHREADS;
             const int e = item % C_SUB, p = item / C_SUB;
-            if (blk*C_SUB + e >= neles)
-                continue;
+            if (item < NPTS*C_SUB && blk*C_SUB + e < neles)
+            {{
 {geom}
-            (void) rcpdjac_v;
-            fpdtype_t us[NVARS], g[NDIMS][NVARS];
-            UNROLL for (int v = 0; v < NVARS; v++)
-                us[v] = U[p*LD + COFF(e, v, NVARS)];
-            UNROLL for (int d = 0; d < NDIMS; d++)
-                UNROLL for (int v = 0; v < NVARS; v++)
-                    g[d][v] = G[(d*NPTS + p)*LD + COFF(e, v, NVARS)];
+                (void) rcpdjac_v;
+                fpdtype_t g[NDIMS][NVARS];
+                UNROLL for (int d = 0; d < NDIMS; d++)
+                    UNROLL for (int v = 0; v < NVARS; v++)
+                        g[d][v] = G[(d*NPTS + p)*LD + COFF(e, v, NVARS)];
 
-            fpdtype_t ft[NDIMS][NVARS], fo[NDIMS][NVARS], pr, vel[NDIMS];
-            inviscid_flux(us, ft, pr, vel);
-            viscous_flux_add(us, g, ft);
-            transform_flux(ft, s, fo);
+                fpdtype_t ft[NDIMS][NVARS], fo[NDIMS][NVARS], pr, vel[NDIMS];
+                inviscid_flux(ureg[r], ft, pr, vel);
+                viscous_flux_add(ureg[r], g, ft);
+                transform_flux(ft, s, fo);
 
-            UNROLL for (int d = 0; d < NDIMS; d++)
-                UNROLL for (int v = 0; v < NVARS; v++)
-                    G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = fo[d][v];
+                UNROLL for (int d = 0; d < NDIMS; d++)
+                    UNROLL for (int v = 0; v < NVARS; v++)
+                        G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = fo[d][v];
+            }}
         }}
         __syncthreads();
 
-        // u consumed: fetch the next block's
-        if (tid == 0 && nxt < nblocks)
-        {{
-            mbar_expect_tx(&bars[0], U_WORDS*sizeof(fpdtype_t));
-            tma_load_1d(U, u + nxt*u_bsz, U_WORDS*sizeof(fpdtype_t),
-                        &bars[0]);
-        }}
+        // ---- phase 5: divergence: line transforms, then the sum -> HBM ---
+        {p5}
+        __syncthreads();
 
-        // ---- phase 5: divergence of the discontinuous flux -> HBM --------
-        if (active)
-        {{
-{p5}
-        }}
+        for (int item = tid; item < NPTS*LD; item += NTHREADS)
+            fout[fob + item] = {psum};
         __syncthreads();
     }}
 }}
 '''
-    meta = dict(nthreads=nthreads, smem=smem, R=R,
+    meta = dict(nthreads=nthreads, smem=smem,
                 words_per_block=(2*nu + nf + nd*nf)*LD)
 
     return src, 'gradflux', meta
