@@ -56,7 +56,8 @@ def test_tgv_rhs_matches_oracle(built, kw, variant):
         assert 'gradflux' in kinds and 'mul+negdivconf' in kinds
         assert 'copy' not in kinds
     elif variant == 'nofuse':
-        assert 'gradflux' not in kinds and 'copy' in kinds
+        assert 'gradflux' not in kinds
+        assert ('copy' in kinds) == (abs(kw.get('beta', 0.5)) == 0.5)
     elif kw['order'] == 4:
         # 16-wide fp64 blocks at p=4 do not fit the fused kernel's smem
         assert 'gradflux' not in kinds
