@@ -50,6 +50,8 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--opt', action='append', default=[],
+                    help='backend option key=value ([backend-b200])')
     ap.add_argument('--kernel-times', default=None, help='write the '
                     'per-kernel event timings to this JSON file')
     return ap.parse_args()
@@ -216,6 +218,9 @@ def main():
     cfg.set('backend-b200', 'device-id', lrank)
     if args.no_graphs:
         cfg.set('backend-b200', 'graphs', 'false')
+    for kv in args.opt:
+        k, v = kv.split('=', 1)
+        cfg.set('backend-b200', k, v)
 
     be = B200Backend(cfg)
     rt = be.rt

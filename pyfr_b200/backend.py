@@ -64,6 +64,7 @@ class B200Backend(base.BaseBackend):
             raise ValueError('n-csub must be a multiple of n-soa')
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
+        self.cflux_minblocks = cfg.getint(sect, 'cflux-minblocks', 5)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

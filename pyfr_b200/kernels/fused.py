@@ -153,11 +153,42 @@ def _fma_chain(pairs, acc=None):
 
 
 class PhaseEmitter:
-    """Renders class loops and collects their index tables."""
+    """Renders class loops and collects their index tables.
+
+    Row offsets (``row*LD``) are stored as 16-bit values, eight to a
+    16-byte record, and staged in shared memory once per CTA, so a work
+    item fetches all its indices with one or two 128-bit loads."""
 
     def __init__(self, LD):
         self.LD = LD
-        self.tables = []
+        self.tables = []        # (name, flat list of uint16)
+
+    @property
+    def table_bytes(self):
+        return sum(2*len(t) for _, t in self.tables)
+
+    def decls(self):
+        out = []
+        for name, vals in self.tables:
+            flat = ', '.join(map(str, vals))
+            out.append(f'static __device__ const unsigned short '
+                       f'g_{name}[{len(vals)}] = {{{flat}}};')
+        return '\n'.join(out)
+
+    def smem_layout(self, base):
+        """Carve the staged tables out of the smem pointer ``base``."""
+        out, off = [], 0
+        for name, vals in self.tables:
+            out.append(f'unsigned short *{name} = reinterpret_cast<unsigned '
+                       f'short *>({base}) + {off};')
+            off += len(vals)
+        return '\n    '.join(out)
+
+    def stage(self):
+        return '\n    '.join(
+            f'for (int i = tid; i < {len(v)}; i += NTHREADS) '
+            f'{n}[i] = g_{n}[i];' for n, v in self.tables
+        )
 
     def emit(self, tag, classes, srcs, store, inplace=False):
         """``srcs[t]``: expression of the array term ``t`` reads;
@@ -167,33 +198,45 @@ class PhaseEmitter:
 
         for ci, c in enumerate(classes):
             nidx = (0 if inplace else c.nout) + sum(c.nins)
+            npad = -(-nidx // 8)*8
             tab = []
+
             for rows, ins in c.members:
                 ent = [] if inplace else [r*LD for r in rows]
                 for s in ins:
                     ent += [k*LD for k in s]
-                tab.append(ent)
 
+                if max(ent) > 65535:
+                    raise NotFusable('row offset exceeds 16 bits')
                 if inplace and not set(rows) <= set(ins[0]):
                     raise NotFusable('in-place transform needs rows within '
                                      'inputs')
 
-            name = f'tab_{tag}_{ci}'
-            flat = ', '.join(str(v) for e in tab for v in e)
-            self.tables.append(f'static __device__ const int '
-                               f'{name}[{len(tab)*nidx}] = {{{flat}}};')
+                tab += ent + [0]*(npad - nidx)
 
-            L = [f'for (int item = tid; item < {len(tab)}*LD; '
+            name = f'tab_{tag}_{ci}'
+            self.tables.append((name, tab))
+
+            L = [f'for (int item = tid; item < {len(c.members)}*LD; '
                  'item += NTHREADS)', '{',
-                 '    const int g = item / LD, col = item - g*LD;',
-                 f'    const int *ix = {name} + g*{nidx};']
+                 '    const int g = item / LD, col = item - g*LD;']
+
+            # Fetch the index record: npad/8 128-bit shared loads
+            for q in range(npad // 8):
+                L.append(f'    const uint4 q{q} = *reinterpret_cast<const '
+                         f'uint4 *>({name} + g*{npad} + {8*q});')
+
+            def idx(j):
+                w = 'xyzw'[(j % 8) // 2]
+                word = f'q{j // 8}.{w}'
+                return (f'(int) ({word} >> 16)' if j % 2 else
+                        f'(int) ({word} & 0xffffu)')
 
             base = 0 if inplace else c.nout
             regs, off = [], base
             for t, n in enumerate(c.nins):
                 for j in range(n):
-                    L.append(f'    const int i{t}_{j} = __ldg(ix + {off + j})'
-                             ' + col;')
+                    L.append(f'    const int i{t}_{j} = {idx(off + j)} + col;')
                     L.append(f'    const fpdtype_t x{t}_{j} = '
                              f'{srcs[t]}[i{t}_{j}];')
                 regs.append([f'x{t}_{j}' for j in range(n)])
@@ -214,7 +257,7 @@ class PhaseEmitter:
                         raise NotFusable('inconsistent in-place slots')
                     L.append('    ' + store(f'i0_{j} - col', val))
                 else:
-                    L.append('    ' + store(f'__ldg(ix + {i})', val))
+                    L.append('    ' + store(idx(i), val))
 
             L.append('}')
             out.append('\n        '.join(L))
@@ -245,7 +288,6 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     npoints = nu*csub
     nrounds = -(-npoints // nthreads)
 
-    smem = (nu + nf + nd*nu)*LD*isz + 64
     defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
             ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
             ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds)]
@@ -277,23 +319,33 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     if linear:
         gsrc = ph.linear_smats_src(nd, tplargs['nverts'],
                                    tplargs['jac_exprs'])
-        rows = ', '.join('{' + ', '.join(ph.fpconst(v) for v in row) + '}'
-                         for row in pts)
-        gsrc = (f'static __device__ const fpdtype_t c_pts[{len(pts)}][{nd}]'
+        rows = ', '.join(ph.fpconst(v) for row in pts for v in row)
+        gsrc = (f'static __device__ const fpdtype_t c_pts[{len(pts)*nd}]'
                 f' = {{{rows}}};\n' + gsrc)
         gargs = 'const fpdtype_t* __restrict__ verts, long long verts_bsz'
         geom = r'''
             fpdtype_t V[NVERTS][NDIMS], x[NDIMS], s[NDIMS][NDIMS], djac;
             UNROLL for (int n = 0; n < NVERTS; n++)
                 UNROLL for (int i = 0; i < NDIMS; i++)
-                    V[n][i] = __ldg(verts + blk*verts_bsz + n*(NDIMS*C_SUB)
-                                    + COFF(e, i, NDIMS));
+                    V[n][i] = VS[n*(NDIMS*C_SUB) + COFF(e, i, NDIMS)];
             UNROLL for (int i = 0; i < NDIMS; i++)
-                x[i] = __ldg(&c_pts[p][i]);
+                x[i] = PTS[p*NDIMS + i];
             calc_smats_detj(V, x, s, djac);
             const fpdtype_t rcpdjac_v = FP(1.0)/djac;
 '''
+        geo_words = 2*tplargs['nverts']*nd*csub + nu*nd
+        geo_words += (-geo_words*isz // 16 * -16 - geo_words*isz)//isz
+        geo_decl = '''fpdtype_t *VSB = G + G_WORDS;
+    fpdtype_t *PTS = VSB + 2*V_WORDS;'''
+        geo_stage = '''for (int i = tid; i < NPTS*NDIMS; i += NTHREADS)
+        PTS[i] = c_pts[i];'''
+        geo_fetch = '''tma_load_1d(VSB + (n & 1)*V_WORDS, verts + b*verts_bsz,
+                    V_WORDS*sizeof(fpdtype_t), &bars[0]);'''
+        geo_bytes = ' + V_WORDS*sizeof(fpdtype_t)'
+        geo_blk = 'const fpdtype_t *VS = VSB + (it & 1)*V_WORDS;'
     else:
+        geo_words, geo_decl, geo_stage, geo_fetch = 0, '', '', ''
+        geo_bytes, geo_blk = '', ''
         gsrc = ''
         gargs = ('const fpdtype_t* __restrict__ smats, long long smats_bsz, '
                  'const fpdtype_t* __restrict__ rcpdjac, '
@@ -309,7 +361,12 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
                                               + p*C_SUB + e);
 '''
 
-    tables = '\n'.join(em.tables)
+    tables = em.decls()
+    data_words = (nu + nf + nd*nu) + 0
+    smem = (data_words*LD + geo_words)*isz + em.table_bytes + 64
+
+    if smem > be.smem_budget + 8*1024:
+        raise NotFusable(f'needs {smem} bytes of shared memory')
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz, defs)}
@@ -323,6 +380,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
 #define U_WORDS (NPTS*LD)
 #define C_WORDS (NFPTS*LD)
 #define G_WORDS (NDIMS*NPTS*LD)
+#define V_WORDS (NVERTS*NDIMS*C_SUB)
 
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
 gradflux(int nblocks, int neles,
@@ -336,10 +394,17 @@ gradflux(int nblocks, int neles,
     fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
     fpdtype_t *C = U + U_WORDS;
     fpdtype_t *G = C + C_WORDS;
-    unsigned long long *bars =
-        reinterpret_cast<unsigned long long *>(G + G_WORDS);
+    {geo_decl}
+    {em.smem_layout(f'G + G_WORDS + {geo_words}')}
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<unsigned char *>(G + G_WORDS + {geo_words})
+        + {-(-em.table_bytes // 16)*16});
 
     const int tid = threadIdx.x;
+
+    // Stage the index tables and the reference point set once per CTA
+    {em.stage()}
+    {geo_stage}
 
     if (tid == 0)
     {{
@@ -348,17 +413,19 @@ gradflux(int nblocks, int neles,
     }}
     __syncthreads();
 
-    auto fetch = [&](long long b)
+    auto fetch = [&](long long b, unsigned n)
     {{
-        mbar_expect_tx(&bars[0], (U_WORDS + C_WORDS)*sizeof(fpdtype_t));
+        mbar_expect_tx(&bars[0], (U_WORDS + C_WORDS)*sizeof(fpdtype_t)
+                                 {geo_bytes});
         tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
         tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
                     &bars[0]);
+        {geo_fetch}
     }};
 
     long long blk = blockIdx.x;
     if (tid == 0 && blk < nblocks)
-        fetch(blk);
+        fetch(blk, 0);
 
     for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
     {{
@@ -366,6 +433,7 @@ gradflux(int nblocks, int neles,
         const long long vfb = blk*vf_bsz, fob = blk*fout_bsz;
 
         mbar_wait(&bars[0], it & 1);
+        {geo_blk}
 
         // ---- phase 1: corrected transformed gradient ------------------
         {p1}
@@ -387,7 +455,7 @@ gradflux(int nblocks, int neles,
         // u and ucomm are consumed: fetch the next block's behind the
         // remaining phases
         if (tid == 0 && nxt < nblocks)
-            fetch(nxt);
+            fetch(nxt, it + 1);
 
         // ---- phase 2: physical gradient (in place) ---------------------
         for (int item = tid; item < NPTS*C_SUB; item += NTHREADS)

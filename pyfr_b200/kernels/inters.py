@@ -171,7 +171,8 @@ def cflux_source(be, tplargs, viscous, mpi):
 {ph.visc_src if viscous else ''}
 {ph.rsolve_src[tplargs['rsolver']]}
 
-extern "C" __global__ void __launch_bounds__(128)
+extern "C" __global__ void
+__launch_bounds__(128, {getattr(be, 'cflux_minblocks', 4) if viscous else 8})
 {name}({', '.join(args)})
 {{
 {_head}
