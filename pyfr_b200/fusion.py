@@ -97,10 +97,7 @@ def fuse_gradflux(be, kerns, subs):
     if VF.nrow != nd*nf or VF.leaddim != LD or FOUT.leaddim != LD:
         return None
 
-    # Shared memory: u + ucomm + G
     isz = U.itemsize
-    if (nu + nf + nd*nu)*LD*isz + 64 > be.smem_budget + 8*1024:
-        return None
 
     ops = dict(A1=i0['A'], M6=i1['A'], M0=M0, A5=i5['A'])
     out = []
@@ -209,7 +206,8 @@ def fuse_group(be, kerns, subs):
     for f in _group_fusers:
         try:
             new = f(be, kerns, subs)
-        except (KeyError, AttributeError, AssertionError):
+        except (KeyError, AttributeError, AssertionError,
+                kfused.NotFusable):
             new = None
 
         if new:
