@@ -140,47 +140,71 @@ def build_classes(terms, max_classes=24):
     return list(classes.values())
 
 
-def _fma_chain(pairs, acc=None):
+class ConstPool:
+    """Operator coefficients.  A 64-bit immediate cannot be encoded in a
+    DFMA, so literals cost two uniform-register moves per use; placed in
+    ``__constant__`` memory they become constant-bank operands of the FMA
+    itself.  fp32 coefficients stay literals (FFMA takes a 32-bit
+    immediate)."""
+
+    def __init__(self, use_table):
+        self.use_table, self.vals = use_table, {}
+
+    def __call__(self, a):
+        a = float(a)
+        if not self.use_table:
+            return ph.fpconst(a)
+        return f'KC[{self.vals.setdefault(a, len(self.vals))}]'
+
+    def decl(self):
+        if not self.vals:
+            return ''
+        body = ', '.join(ph.fpconst(v) for v in self.vals)
+        return f'__constant__ fpdtype_t KC[{len(self.vals)}] = {{{body}}};'
+
+
+def _fma_chain(pairs, K, acc=None):
     expr = acc
     for a, x in pairs:
         if a == 0:
             continue
         if expr is None:
-            expr = f'{ph.fpconst(a)}*{x}'
+            expr = f'{K(a)}*{x}'
         else:
-            expr = f'fma({ph.fpconst(a)}, {x}, {expr})'
+            expr = f'fma({K(a)}, {x}, {expr})'
     return expr or 'FP(0.0)'
 
 
 class PhaseEmitter:
     """Renders class loops and collects their index tables.
 
-    Row offsets (``row*LD``) are stored as 16-bit values, eight to a
-    16-byte record, and staged in shared memory once per CTA, so a work
-    item fetches all its indices with one or two 128-bit loads."""
+    Table entries are byte offsets (``row*LD*sizeof``) held as 32-bit
+    integers, four to a 16-byte record, staged in shared memory once per
+    CTA: a work item fetches its indices with a few 128-bit loads and
+    forms every address with a single add."""
 
-    def __init__(self, LD):
-        self.LD = LD
-        self.tables = []        # (name, flat list of uint16)
+    def __init__(self, LD, itemsize, K):
+        self.LD, self.isz, self.K = LD, itemsize, K
+        self.tables = []        # (name, flat list of ints)
 
     @property
     def table_bytes(self):
-        return sum(2*len(t) for _, t in self.tables)
+        return sum(4*len(t) for _, t in self.tables)
 
     def decls(self):
         out = []
         for name, vals in self.tables:
             flat = ', '.join(map(str, vals))
-            out.append(f'static __device__ const unsigned short '
-                       f'g_{name}[{len(vals)}] = {{{flat}}};')
+            out.append(f'static __device__ const int g_{name}[{len(vals)}] '
+                       f'= {{{flat}}};')
         return '\n'.join(out)
 
     def smem_layout(self, base):
         """Carve the staged tables out of the smem pointer ``base``."""
         out, off = [], 0
         for name, vals in self.tables:
-            out.append(f'unsigned short *{name} = reinterpret_cast<unsigned '
-                       f'short *>({base}) + {off};')
+            out.append(f'int *{name} = reinterpret_cast<int *>({base}) + '
+                       f'{off};')
             off += len(vals)
         return '\n    '.join(out)
 
@@ -191,23 +215,20 @@ class PhaseEmitter:
         )
 
     def emit(self, tag, classes, srcs, store, inplace=False):
-        """``srcs[t]``: expression of the array term ``t`` reads;
-        ``store(ixexpr, val)``: renders a store at element offset
-        ``ixexpr + col``."""
-        LD, out = self.LD, []
+        """``srcs[t]``: name of the (shared) array term ``t`` reads;
+        ``store(byte offset expr, val)`` renders a store."""
+        LD, isz, K, out = self.LD, self.isz, self.K, []
 
         for ci, c in enumerate(classes):
             nidx = (0 if inplace else c.nout) + sum(c.nins)
-            npad = -(-nidx // 8)*8
+            npad = -(-nidx // 4)*4
             tab = []
 
             for rows, ins in c.members:
-                ent = [] if inplace else [r*LD for r in rows]
-                for s in ins:
-                    ent += [k*LD for k in s]
+                ent = [] if inplace else [r*LD*isz for r in rows]
+                for sidx in ins:
+                    ent += [k*LD*isz for k in sidx]
 
-                if max(ent) > 65535:
-                    raise NotFusable('row offset exceeds 16 bits')
                 if inplace and not set(rows) <= set(ins[0]):
                     raise NotFusable('in-place transform needs rows within '
                                      'inputs')
@@ -219,26 +240,24 @@ class PhaseEmitter:
 
             L = [f'for (int item = tid; item < {len(c.members)}*LD; '
                  'item += NTHREADS)', '{',
-                 '    const int g = item / LD, col = item - g*LD;']
+                 '    const int g = item / LD;',
+                 f'    const int cb = (item - g*LD)*{isz};']
 
-            # Fetch the index record: npad/8 128-bit shared loads
-            for q in range(npad // 8):
-                L.append(f'    const uint4 q{q} = *reinterpret_cast<const '
-                         f'uint4 *>({name} + g*{npad} + {8*q});')
+            for q in range(npad // 4):
+                L.append(f'    const int4 q{q} = *reinterpret_cast<const '
+                         f'int4 *>({name} + g*{npad} + {4*q});')
 
-            def idx(j):
-                w = 'xyzw'[(j % 8) // 2]
-                word = f'q{j // 8}.{w}'
-                return (f'(int) ({word} >> 16)' if j % 2 else
-                        f'(int) ({word} & 0xffffu)')
+            idx = lambda j: f'q{j // 4}.{"xyzw"[j % 4]}'
+            at = lambda arr, off: (f'*reinterpret_cast<fpdtype_t *>('
+                                   f'reinterpret_cast<char *>({arr}) + {off})')
 
             base = 0 if inplace else c.nout
             regs, off = [], base
             for t, n in enumerate(c.nins):
                 for j in range(n):
-                    L.append(f'    const int i{t}_{j} = {idx(off + j)} + col;')
+                    L.append(f'    const int i{t}_{j} = {idx(off + j)} + cb;')
                     L.append(f'    const fpdtype_t x{t}_{j} = '
-                             f'{srcs[t]}[i{t}_{j}];')
+                             f'{at(srcs[t], f"i{t}_{j}")};')
                 regs.append([f'x{t}_{j}' for j in range(n)])
                 off += n
 
@@ -246,7 +265,7 @@ class PhaseEmitter:
                 pairs = [(c.coefs[t][i, j], regs[t][j])
                          for t in range(len(c.nins))
                          for j in range(c.nins[t])]
-                val = _fma_chain(pairs)
+                val = _fma_chain(pairs, K)
 
                 if inplace:
                     # Output row i lives where the same point's input was
@@ -255,9 +274,9 @@ class PhaseEmitter:
                     if any(ins[0].index(rows[i]) != j
                            for rows, ins in c.members):
                         raise NotFusable('inconsistent in-place slots')
-                    L.append('    ' + store(f'i0_{j} - col', val))
+                    L.append('    ' + store(f'i0_{j}', val, at))
                 else:
-                    L.append('    ' + store(idx(i), val))
+                    L.append('    ' + store(f'{idx(i)} + cb', val, at))
 
             L.append('}')
             out.append('\n        '.join(L))
@@ -294,18 +313,19 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
                                True)
 
-    em = PhaseEmitter(LD)
+    K = ConstPool(isz == 8)
+    em = PhaseEmitter(LD, isz, K)
 
     # Phase 1: G = A1 @ U + M6 @ C
     p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
-                 lambda ix, v: f'G[{ix} + col] = {v};')
+                 lambda off, v, at: f'{at("G", off)} = {v};')
 
     # Phase 3: vect_fpts[d] = M0 @ G[d]
     M0d = np.zeros((nd*nf, nd*nu))
     for d in range(nd):
         M0d[d*nf:(d + 1)*nf, d*nu:(d + 1)*nu] = M0
     p3 = em.emit('p3', build_classes([M0d]), ['G'],
-                 lambda ix, v: f'vf[vfb + {ix} + col] = {v};')
+                 lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};')
 
     # Phase 5: in-place line transforms of the flux, direction by
     # direction (block d of A5 acts on rows d*nu.. of G), then the sum
@@ -313,7 +333,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     for d in range(nd):
         A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
     p5 = em.emit('p5', build_classes([A5d]), ['G'],
-                 lambda ix, v: f'G[{ix} + col] = {v};', inplace=True)
+                 lambda off, v, at: f'{at("G", off)} = {v};', inplace=True)
     psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
 
     if linear:
@@ -376,6 +396,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
 {ph.geom_src}
 {gsrc}
 {tables}
+{K.decl()}
 
 #define U_WORDS (NPTS*LD)
 #define C_WORDS (NFPTS*LD)
@@ -398,7 +419,7 @@ gradflux(int nblocks, int neles,
     {em.smem_layout(f'G + G_WORDS + {geo_words}')}
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         reinterpret_cast<unsigned char *>(G + G_WORDS + {geo_words})
-        + {-(-em.table_bytes // 16)*16});
+        + {em.table_bytes});
 
     const int tid = threadIdx.x;
 
