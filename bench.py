@@ -50,6 +50,8 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--no-clocks', action='store_true', help='skip the '
+                    'nvidia-smi sampling load (for runs under ncu)')
     ap.add_argument('--opt', action='append', default=[],
                     help='backend option key=value ([backend-b200])')
     ap.add_argument('--kernel-times', default=None, help='write the '
@@ -63,23 +65,28 @@ def bricks(nparts):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region."""
+    """nvidia-smi clock / throttle sampling while the GPU is under the
+    benchmark's load (the profiling recipe's clocks line).  Rows are
+    time-stamped on arrival; ``stop`` summarises those that fall inside
+    the load window opened by ``mark``."""
 
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, period_ms=50):
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.period_ms, self.t0 = period_ms, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.Q}',
-                 '--format=csv,noheader,nounits', '-lms', '100', '-i',
-                 str(self.gpu)], stdout=subprocess.PIPE,
+                 '--format=csv,noheader,nounits', '-lms', str(self.period_ms),
+                 '-i', str(self.gpu)], stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL, text=True
             )
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -89,26 +96,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(),
+                              [c.strip() for c in line.split(',')]))
+
+    def mark(self):
+        self.t0 = time.time()
+
+    def nsamples(self):
+        return sum(1 for t, r in self.rows if self.t0 and t >= self.t0)
 
     def stop(self):
         if self.proc is None:
             return None
 
-        time.sleep(0.15)
+        t1 = time.time()
+        time.sleep(0.1)
         self.proc.terminate()
         self.t.join(timeout=2)
 
-        sm, smax, reasons = [], [], set()
+        sm, smax, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.t0 is None or not (self.t0 <= t <= t1 + 0.05):
+                continue
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
+                pw.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
-            for nm, v in zip(names, r[4:8]):
+            for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(nm)
 
@@ -116,7 +134,8 @@ class ClockSampler:
             return None
 
         return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(smax),
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm),
+                'power_w_max': max(pw)}
 
 
 def cpu_baseline(args):
@@ -273,21 +292,34 @@ def main():
     step = lambda: sysm.rhs(0.0, 0, 1)
 
     # ---- device-resident throughput --------------------------------------
+    sampler = ClockSampler(lrank)
+    if rank == 0 and not args.no_clocks:
+        sampler.start()
+
     for _ in range(max(args.warmup, 3)):
         step()
     rt.device_sync()
 
-    sampler = ClockSampler(lrank)
-    if rank == 0:
-        sampler.start()
-
+    sampler.mark()
     l0 = be.nlaunches
     ms = timed(step, args.steps)
     graphs = sysm.rhs_graphs(0, 1)
     nkern = sum(1 for g in graphs for w, k in g.plan if w == 'kernel')
     launches = (be.nlaunches - l0) if not be.use_graphs else nkern*args.steps
 
+    # nvidia-smi needs a second or so of load to return a handful of
+    # samples: keep the identical load running (untimed; the same count on
+    # every rank, derived from the max-over-ranks time) until it has them
+    extra = (0 if args.no_clocks else
+             int(np.ceil(max(0.0, 1500.0 - ms)/(ms/args.steps))))
+    for _ in range(extra):
+        step()
+    rt.device_sync()
+
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks['load'] = (f'{args.steps} timed + {extra} further identical '
+                          'untimed steps')
     ms_per_step = ms/args.steps
     value = ndof/(ms_per_step*1e-3)/1e9
 

@@ -423,8 +423,13 @@ def _evalsrcmacros(be, tplargs, dims, extrns={}, ploc=None, u=None, **kw):
     return be.kernel_cls(run, rtnames=('t',))
 
 
-def _mpi_rows(xm):
-    return _mat3(xm)[0]
+def _mpi_rows(xm, n):
+    """A received halo matrix as its ``[nvrow*nvcol][n]`` rows: 'mpi'
+    arguments are tightly packed and addressed ``(nv*i + v)*_nx + x``
+    (pyfr/backends/base/generator.py:214-226)."""
+    a = _mat3(xm)[0]
+    assert a.shape[1] == xm.leaddim
+    return a.reshape(-1, n)
 
 
 def _intcflux_euler(be, tplargs, dims, extrns={}, ul=None, ur=None, nl=None,
@@ -452,7 +457,7 @@ def _mpicflux_euler(be, tplargs, dims, extrns={}, ul=None, ur=None, nl=None,
 
     def run():
         l = [vl.load(i) for i in range(nv)]
-        r = list(_mpi_rows(ur))
+        r = list(_mpi_rows(ur, dims[0]))
         fn = ph.euler_common_flux(l, r, n, nd, nv, c, rs)
         for i in range(nv):
             vl.store(fn[i], i)
@@ -485,7 +490,7 @@ def _mpiconu(be, tplargs, dims, extrns={}, ulin=None, urin=None, ulout=None,
 
     def run():
         l = [li.load(i) for i in range(nv)]
-        r = list(_mpi_rows(urin))
+        r = list(_mpi_rows(urin, dims[0]))
 
         # mpiconu.mako:9-18: beta = -1/2 keeps our own trace
         if beta == -0.5:
@@ -517,9 +522,9 @@ def _cflux_ns(mpi):
             gL = gR = None
 
             if mpi:
-                r = list(_mpi_rows(ur))
+                r = list(_mpi_rows(ur, dims[0]))
                 if beta != 0.5:
-                    rows = _mpi_rows(gradur)
+                    rows = _mpi_rows(gradur, dims[0])
                     gR = [[rows[nv*d + j] for j in range(nv)]
                           for d in range(nd)]
             else:

@@ -65,6 +65,9 @@ class B200Backend(base.BaseBackend):
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
         self.cflux_minblocks = cfg.getint(sect, 'cflux-minblocks', 5)
+        self.gradflux_maxctas = cfg.getint(sect, 'gradflux-maxctas', 2)
+        self.gradflux_threads = cfg.getint(sect, 'gradflux-threads', 0)
+        self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', True)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

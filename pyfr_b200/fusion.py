@@ -140,7 +140,7 @@ def fuse_gradflux(be, kerns, subs):
             geo = [s, r]
 
         out.append(B200Kernel(
-            be, fn, (min(nblocks, be.sm_count), 1, 1),
+            be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
             (meta['nthreads'], 1, 1), meta['smem'], args,
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
             traffic=meta['words_per_block']*nblocks*isz, kind='gradflux',

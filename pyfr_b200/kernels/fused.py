@@ -112,12 +112,13 @@ class OpClass:
         self.members = []       # (out rows, [input rows per term])
 
 
-def build_classes(terms, max_classes=24):
-    """Decompose ``out = sum_t A_t @ src_t`` into line classes."""
+def build_classes(terms, max_classes=24, rows=None):
+    """Decompose ``out = sum_t A_t @ src_t`` (restricted to the output
+    ``rows`` when given) into line classes."""
     M = terms[0].shape[0]
     classes = {}
 
-    for g in _row_groups(terms, range(M)):
+    for g in _row_groups(terms, range(M) if rows is None else rows):
         sups = [sorted(set().union(*[_support(A, m) for m in g]))
                 for A in terms]
         blocks = [A[np.ix_(g, s)] for A, s in zip(terms, sups)]
@@ -186,33 +187,137 @@ class PhaseEmitter:
     def __init__(self, LD, itemsize, K):
         self.LD, self.isz, self.K = LD, itemsize, K
         self.tables = []        # (name, flat list of ints)
+        self.staged = None      # names of the tables copied to smem
+
+    def plan(self, budget):
+        """Choose the tables staged in shared memory (smallest first)
+        within ``budget`` bytes; the rest are read through L1."""
+        self.staged, used = set(), 0
+        for name, vals in sorted(self.tables, key=lambda t: len(t[1])):
+            if used + 4*len(vals) <= budget:
+                self.staged.add(name)
+                used += 4*len(vals)
 
     @property
     def table_bytes(self):
-        return sum(4*len(t) for _, t in self.tables)
+        return sum(4*len(t) for n, t in self.tables if n in self.staged)
 
     def decls(self):
         out = []
         for name, vals in self.tables:
             flat = ', '.join(map(str, vals))
-            out.append(f'static __device__ const int g_{name}[{len(vals)}] '
-                       f'= {{{flat}}};')
+            out.append(f'static __device__ __align__(16) const int '
+                       f'g_{name}[{len(vals)}] = {{{flat}}};')
         return '\n'.join(out)
 
     def smem_layout(self, base):
         """Carve the staged tables out of the smem pointer ``base``."""
         out, off = [], 0
         for name, vals in self.tables:
-            out.append(f'int *{name} = reinterpret_cast<int *>({base}) + '
-                       f'{off};')
-            off += len(vals)
+            if name in self.staged:
+                out.append(f'const int *{name} = reinterpret_cast<int *>('
+                           f'{base}) + {off};')
+                off += len(vals)
+            else:
+                out.append(f'const int *{name} = g_{name};')
         return '\n    '.join(out)
 
-    def stage(self):
-        return '\n    '.join(
-            f'for (int i = tid; i < {len(v)}; i += NTHREADS) '
-            f'{n}[i] = g_{n}[i];' for n, v in self.tables
-        )
+    def stage(self, base):
+        out, off = [], 0
+        for n, v in self.tables:
+            if n in self.staged:
+                out.append(f'for (int i = tid; i < {len(v)}; i += NTHREADS) '
+                           f'(reinterpret_cast<int *>({base}) + {off})[i] = '
+                           f'g_{n}[i];')
+                off += len(v)
+        return '\n    '.join(out)
+
+    def emit_planes(self, tag, blocks, boffs, extra, store):
+        """``out[p] = sum_d blocks[d][p, :] @ src[boffs[d] + :] + extra``
+        with one thread per (plane, column): the plane's outputs are
+        accumulated in registers while each input is read from shared
+        memory exactly once -- per output ``ndirs`` loads instead of the
+        ``2*ndirs`` loads + stores of line-by-line in-place transforms.
+
+        ``boffs``: first row of each direction's block in ``G``;
+        ``extra(byte offset expr, at)``: optional additional addend read
+        at the output point; ``store(byte offset expr, value)``."""
+        LD, isz, K = self.LD, self.isz, self.K
+        planes = find_planes(blocks)
+        if planes is None:
+            raise NotFusable('planes too large')
+
+        # Classes of planes with identical coefficient blocks
+        classes = {}
+        for P in planes:
+            key = tuple(tuple(B[np.ix_(P, P)].ravel()) for B in blocks)
+            classes.setdefault(key, []).append(P)
+
+        out = []
+        for ci, (key, members) in enumerate(classes.items()):
+            np_ = len(members[0])
+            npad = -(-np_ // 4)*4
+            coefs = [np.array(k).reshape(np_, np_) for k in key]
+
+            tab = []
+            for P in members:
+                tab += [r*LD*isz for r in P] + [0]*(npad - np_)
+            name = f'tab_{tag}_{ci}'
+            self.tables.append((name, tab))
+
+            at = lambda arr, off: (f'*reinterpret_cast<fpdtype_t *>('
+                                   f'reinterpret_cast<char *>({arr}) + {off})')
+            idx = lambda j: f'q.{"xyzw"[j % 4]}'
+            ldq = lambda q: (f'const int4 q = *reinterpret_cast<const int4 *>'
+                             f'({name} + g*{npad} + {4*q});')
+
+            L = [f'for (int item = tid; item < {len(members)}*LD; '
+                 'item += NTHREADS)', '{',
+                 '    const int g = item / LD;',
+                 f'    const int cb = (item - g*LD)*{isz};',
+                 '    fpdtype_t ' + ', '.join(f'a{i}' for i in range(np_))
+                 + ';']
+
+            # Indices are fetched four at a time next to their use (and
+            # again for the stores) rather than held in registers
+            acc = [None]*np_
+            for j in range(np_):
+                if j % 4 == 0:
+                    L.append('    {')
+                    L.append('    ' + ldq(j // 4))
+                for d, (C, bo) in enumerate(zip(coefs, boffs)):
+                    if not np.any(C[:, j]):
+                        continue
+                    L.append(f'    const fpdtype_t x{d}_{j} = '
+                             f'{at("G", f"{idx(j)} + cb + {bo*LD*isz}")};')
+                    for i in range(np_):
+                        if C[i, j] != 0:
+                            a = K(C[i, j])
+                            L.append(
+                                f'    a{i} = {a}*x{d}_{j};'
+                                if acc[i] is None else
+                                f'    a{i} = fma({a}, x{d}_{j}, a{i});'
+                            )
+                            acc[i] = True
+                if j % 4 == 3 or j == np_ - 1:
+                    L.append('    }')
+
+            for i in range(np_):
+                if i % 4 == 0:
+                    L.append('    {')
+                    L.append('    ' + ldq(i // 4))
+                off = f'{idx(i)} + cb'
+                val = f'a{i}' if acc[i] else 'FP(0.0)'
+                if extra is not None:
+                    val = f'{val} + {extra(off, at)}'
+                L.append('    ' + store(off, val, at))
+                if i % 4 == 3 or i == np_ - 1:
+                    L.append('    }')
+
+            L.append('}')
+            out.append('\n        '.join(L))
+
+        return '\n        '.join(out)
 
     def emit(self, tag, classes, srcs, store, inplace=False):
         """``srcs[t]``: name of the (shared) array term ``t`` reads;
@@ -284,7 +389,39 @@ class PhaseEmitter:
         return '\n        '.join(out)
 
 
-def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
+def find_planes(blocks, maxsize=36):
+    """Partition the points into the connected components of the coupling
+    graph of the square operator ``blocks`` (one per direction): for a
+    tensor-product element and two directions these are its coordinate
+    planes.  Returns a list of sorted index lists, or None if a component
+    exceeds ``maxsize`` points (too many accumulators for one thread)."""
+    n = blocks[0].shape[0]
+    adj = sum((B != 0).astype(int) for B in blocks)
+    adj = (adj + adj.T) != 0
+    seen, comps = np.zeros(n, dtype=bool), []
+
+    for p0 in range(n):
+        if seen[p0]:
+            continue
+
+        comp, todo = [], [p0]
+        seen[p0] = True
+        while todo:
+            p = todo.pop()
+            comp.append(p)
+            for q in np.flatnonzero(adj[p]):
+                if not seen[q]:
+                    seen[q] = True
+                    todo.append(q)
+
+        if len(comp) > maxsize:
+            return None
+        comps.append(sorted(comp))
+
+    return comps
+
+
+def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
     """Source of the fused kernel.
 
     ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
@@ -305,6 +442,19 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
 
     linear = 'linear' in tplargs['ktype']
     npoints = nu*csub
+
+    # Occupancy plan: as many CTAs per SM as the shared-memory footprint
+    # allows (two when a block is half an SM's worth), sharing a budget of
+    # 512 threads so that each keeps ~128 registers.  Co-resident CTAs run
+    # different phases at any one time, which overlaps the FP64-heavy
+    # pointwise phases of one with the shared-memory/HBM phases of another.
+    smem_fix = ((nu + nf + nd*nu)*LD + (2*tplargs.get('nverts', 0)*nd*csub
+                                        + nu*nd + 2 if linear else 0))*isz + 64
+    smem_sm = 228*1024
+    nctas = max(1, min(getattr(be, 'gradflux_maxctas', 2),
+                       smem_sm // (smem_fix + 1024)))
+    if nthreads is None:
+        nthreads = getattr(be, 'gradflux_threads', 0) or 512 // nctas
     nrounds = -(-npoints // nthreads)
 
     defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
@@ -332,9 +482,44 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
     A5d = np.zeros((nd*nu, nd*nu))
     for d in range(nd):
         A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
-    p5 = em.emit('p5', build_classes([A5d]), ['G'],
-                 lambda off, v, at: f'{at("G", off)} = {v};', inplace=True)
+    p5lines = em.emit('p5', build_classes([A5d]), ['G'],
+                      lambda off, v, at: f'{at("G", off)} = {v};',
+                      inplace=True)
     psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
+    p5 = f'''{p5lines}
+        __syncthreads();
+
+        for (int item = tid; item < NPTS*LD; item += NTHREADS)
+            fout[fob + item] = {psum};'''
+
+    # Preferred form: the last direction by in-place line transforms, the
+    # first two accumulated plane by plane in registers and streamed out
+    if getattr(be, 'gradflux_planes', True):
+        blocks = [A5[:, d*nu:(d + 1)*nu] for d in range(nd)]
+        try:
+            mark = len(em.tables)
+            if nd == 3:
+                A5l = np.zeros_like(A5d)
+                A5l[2*nu:, 2*nu:] = blocks[2]
+                # Rows of the other directions are left untouched
+                lines = build_classes([A5l], rows=range(2*nu, 3*nu))
+                p5a = em.emit('p5l', lines, ['G'],
+                              lambda off, v, at: f'{at("G", off)} = {v};',
+                              inplace=True) + '\n        __syncthreads();'
+                extra = lambda off, at: at('G', f'{off} + {2*nu*LD*isz}')
+            else:
+                p5a, extra = '', None
+
+            p5b = em.emit_planes(
+                'p5p', blocks[:2], [0, nu], extra,
+                lambda off, v, at: f'{at("(fout + fob)", off)} = {v};'
+            )
+            # Drop the tables of the line-only variant
+            em.tables = [t for t in em.tables[:mark]
+                         if not t[0].startswith('tab_p5_')] + em.tables[mark:]
+            p5 = f'{p5a}\n        {p5b}'
+        except NotFusable:
+            em.tables = em.tables[:mark]
 
     if linear:
         gsrc = ph.linear_smats_src(nd, tplargs['nverts'],
@@ -381,11 +566,15 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
                                               + p*C_SUB + e);
 '''
 
+    # Index tables go to shared memory as far as the per-CTA share of the
+    # SM's 228 KB (1 KB of it reserved per resident CTA) allows
     tables = em.decls()
     data_words = (nu + nf + nd*nu) + 0
-    smem = (data_words*LD + geo_words)*isz + em.table_bytes + 64
+    smem = (data_words*LD + geo_words)*isz + 64
+    em.plan(min(smem_sm // nctas - 1024, 227*1024) - smem)
+    smem += em.table_bytes
 
-    if smem > be.smem_budget + 8*1024:
+    if smem > 227*1024:
         raise NotFusable(f'needs {smem} bytes of shared memory')
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
@@ -403,7 +592,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=512):
 #define G_WORDS (NDIMS*NPTS*LD)
 #define V_WORDS (NVERTS*NDIMS*C_SUB)
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+extern "C" __global__ void __launch_bounds__(NTHREADS, {nctas})
 gradflux(int nblocks, int neles,
          const fpdtype_t* __restrict__ u, long long u_bsz,
          const fpdtype_t* ucomm, long long ucomm_bsz,
@@ -424,7 +613,7 @@ gradflux(int nblocks, int neles,
     const int tid = threadIdx.x;
 
     // Stage the index tables and the reference point set once per CTA
-    {em.stage()}
+    {em.stage(f'G + G_WORDS + {geo_words}')}
     {geo_stage}
 
     if (tid == 0)
@@ -531,14 +720,10 @@ gradflux(int nblocks, int neles,
         // ---- phase 5: divergence: line transforms, then the sum -> HBM ---
         {p5}
         __syncthreads();
-
-        for (int item = tid; item < NPTS*LD; item += NTHREADS)
-            fout[fob + item] = {psum};
-        __syncthreads();
     }}
 }}
 '''
-    meta = dict(nthreads=nthreads, smem=smem,
+    meta = dict(nthreads=nthreads, smem=smem, nctas=nctas,
                 words_per_block=(2*nu + nf + nd*nf)*LD)
 
     return src, 'gradflux', meta

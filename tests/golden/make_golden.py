@@ -1,0 +1,224 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the REFERENCE.
+
+Runs only where /root/reference exists (the build container); the fixtures
+it writes are committed so the CPU and GPU test suites can run anywhere.
+
+    python tests/golden/make_golden.py
+
+What is pinned, and by what:
+
+* ``opmats.npz`` -- operator matrices produced by the reference's own
+  ``pyfr/shapes.py`` (``BaseShape.opmat``, :79-135) for the element types
+  and orders of BASELINE.json's configs.  The hex p=3 Gauss-Legendre
+  ``m0..m3`` are additionally checked here against the reference's own
+  golden file ``pyfr/tests/hex-gleg-ord3.npz`` (the single known-answer
+  test the reference ships, ``pyfr/tests/test_ele_mats.py:10-27``).
+* ``host_<case>.npz`` -- the reference's own ``NavierStokesSystem`` /
+  ``EulerSystem`` (``pyfr/solvers/*``; imported with name-only stubs for
+  the absent third-party packages, oracle/refharness.py) run on the NumPy
+  oracle backend: every view index array the reference's host code hands
+  to the backend (``View.mapping`` / ``rstrides``), the halo message
+  sizes, the initial condition and the resulting RHS.  These pin this
+  repository's host mirror (pyfr_b200/host): same mesh + same backend must
+  give bit-identical indices and the same RHS to round-off.
+"""
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refharness as rh                       # noqa: E402
+from oracle.npbackend import LocalComm                    # noqa: E402
+from pyfr_b200 import cases                               # noqa: E402
+
+# name -> (case, mesh, case kwargs, partition bricks, oracle-backend options)
+HOST_CASES = {
+    'tgv_p2_rusanov': ('tgv', (3, 2, 2), dict(order=2, warp=0.1),
+                       (1, 1, 1), {}),
+    'tgv_p3_hllc_blocked': ('tgv', (3, 2, 2),
+                            dict(order=3, rsolver='hllc', warp=0.1),
+                            (1, 1, 1), {'blocks': 1, 'soasz': 8,
+                                        'csubsz': 8}),
+    'tgv_p2_beta0_2parts': ('tgv', (4, 2, 3), dict(order=2, beta=0.0,
+                                                   warp=0.1),
+                            (2, 1, 1), {}),
+    'tgv_p1_4parts_blocked': ('tgv', (4, 4, 2), dict(order=1, warp=0.05),
+                              (2, 2, 1), {'blocks': 1, 'soasz': 8,
+                                          'csubsz': 8}),
+    'tgv_p4_rusanov': ('tgv', (2, 2, 2), dict(order=4, warp=0.1),
+                       (1, 1, 1), {}),
+    'vortex_p3_rusanov': ('vortex', 4, dict(order=3), (1, 1), {}),
+    'vortex_p3_hllc_2parts': ('vortex', (6, 4), dict(order=3,
+                                                     rsolver='hllc'),
+                              (2, 1), {'blocks': 1, 'soasz': 8,
+                                       'csubsz': 16}),
+}
+
+OPMAT_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
+                ('hex', 3, 'gauss-legendre'), ('hex', 4, 'gauss-legendre'),
+                ('hex', 4, 'gauss-legendre-lobatto'),
+                ('hex', 6, 'gauss-legendre')]
+OPMAT_EXPRS = ['M0', 'M4 - M6*M0', 'M6', 'M1 - M3*M2', 'M3']
+
+
+def cfg_text(case, kw, beopts):
+    kw = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = cases.tgv_cfg(**kw) if case == 'tgv' else cases.vortex_cfg(**kw)
+    if beopts:
+        txt += '\n[backend-oracle]\n' + ''.join(f'{k} = {v}\n'
+                                                for k, v in beopts.items())
+    return txt
+
+
+def record_views(be):
+    """Wrap ``be.view`` so every view's index arrays are recorded."""
+    trace, orig = [], be.view
+
+    def view(*a, **k):
+        v = orig(*a, **k)
+        trace.append(v)
+        return v
+
+    be.view = view
+    return trace
+
+
+def record_consts(becls):
+    """Wrap ``const_matrix`` of a backend base class so the floating-point
+    constant tables (normals, metric terms, vertices) are recorded.
+    Returns (list, undo callable)."""
+    rec, orig = [], becls.const_matrix
+
+    def const_matrix(self, initval, *a, **k):
+        iv = np.asarray(initval)
+        tags = k.get('tags', a[1] if len(a) > 1 else set())
+        if iv.dtype.kind == 'f' and not any(t.startswith('M') for t in tags):
+            rec.append(np.array(iv))
+        return orig(self, initval, *a, **k)
+
+    becls.const_matrix = const_matrix
+    return rec, lambda: setattr(becls, 'const_matrix', orig)
+
+
+def consts_digest(rec):
+    """Constant tables in a creation-order independent order."""
+    return sorted(rec, key=lambda a: (a.shape, float(np.abs(a).sum())))
+
+
+def trace_digest(trace):
+    """Order-independent fingerprint + the raw arrays of a view trace."""
+    arrs = []
+    for v in trace:
+        arrs.append(np.ascontiguousarray(v.mapping.get()[0]))
+        if v.rstrides is not None:
+            arrs.append(np.ascontiguousarray(v.rstrides.get()[0]))
+
+    keys = sorted(f'{a.dtype}:{a.shape}:' + hashlib.sha256(a.tobytes())
+                  .hexdigest() for a in arrs)
+    return keys, arrs
+
+
+def ref_opmats():
+    rh.install_stubs()
+    from pyfr.inifile import Inifile
+    from pyfr.shapes import HexShape, QuadShape
+
+    out = {}
+    for et, order, pts in OPMAT_SHAPES:
+        face = 'line' if et == 'quad' else 'quad'
+        cfg = Inifile(f'[solver]\norder = {order}\n'
+                      f'[solver-elements-{et}]\nsoln-pts = {pts}\n'
+                      f'[solver-interfaces-{face}]\nflux-pts = {pts}\n')
+        shape = {'quad': QuadShape, 'hex': HexShape}[et](None, cfg)
+
+        for expr in OPMAT_EXPRS:
+            out[f'{et}|{order}|{pts}|{expr}'] = shape.opmat(expr)
+
+        if (et, order, pts) == ('hex', 3, 'gauss-legendre'):
+            kat = np.load('/root/reference/pyfr/tests/hex-gleg-ord3.npz')
+            for m in ('m0', 'm1', 'm2', 'm3'):
+                assert np.allclose(getattr(shape, m), kat[m]), m
+                out[f'kat|hex|3|gauss-legendre|{m}'] = getattr(shape, m)
+
+    return out
+
+
+def ref_host_case(name):
+    case, n, kw, parts, beopts = HOST_CASES[name]
+    txt = cfg_text(case, kw, beopts)
+    _, box = cases.make(case, n, **kw)
+    nparts = int(np.prod(parts))
+    vparts = box.brick_partition(parts) if nparts > 1 else None
+
+    world = LocalComm(0, nparts)
+    systems, traces, consts = [], [], []
+
+    rh.install_stubs()
+    import pyfr.backends.base.backend as rbb
+
+    for r in range(nparts):
+        # Record the views the reference's host code creates
+        holder = {}
+        orig_init = rbb.BaseBackend.__init__
+
+        def init(self, cfg, _h=holder, _o=orig_init):
+            _o(self, cfg)
+            _h['trace'] = record_views(self)
+
+        rbb.BaseBackend.__init__ = init
+        crec, undo = record_consts(rbb.BaseBackend)
+        try:
+            s, be = rh.ref_system(txt, box.local_mesh(vparts, r), 2,
+                                  world.peer(r))
+        finally:
+            rbb.BaseBackend.__init__ = orig_init
+            undo()
+
+        consts.append(consts_digest(crec))
+
+        systems.append(s)
+        traces.append(holder['trace'])
+
+    graphs = [s._rhs_graphs(0, 1) for s in systems]
+    for s in systems:
+        s._prepare_kernels(0.0, 0, 1)
+    for stage in zip(*graphs):
+        for g in stage:
+            g.run()
+        world.deliver()
+
+    out = {}
+    for r, (s, tr) in enumerate(zip(systems, traces)):
+        keys, arrs = trace_digest(tr)
+        out[f'r{r}_viewkeys'] = np.array(keys)
+        for i, a in enumerate(arrs):
+            out[f'r{r}_view{i}'] = a
+        for i, a in enumerate(consts[r]):
+            out[f'r{r}_const{i}'] = a
+        out[f'r{r}_ics'] = s.ele_scal_upts(0)[0]
+        out[f'r{r}_rhs'] = s.ele_scal_upts(1)[0]
+
+    return out
+
+
+def main():
+    rh.install_stubs()
+
+    np.savez_compressed(os.path.join(HERE, 'opmats.npz'), **ref_opmats())
+    print('opmats.npz written')
+
+    for name in HOST_CASES:
+        np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
+                            **ref_host_case(name))
+        print(f'host_{name}.npz written')
+
+
+if __name__ == '__main__':
+    main()

@@ -18,7 +18,8 @@ TOL64 = 1e-12
 
 # Backend variants: default (64-byte SoA, fused kernels), the wide layout
 # (fused element kernel does not fit -> individual kernels) and fusion off
-VARIANTS = {'default': {}, 'soa16': {'n-soa': 16}, 'nofuse': {'fusion': 0}}
+VARIANTS = {'default': {}, 'soa16': {'n-soa': 16}, 'nofuse': {'fusion': 0},
+            'soa4': {'n-soa': 4}}
 
 
 def b200_rhs(case, n, opts={}, **kw):
@@ -52,7 +53,7 @@ def test_tgv_rhs_matches_oracle(built, kw, variant):
 
     kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
              for w, k in g.plan if w == 'kernel']
-    if variant == 'default':
+    if variant in ('default', 'soa4'):
         assert 'gradflux' in kinds and 'mul+negdivconf' in kinds
         assert 'copy' not in kinds
     elif variant == 'nofuse':
