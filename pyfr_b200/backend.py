@@ -67,12 +67,16 @@ class B200Backend(base.BaseBackend):
         self.cflux_minblocks = cfg.getint(sect, 'cflux-minblocks', 5)
         self.gradflux_maxctas = cfg.getint(sect, 'gradflux-maxctas', 2)
         self.gradflux_threads = cfg.getint(sect, 'gradflux-threads', 0)
-        self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', True)
+        self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
+        self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
+        self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 2)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 
         self.compiler = KernelCompiler(rt)
         self.nlaunches = 0
+        self.view_uses = []
+        self.dead_rows = cfg.getbool(sect, 'dead-rows', True)
 
         # Compute stream, communication stream and fork/join events
         self.stream = rt.new_ptr(rt.stream_create)

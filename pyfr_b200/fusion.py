@@ -46,6 +46,57 @@ def _rows_of(m):
     return _root(m), getattr(m, 'ra', 0), m.nrow
 
 
+def row_need_classes(be, mat, nrows, nblocks, maxclasses=15):
+    """Which rows of ``mat`` (an element buffer whose first ``nrows`` rows
+    are addressed by interface views; further row groups are reached
+    through the views' row strides) are ever *read* through a view, per
+    element block.
+
+    Rows with the same need pattern over all blocks form a class.  Returns
+    ``(cls, masks)``: ``cls[row]`` in ``[0, nclasses)`` and ``masks[block]``
+    with bit ``c`` set when class ``c`` is read in that block -- or None
+    when everything is read everywhere (or the pattern is too irregular
+    to be worth encoding).  A one-sided LDG flux (|beta| = 1/2) reads the
+    gradient on one side of each interface only, so on meshes whose blocks
+    agree on which faces are left-hand sides about half of the rows are
+    dead stores."""
+    isz, LD = mat.itemsize, mat.leaddim
+    lo = mat.offset // isz
+    hi = lo + mat.nbytes // isz
+    need = np.zeros((nblocks, nrows), dtype=bool)
+
+    for v, mode in be.view_uses:
+        if 'r' not in mode or not any(_root(m) is mat for m in v._mats):
+            continue
+
+        mp = v.mapping.get()[0].astype(np.int64)
+        sel = (mp >= lo) & (mp < hi)
+        idx = mp[sel] - lo
+        blk, row = idx // mat.blocksz, (idx % mat.blocksz) // LD
+
+        if v.nvrow > 1:
+            rs = v.rstrides.get()[0][sel]
+            if np.any(rs != nrows*LD):
+                return None
+        if np.any(row >= nrows) or np.any(blk >= nblocks):
+            return None
+
+        need[blk, row] = True
+
+    if need.all():
+        return None
+
+    pats, cls = np.unique(need.T, axis=0, return_inverse=True)
+    if len(pats) > maxclasses:
+        return None
+
+    masks = np.zeros(nblocks, dtype=np.int32)
+    for c, pat in enumerate(pats):
+        masks |= pat.astype(np.int32) << c
+
+    return cls.ravel(), masks
+
+
 def fuse_gradflux(be, kerns, subs):
     """tgradpcoru .. tdivtpcorf of one element type -> ``gradflux``."""
     from pyfr_b200.providers import B200Kernel
@@ -102,6 +153,9 @@ def fuse_gradflux(be, kerns, subs):
     ops = dict(A1=i0['A'], M6=i1['A'], M0=M0, A5=i5['A'])
     out = []
 
+    # Dead-store elimination on vect_fpts
+    rneed = row_need_classes(be, VF, nf, VF.nblocks) if be.dead_rows else None
+
     # One launch per mesh region (curved / linear)
     for kg, kt in zip(g2, g4):
         ti, gi = kt.info, kg.info
@@ -117,8 +171,10 @@ def fuse_gradflux(be, kerns, subs):
         nblocks = -(-neles // be.csubsz)
         pts = ti['upts'].get() if ti['upts'] is not None else None
 
-        src, name, meta = kfused.gradflux_source(be, ops, ti['tplargs'], pts,
-                                                 LD)
+        src, name, meta = kfused.gradflux_source(
+            be, ops, ti['tplargs'], pts, LD,
+            rowcls=None if rneed is None else rneed[0]
+        )
         fn = be.pointwise._function(src, name)
         fn.set_smem(meta['smem'])
 
@@ -139,12 +195,25 @@ def fuse_gradflux(be, kerns, subs):
                      ('l', r.blocksz)]
             geo = [s, r]
 
+        words = meta['words_per_block']*nblocks
+        if rneed is not None:
+            fm = be.const_matrix(rneed[1][None, b0:b0 + nblocks],
+                                 dtype=np.int32, tags={'noblock'})
+            args.append(('p', fm.data))
+            geo = geo + [fm]
+
+            # Rows actually written
+            cls, masks = rneed
+            live = sum(int(((masks[b0:b0 + nblocks] >> c) & 1).sum()) *
+                       int((cls == c).sum()) for c in range(cls.max() + 1))
+            words -= nd*(nf*nblocks - live)*LD
+
         out.append(B200Kernel(
             be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
             (meta['nthreads'], 1, 1), meta['smem'], args,
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
-            traffic=meta['words_per_block']*nblocks*isz, kind='gradflux',
-            info=dict(replaces=kerns)
+            traffic=words*isz, kind='gradflux',
+            info=dict(replaces=kerns, dead_rows=rneed is not None)
         ))
 
     return out

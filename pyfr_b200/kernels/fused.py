@@ -184,8 +184,8 @@ class PhaseEmitter:
     CTA: a work item fetches its indices with a few 128-bit loads and
     forms every address with a single add."""
 
-    def __init__(self, LD, itemsize, K):
-        self.LD, self.isz, self.K = LD, itemsize, K
+    def __init__(self, LD, itemsize, K, ncol=1):
+        self.LD, self.isz, self.K, self.ncol = LD, itemsize, K, ncol
         self.tables = []        # (name, flat list of ints)
         self.staged = None      # names of the tables copied to smem
 
@@ -319,72 +319,125 @@ class PhaseEmitter:
 
         return '\n        '.join(out)
 
-    def emit(self, tag, classes, srcs, store, inplace=False):
+    def emit(self, tag, classes, srcs, store, inplace=False, outtag=None,
+             rep=None):
         """``srcs[t]``: name of the (shared) array term ``t`` reads;
-        ``store(byte offset expr, val)`` renders a store."""
+        ``store(byte offset expr, val)`` renders a store.  ``rep = (n,
+        out stride, in stride)`` applies the same classes ``n`` times with
+        all output / input rows shifted by the given byte strides (a block
+        diagonal operator with identical blocks needs one table).
+
+        ``outtag(row)``: class of an output row; the kernel holds a
+        per-block mask ``fm`` and skips outputs whose class bit is clear.
+        Lines are sub-divided by the classes of their outputs, so the test
+        is a block-uniform branch on a compile-time bit, not per-lane
+        arithmetic.
+
+        A work item handles one line for ``self.ncol`` columns ``LD/ncol``
+        apart: the index fetches and address additions are shared, the
+        extra columns being reached through immediate offsets."""
         LD, isz, K, out = self.LD, self.isz, self.K, []
+        NC = self.ncol if LD % self.ncol == 0 else 1
+        W, WB = LD // NC, (LD // NC)*isz
 
         for ci, c in enumerate(classes):
             nidx = (0 if inplace else c.nout) + sum(c.nins)
             npad = -(-nidx // 4)*4
-            tab = []
 
+            # Sub-divide by the output classes (one group when untagged)
+            parts = {}
             for rows, ins in c.members:
-                ent = [] if inplace else [r*LD*isz for r in rows]
-                for sidx in ins:
-                    ent += [k*LD*isz for k in sidx]
-
                 if inplace and not set(rows) <= set(ins[0]):
                     raise NotFusable('in-place transform needs rows within '
                                      'inputs')
+                key = tuple(outtag(r) for r in rows) if outtag else ()
+                parts.setdefault(key, []).append((rows, ins))
 
-                tab += ent + [0]*(npad - nidx)
+            for pi, (key, members) in enumerate(parts.items()):
+                tab = []
+                for rows, ins in members:
+                    ent = [] if inplace else [r*LD*isz for r in rows]
+                    for sidx in ins:
+                        ent += [k*LD*isz for k in sidx]
+                    tab += ent + [0]*(npad - nidx)
 
-            name = f'tab_{tag}_{ci}'
-            self.tables.append((name, tab))
+                name = f'tab_{tag}_{ci}_{pi}'
+                self.tables.append((name, tab))
+                nmem = len(members)
 
-            L = [f'for (int item = tid; item < {len(c.members)}*LD; '
-                 'item += NTHREADS)', '{',
-                 '    const int g = item / LD;',
-                 f'    const int cb = (item - g*LD)*{isz};']
-
-            for q in range(npad // 4):
-                L.append(f'    const int4 q{q} = *reinterpret_cast<const '
-                         f'int4 *>({name} + g*{npad} + {4*q});')
-
-            idx = lambda j: f'q{j // 4}.{"xyzw"[j % 4]}'
-            at = lambda arr, off: (f'*reinterpret_cast<fpdtype_t *>('
-                                   f'reinterpret_cast<char *>({arr}) + {off})')
-
-            base = 0 if inplace else c.nout
-            regs, off = [], base
-            for t, n in enumerate(c.nins):
-                for j in range(n):
-                    L.append(f'    const int i{t}_{j} = {idx(off + j)} + cb;')
-                    L.append(f'    const fpdtype_t x{t}_{j} = '
-                             f'{at(srcs[t], f"i{t}_{j}")};')
-                regs.append([f'x{t}_{j}' for j in range(n)])
-                off += n
-
-            for i in range(c.nout):
-                pairs = [(c.coefs[t][i, j], regs[t][j])
-                         for t in range(len(c.nins))
-                         for j in range(c.nins[t])]
-                val = _fma_chain(pairs, K)
-
-                if inplace:
-                    # Output row i lives where the same point's input was
-                    rows0, ins0 = c.members[0]
-                    j = ins0[0].index(rows0[i])
-                    if any(ins[0].index(rows[i]) != j
-                           for rows, ins in c.members):
-                        raise NotFusable('inconsistent in-place slots')
-                    L.append('    ' + store(f'i0_{j}', val, at))
+                L = []
+                if key:
+                    bits = ' | '.join(f'{1 << k}u' for k in sorted(set(key)))
+                    L += [f'if (fm & ({bits}))']
+                if rep:
+                    L += [f'for (int item = tid; item < {rep[0]*nmem*W}; '
+                          'item += NTHREADS)', '{',
+                          f'    const int rd = item / {nmem*W};',
+                          f'    const int ritem = item - rd*{nmem*W};',
+                          f'    const int g = ritem / {W};',
+                          f'    const int cbi = (ritem - g*{W})*{isz} + '
+                          f'rd*{rep[2]};',
+                          f'    const int cb = (ritem - g*{W})*{isz} + '
+                          f'rd*{rep[1]};']
                 else:
-                    L.append('    ' + store(f'{idx(i)} + cb', val, at))
+                    L += [f'for (int item = tid; item < {nmem*W}; '
+                          'item += NTHREADS)', '{',
+                          f'    const int g = item / {W};',
+                          f'    const int cb = (item - g*{W})*{isz};',
+                          '    const int cbi = cb;']
 
-            L.append('}')
-            out.append('\n        '.join(L))
+                for q in range(npad // 4):
+                    L.append(f'    const int4 q{q} = *reinterpret_cast<const '
+                             f'int4 *>({name} + g*{npad} + {4*q});')
+
+                idx = lambda j: f'q{j // 4}.{"xyzw"[j % 4]}'
+                at = lambda arr, off: (
+                    f'*reinterpret_cast<fpdtype_t *>('
+                    f'reinterpret_cast<char *>({arr}) + {off})')
+
+                base = 0 if inplace else c.nout
+                regs, off = [], base
+                for t, n in enumerate(c.nins):
+                    for j in range(n):
+                        L.append(f'    const int i{t}_{j} = {idx(off + j)} '
+                                 '+ cbi;')
+                        for k in range(NC):
+                            L.append(
+                                f'    const fpdtype_t x{t}_{j}_{k} = '
+                                f'{at(srcs[t], f"i{t}_{j} + {k*WB}")};')
+                    regs.append([f'x{t}_{j}' for j in range(n)])
+                    off += n
+
+                for i in range(c.nout):
+                    if inplace:
+                        # Output i lives where the same point's input was
+                        rows0, ins0 = members[0]
+                        j = ins0[0].index(rows0[i])
+                        if any(ins[0].index(rows[i]) != j
+                               for rows, ins in members):
+                            raise NotFusable('inconsistent in-place slots')
+                        dst = f'i0_{j}'
+                    else:
+                        dst = f'{idx(i)} + cb'
+
+                    body = []
+                    for k in range(NC):
+                        pairs = [(c.coefs[t][i, j], f'{regs[t][j]}_{k}')
+                                 for t in range(len(c.nins))
+                                 for j in range(c.nins[t])]
+                        body.append(store(f'{dst} + {k*WB}',
+                                          _fma_chain(pairs, K), at))
+
+                    if key:
+                        L.append(f'    if (fm & {1 << key[i]}u)')
+                        L.append('    {')
+                        L += ['        ' + b for b in body]
+                        L.append('    }')
+                    else:
+                        L += ['    ' + b for b in body]
+
+                L.append('}')
+                out.append('\n        '.join(L))
 
         return '\n        '.join(out)
 
@@ -421,8 +474,13 @@ def find_planes(blocks, maxsize=36):
     return comps
 
 
-def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
+def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None):
     """Source of the fused kernel.
+
+    ``rowcls``: optional class index (< 16) per flux-point row; the kernel
+    then takes a per-block bit mask ``fmask`` and neither computes nor
+    stores the gradients of rows whose class bit is clear (rows no
+    interface kernel ever reads, see fusion.row_need_classes).
 
     ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
     ``M6`` (ndims*nupts x nfpts), ``M0`` (nfpts x nupts) and ``A5``
@@ -449,7 +507,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
     # different phases at any one time, which overlaps the FP64-heavy
     # pointwise phases of one with the shared-memory/HBM phases of another.
     smem_fix = ((nu + nf + nd*nu)*LD + (2*tplargs.get('nverts', 0)*nd*csub
-                                        + nu*nd + 2 if linear else 0))*isz + 64
+                                        + 2*nu*nd + 16*nd*csub if linear else 0))*isz + 64
     smem_sm = 228*1024
     nctas = max(1, min(getattr(be, 'gradflux_maxctas', 2),
                        smem_sm // (smem_fix + 1024)))
@@ -464,7 +522,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
                                True)
 
     K = ConstPool(isz == 8)
-    em = PhaseEmitter(LD, isz, K)
+    em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 2))
 
     # Phase 1: G = A1 @ U + M6 @ C
     p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
@@ -474,8 +532,16 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
     M0d = np.zeros((nd*nf, nd*nu))
     for d in range(nd):
         M0d[d*nf:(d + 1)*nf, d*nu:(d + 1)*nu] = M0
-    p3 = em.emit('p3', build_classes([M0d]), ['G'],
-                 lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};')
+    if rowcls is not None and max(rowcls) < 16:
+        outtag = lambda r: int(rowcls[r % nf])
+        fm_arg = ',\n         const int* __restrict__ fmask'
+        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + blk);'
+    else:
+        outtag, fm_arg, fm_load = None, '', ''
+
+    p3 = em.emit('p3', build_classes([M0]), ['G'],
+                 lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};',
+                 outtag=outtag, rep=(nd, nf*LD*isz, nu*LD*isz))
 
     # Phase 5: in-place line transforms of the flux, direction by
     # direction (block d of A5 acts on rows d*nu.. of G), then the sum
@@ -485,8 +551,23 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
     p5lines = em.emit('p5', build_classes([A5d]), ['G'],
                       lambda off, v, at: f'{at("G", off)} = {v};',
                       inplace=True)
-    psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
-    p5 = f'''{p5lines}
+    if LD % 2 == 0:
+        gv = 'reinterpret_cast<const fpdtype2_t *>(G)'
+        sx = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].x' for d in range(nd))
+        sy = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].y' for d in range(nd))
+        p5 = f'''{p5lines}
+        __syncthreads();
+
+        for (int item = tid; item < NPTS*LD/2; item += NTHREADS)
+        {{
+            fpdtype2_t t;
+            t.x = {sx};
+            t.y = {sy};
+            reinterpret_cast<fpdtype2_t *>(fout + fob)[item] = t;
+        }}'''
+    else:
+        psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
+        p5 = f'''{p5lines}
         __syncthreads();
 
         for (int item = tid; item < NPTS*LD; item += NTHREADS)
@@ -521,14 +602,106 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
         except NotFusable:
             em.tables = em.tables[:mark]
 
+    geo_elem = ''
     if linear:
-        gsrc = ph.linear_smats_src(nd, tplargs['nverts'],
-                                   tplargs['jac_exprs'])
-        rows = ', '.join(ph.fpconst(v) for row in pts for v in row)
-        gsrc = (f'static __device__ const fpdtype_t c_pts[{len(pts)*nd}]'
-                f' = {{{rows}}};\n' + gsrc)
+        nverts = tplargs['nverts']
         gargs = 'const fpdtype_t* __restrict__ verts, long long verts_bsz'
-        geom = r'''
+        mj = (ph.multilinear_jacobian(tplargs['jac_exprs'], nd, nverts)
+              if getattr(be, 'gradflux_monojac', True) else None)
+
+        if mj is not None:
+            # Per element: Q[q][i] = sum_n W[d][k][n] V[n][i] for every
+            # (d, monomial k) with a non-zero coefficient; per point: the
+            # monomial values.  j[d][i] = sum_k mono_k(x_p) Q[(d,k)][i].
+            monos, W = mj
+            used = [k for k in range(len(monos)) if monos[k] and
+                    np.any(W[:, k])]
+            nm = len(used) + len(used) % 2          # padded to pairs
+
+            # Q is stored element by element, (entry, component) pairs
+            # contiguous, so a lane fetches two values per 16-byte load;
+            # the per-element stride is padded to keep the eight lanes of
+            # a row group on distinct banks
+            qidx, qsrc = {}, []
+            for d in range(nd):
+                for k in range(len(monos)):
+                    if np.any(W[d, k]):
+                        qidx[d, k] = len(qidx)
+            nqv = len(qidx)*nd
+            nqv += nqv % 2
+            qstride = nqv + 2
+
+            for (d, k), q in qidx.items():
+                terms = ' '.join(
+                    f'{"+" if W[d, k, n] > 0 else "-"} '
+                    f'{ph.fpconst(abs(W[d, k, n]))}*v[{n}]'
+                    for n in range(nverts) if W[d, k, n] != 0)
+                qsrc.append(f'QS[e*{qstride} + {q}*NDIMS + i] = {terms};')
+
+            vals = []
+            for row in pts:
+                mv = [np.prod(row[list(monos[k])]) for k in used]
+                vals += mv + [0.0]*(nm - len(mv))
+            rows = ', '.join(ph.fpconst(v) for v in vals)
+            gsrc = (f'static __device__ const fpdtype_t c_pts[{len(pts)*nm}]'
+                    f' = {{{rows}}};\n' + ph.smats_from_jac_src(nd))
+
+            jl = []
+            for d in range(nd):
+                for i in range(nd):
+                    e = None
+                    for k in range(len(monos)):
+                        if (d, k) not in qidx:
+                            continue
+                        q = f'qv[{qidx[d, k]*nd + i}]'
+                        if not monos[k]:
+                            e = q if e is None else f'({e} + {q})'
+                        else:
+                            m = f'mv[{used.index(k)}]'
+                            e = (f'{m}*{q}' if e is None
+                                 else f'fma({m}, {q}, {e})')
+                    jl.append(f'jm[{d}][{i}] = {e or "FP(0.0)"};')
+
+            geom = (rf'''
+            fpdtype_t s[NDIMS][NDIMS], djac;
+            {{
+                fpdtype_t jm[NDIMS][NDIMS], qv[{nqv}], mv[{nm}];
+                UNROLL for (int a = 0; a < {nqv // 2}; a++)
+                {{
+                    const fpdtype2_t t = reinterpret_cast<const fpdtype2_t *>(
+                        QS + e*{qstride})[a];
+                    qv[2*a] = t.x; qv[2*a + 1] = t.y;
+                }}
+                UNROLL for (int a = 0; a < {nm // 2}; a++)
+                {{
+                    const fpdtype2_t t = reinterpret_cast<const fpdtype2_t *>(
+                        PTS + p*{nm})[a];
+                    mv[2*a] = t.x; mv[2*a + 1] = t.y;
+                }}
+                ''' + '\n                '.join(jl) + r'''
+                smats_detj_from_jac(jm, s, djac);
+            }
+            const fpdtype_t rcpdjac_v = FP(1.0)/djac;
+''')
+            npt_words = nu*nm
+            q_words = qstride*csub
+            geo_elem = (r'''
+        // Element-wise Jacobian coefficients from the vertices
+        if (tid < NDIMS*C_SUB)
+        {
+            const int e = tid % C_SUB, i = tid / C_SUB;
+            fpdtype_t v[NVERTS];
+            UNROLL for (int n = 0; n < NVERTS; n++)
+                v[n] = VS[n*(NDIMS*C_SUB) + COFF(e, i, NDIMS)];
+            ''' + '\n            '.join(qsrc) + '''
+        }
+''')
+        else:
+            gsrc = ph.linear_smats_src(nd, nverts, tplargs['jac_exprs'])
+            rows = ', '.join(ph.fpconst(v) for row in pts for v in row)
+            gsrc = (f'static __device__ const fpdtype_t c_pts[{len(pts)*nd}]'
+                    f' = {{{rows}}};\n' + gsrc)
+            geom = r'''
             fpdtype_t V[NVERTS][NDIMS], x[NDIMS], s[NDIMS][NDIMS], djac;
             UNROLL for (int n = 0; n < NVERTS; n++)
                 UNROLL for (int i = 0; i < NDIMS; i++)
@@ -538,11 +711,15 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None):
             calc_smats_detj(V, x, s, djac);
             const fpdtype_t rcpdjac_v = FP(1.0)/djac;
 '''
-        geo_words = 2*tplargs['nverts']*nd*csub + nu*nd
+            npt_words, q_words = nu*nd, 0
+
+        npt_words += npt_words % 2
+        geo_words = 2*nverts*nd*csub + npt_words + q_words
         geo_words += (-geo_words*isz // 16 * -16 - geo_words*isz)//isz
-        geo_decl = '''fpdtype_t *VSB = G + G_WORDS;
-    fpdtype_t *PTS = VSB + 2*V_WORDS;'''
-        geo_stage = '''for (int i = tid; i < NPTS*NDIMS; i += NTHREADS)
+        geo_decl = f'''fpdtype_t *VSB = G + G_WORDS;
+    fpdtype_t *PTS = VSB + 2*V_WORDS;
+    fpdtype_t *QS = PTS + {npt_words};'''
+        geo_stage = f'''for (int i = tid; i < {npt_words}; i += NTHREADS)
         PTS[i] = c_pts[i];'''
         geo_fetch = '''tma_load_1d(VSB + (n & 1)*V_WORDS, verts + b*verts_bsz,
                     V_WORDS*sizeof(fpdtype_t), &bars[0]);'''
@@ -598,7 +775,7 @@ gradflux(int nblocks, int neles,
          const fpdtype_t* ucomm, long long ucomm_bsz,
          fpdtype_t* vf, long long vf_bsz,
          fpdtype_t* __restrict__ fout, long long fout_bsz,
-         {gargs})
+         {gargs}{fm_arg})
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
@@ -644,6 +821,8 @@ gradflux(int nblocks, int neles,
 
         mbar_wait(&bars[0], it & 1);
         {geo_blk}
+        {fm_load}
+{geo_elem}
 
         // ---- phase 1: corrected transformed gradient ------------------
         {p1}

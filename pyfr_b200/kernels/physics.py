@@ -20,6 +20,7 @@ def prologue(fpdtype, ixdtype, soasz, csubsz, defines=()):
     lines = [
         f'typedef {fp} fpdtype_t;',
         f'typedef {ix} ixdtype_t;',
+        f'typedef {fp}2 fpdtype2_t;',
         f'#define K_SOA {soasz}',
         f'#define C_SUB {csubsz}',
         *[f'#define {k} {v}' for k, v in defines],
@@ -312,6 +313,91 @@ calc_smats_detj(const fpdtype_t V[{nverts}][NDIMS], const fpdtype_t x[NDIMS],
 {body}
 }}
 '''
+
+
+def smats_from_jac_src(ndims):
+    """S-matrices (adjugate) and determinant from a Jacobian ``j[d][i] =
+    d x_i/d xi_d`` -- the second half of ``calc_smats_detj``."""
+    if ndims == 2:
+        body = '''
+    s[0][0] =  j[1][1]; s[0][1] = -j[1][0];
+    s[1][0] = -j[0][1]; s[1][1] =  j[0][0];
+    d = s[0][0]*s[1][1] - s[0][1]*s[1][0];'''
+    else:
+        body = ''.join(f'''
+    s[{i}][0] = j[{a}][1]*j[{b}][2] - j[{a}][2]*j[{b}][1];
+    s[{i}][1] = j[{a}][2]*j[{b}][0] - j[{a}][0]*j[{b}][2];
+    s[{i}][2] = j[{a}][0]*j[{b}][1] - j[{a}][1]*j[{b}][0];'''
+                       for i, (a, b) in enumerate([(1, 2), (2, 0), (0, 1)]))
+        body += '''
+    d = j[0][0]*s[0][0] + j[0][1]*s[0][1] + j[0][2]*s[0][2];'''
+
+    return f'''
+__device__ __forceinline__ void
+smats_detj_from_jac(const fpdtype_t j[NDIMS][NDIMS],
+                    fpdtype_t s[NDIMS][NDIMS], fpdtype_t &d)
+{{
+{body}
+}}
+'''
+
+
+def multilinear_jacobian(jac_exprs, ndims, nverts):
+    """Monomial form of the Jacobian expressions of a linear element.
+
+    ``jac_exprs[d][i]`` (C expressions in the vertices ``V[n][i]`` and the
+    reference point ``x[e]``, supplied by the shape class exactly as the
+    reference's ``jac_exprs`` template argument) is linear in ``V`` with
+    coefficients multilinear in ``x``.  Returns ``(monos, W)`` with
+    ``monos`` a list of variable-index tuples (``()`` is the constant) and
+    ``W[d][k][n]`` such that
+
+        j[d][i] = sum_k prod(x[e] for e in monos[k]) * sum_n W[d][k][n]*V[n][i]
+
+    or None when the expressions are not of that form.  The inner sums
+    depend on the element only, so a kernel forms them once per element
+    and evaluates the Jacobian at a point with a handful of FMAs instead
+    of ``nverts*ndims`` products per entry."""
+    import itertools as it
+
+    import numpy as np
+
+    monos = [m for r in range(ndims + 1)
+             for m in it.combinations(range(ndims), r)]
+    rng = np.random.default_rng(7)
+    xs = rng.uniform(-1, 1, size=(4*len(monos), ndims))
+    A = np.array([[np.prod(x[list(m)]) for m in monos] for x in xs])
+
+    W = np.zeros((ndims, len(monos), nverts))
+    for d in range(ndims):
+        for n in range(nverts):
+            cref = None
+            for i in range(ndims):
+                V = np.zeros((nverts, ndims))
+                V[n][i] = 1.0
+                try:
+                    vals = np.array([eval(jac_exprs[d][i],
+                                          {'V': V, 'x': x}) for x in xs])
+                except Exception:
+                    return None
+
+                c, *_ = np.linalg.lstsq(A, vals, rcond=None)
+                if np.abs(A @ c - vals).max() > 1e-12:
+                    return None
+                if cref is None:
+                    cref = c
+                elif np.abs(c - cref).max() > 1e-12:
+                    return None
+
+            cref[np.abs(cref) < 1e-12] = 0.0
+            W[d, :, n] = cref
+
+    # Coefficients of these maps are small dyadic rationals: snap them
+    Wr = np.round(W*1024)/1024
+    if np.abs(Wr - W).max() > 1e-12:
+        return None
+
+    return monos, Wr
 
 
 def physics_defines(c, visc_corr='none', viscous=False):

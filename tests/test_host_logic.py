@@ -1,0 +1,339 @@
+"""CPU tests of the oracle physics (analytic checks), of the host logic
+(partition invariance, layout, view arithmetic) and of what the B200
+backend *plans* to launch (dry runtime: kernels are generated and the graph
+rewrites applied, nothing is executed)."""
+
+import re
+
+import numpy as np
+import pytest
+
+from oracle.npbackend import LocalComm
+from pyfr_b200 import base, cases
+from pyfr_b200.host.config import Config
+from pyfr_b200.host.system import get_system
+
+from util import (OracleBackend, conservation_defect, oracle_rhs, rel_err,
+                  run_lockstep)
+
+
+def _with_ics(txt, ics):
+    return txt[:txt.index('[soln-ics]')] + '[soln-ics]\n' + ics
+
+
+def _oracle_system(cfg, box, **beopts):
+    for k, v in beopts.items():
+        cfg.set('backend-oracle', k, v)
+    be = OracleBackend(cfg)
+    return get_system(be, box.local_mesh(), cfg, 2)
+
+
+# -- analytic checks of the restated kernel arithmetic ---------------------
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (3, 3, 2), dict(order=3, warp=0.15)),
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, rsolver='hllc', beta=0.0)),
+    ('vortex', 5, dict(order=3)),
+])
+def test_free_stream_preserved(case, n, kw):
+    """Uniform flow on a non-affine mesh has zero RHS (metric identities,
+    consistency of the Riemann solvers and of the LDG fluxes)."""
+    warp = kw.pop('warp', None)
+    txt = cases.tgv_cfg(**kw) if case == 'tgv' else cases.vortex_cfg(**kw)
+    w = 'w = 0.1\n' if case == 'tgv' else ''
+    cfg = Config(_with_ics(txt, f'rho = 1.2\nu = 0.3\nv = -0.2\n{w}p = 2.5\n'))
+    box = (cases.tgv_mesh(n, warp=warp) if case == 'tgv'
+           else cases.vortex_mesh(n))
+
+    s = _oracle_system(cfg, box)
+    s.rhs(0.0, 0, 1)
+
+    assert np.abs(s.ele_scal_upts(1)[0]).max() < 2e-12
+
+
+def test_vortex_rhs_converges_at_design_order():
+    """The isentropic vortex translates with velocity (0, 1): the exact
+    time derivative is -d/dy of the initial condition.  The Euler RHS
+    must converge to it at order >= p between two meshes."""
+    errs = []
+    for n in (40, 80):
+        cfg, box = cases.make('vortex', n, order=3)
+        s = _oracle_system(cfg, box)
+        s.rhs(0.0, 0, 1)
+        rhs = s.ele_scal_upts(1)[0]
+
+        # Central difference of the analytic IC in y (h^2 error 1e-10)
+        h = 1e-4
+        ics = []
+        for sgn in (+1, -1):
+            txt = cases.vortex_cfg(order=3)
+            i = txt.index('[soln-ics]')
+            txt = txt[:i] + re.sub(r'\by\b', f'(y + {sgn*h})', txt[i:])
+            c2 = Config(txt)
+            s2 = _oracle_system(c2, box)
+            ics.append(s2.ele_scal_upts(0)[0])
+        exact = -(ics[0] - ics[1])/(2*h)
+
+        errs.append(np.sqrt(np.mean((rhs - exact)**2)))
+
+    assert errs[1] < errs[0]/8.0, errs
+
+
+def test_shear_layer_viscous_rhs_converges_to_exact():
+    """rho, p uniform, u = A sin(y), v = w = 0: convection and pressure
+    terms vanish identically and d(rho u)/dt = mu u'' = -mu A sin(y),
+    dE/dt = d/dy(mu u u') = mu A^2 cos(2y).  Exercises the whole viscous
+    path (gradient correction, LDG common solution/flux, divergence): the
+    discrete RHS must converge to the exact one at high order."""
+    from pyfr_b200.host.elements import NavierStokesElements
+    from pyfr_b200.host.shapes import shape_map
+
+    A, mu, errs = 0.5, 0.05, []
+    ics = f'rho = 1\nu = {A}*sin(y)\nv = 0\nw = 0\np = 10\n'
+    txt = cases.tgv_cfg(order=4).replace('mu = 6.25e-4', f'mu = {mu}')
+
+    for n in (8, 16):
+        cfg = Config(_with_ics(txt, ics))
+        box = cases.tgv_mesh((2, n, 2))
+        s = _oracle_system(cfg, box)
+        s.rhs(0.0, 0, 1)
+        rhs = s.ele_scal_upts(1)[0]
+
+        e = NavierStokesElements(shape_map['hex'],
+                                 box.local_mesh().spts['hex'], cfg)
+        y = e.ploc_at_np('upts')[:, 1]
+
+        errs.append((np.abs(rhs[:, 1] + mu*A*np.sin(y)).max()/(mu*A),
+                     np.abs(rhs[:, 4] - mu*A*A*np.cos(2*y)).max()/(mu*A*A)))
+        assert np.abs(rhs[:, 0]).max() < 1e-12
+        assert np.abs(rhs[:, 2]).max() < 1e-4*(8/n)**4
+
+    (m0, e0), (m1, e1) = errs
+    assert m1 < 2e-3 and m1 < m0/8, errs
+    assert e1 < 2e-2 and e1 < e0/6, errs
+
+
+# -- partition invariance -------------------------------------------------------
+@pytest.mark.parametrize('case,n,parts,kw', [
+    ('tgv', (4, 2, 2), (2, 1, 1), dict(order=2, warp=0.1, beta=0.0)),
+    ('tgv', (4, 4, 2), (2, 2, 1), dict(order=2, warp=0.1, beta=0.0,
+                                       rsolver='hllc')),
+    ('tgv', (4, 4, 4), (2, 2, 2), dict(order=1, warp=0.05, beta=0.0)),
+    ('vortex', (6, 4), (2, 1), dict(order=3)),
+    ('vortex', (4, 6), (2, 2), dict(order=2, rsolver='hllc')),
+])
+def test_partitioned_rhs_equals_single_partition(case, n, parts, kw):
+    """N partitions exchanging halos (in-process ranks) reproduce the
+    single-partition RHS element for element.  (Only for Euler and for
+    LDG beta = 0: with beta != 0 the reference orients the one-sided LDG
+    fluxes of an inter-partition face by rank parity, pyfr/solvers/
+    baseadvecdiff/inters.py:47-58, and those of an interior face by face
+    order, so a partitioned run is a *different*, equally valid
+    discretisation; that case is pinned by the reference-host fixtures in
+    test_oracle_golden.py and by conservation below.)"""
+    warp = {'warp': kw.pop('warp')} if 'warp' in kw else {}
+    _, ref = oracle_rhs(case, n, **warp, **kw)
+
+    _, box = cases.make(case, n, **warp, **kw)
+    nparts = int(np.prod(parts))
+    vparts = box.brick_partition(parts)
+    systems, out = oracle_rhs(case, n, vparts=vparts, nparts=nparts, **warp,
+                              **kw)
+
+    et = box.etype
+    seen = np.zeros(box.neles, dtype=int)
+    for r, (s, o) in enumerate(zip(systems, out)):
+        gidx = box.local_mesh(vparts, r).eidxs[et]
+        seen[gidx] += 1
+        assert rel_err(o, ref[0][..., gidx]) < 5e-13
+
+    assert np.all(seen == 1)
+
+
+@pytest.mark.parametrize('case,n,parts,kw', [
+    ('tgv', (3, 2, 2), (1, 1, 1), dict(order=3, warp=0.1)),
+    ('tgv', (4, 2, 2), (2, 1, 1), dict(order=2, warp=0.1, rsolver='hllc')),
+    ('tgv', (2, 2, 4), (1, 1, 2), dict(order=2, beta=-0.5)),
+    ('tgv', (4, 4, 2), (2, 2, 1), dict(order=1, warp=0.1, beta=0.25)),
+    ('vortex', (6, 4), (2, 1), dict(order=3)),
+])
+def test_rhs_is_conservative(case, n, parts, kw):
+    """The RHS integrates to zero over the periodic domain for every
+    conserved variable, for any partitioning and LDG orientation."""
+    warp = {'warp': kw.pop('warp')} if 'warp' in kw else {}
+    cfg, box = cases.make(case, n, **warp, **kw)
+    nparts = int(np.prod(parts))
+    vparts = box.brick_partition(parts) if nparts > 1 else None
+    systems, out = oracle_rhs(case, n, vparts=vparts, nparts=nparts, **warp,
+                              **kw)
+
+    tot = mag = 0
+    for r, o in enumerate(out):
+        t, m = conservation_defect(cfg, box.local_mesh(vparts, r), o)
+        tot, mag = tot + t, mag + m
+
+    assert np.all(np.abs(tot) <= 1e-12*mag.max()), (tot, mag)
+
+
+def test_mpi_interfaces_agree_on_point_order():
+    """Both sides of an inter-partition interface list their flux points
+    in the same physical order (what makes the dense halo message
+    meaningful without an index exchange)."""
+    from pyfr_b200.host.elements import NavierStokesElements
+    from pyfr_b200.host.shapes import shape_map
+
+    cfg, box = cases.make('tgv', (4, 2, 2), order=2, warp=0.1)
+    vparts = box.brick_partition((2, 1, 1))
+    L = box.hi - box.lo
+
+    locs = {}
+    for r in range(2):
+        m = box.local_mesh(vparts, r)
+        e = NavierStokesElements(shape_map['hex'], m.spts['hex'], cfg)
+        con = m.con_p[1 - r]
+        pts = []
+        for etype, fidx, eidxs, _ in con.foreach():
+            rows = e.srtd_face_fpts[fidx][eidxs]
+            pts.append((con, fidx, e.plocfpts[rows, eidxs[:, None]]))
+        # Re-assemble in connectivity order
+        full = np.empty((len(con), e.nfacefpts[0], 3))
+        for etype, fidx, eidxs, ix in con.foreach():
+            rows = e.srtd_face_fpts[fidx][eidxs]
+            full[ix] = e.plocfpts[rows, eidxs[:, None]]
+        locs[r] = full
+
+    d = np.abs(locs[0] - locs[1])
+    d = np.minimum(d, np.abs(d - L))          # periodic images coincide
+    assert d.max() < 1e-9
+
+
+# -- storage layout and view arithmetic ---------------------
+@pytest.mark.parametrize('blocks,k,csub', [(0, 8, 8), (1, 8, 8), (1, 4, 8),
+                                           (1, 8, 16)])
+def test_matrix_layout_formula(blocks, k, csub):
+    cfg, _ = cases.make('tgv', 2)
+    for o, v in (('blocks', blocks), ('soasz', k), ('csubsz', csub)):
+        cfg.set('backend-oracle', o, v)
+    be = OracleBackend(cfg)
+
+    nrow, nvar, n = 7, 5, 37
+    a = np.random.default_rng(1).standard_normal((nrow, nvar, n))
+    m = be.matrix((nrow, nvar, n), a, tags={'align'})
+    be.commit()
+
+    assert np.array_equal(m.get(), a)
+
+    flat = m.basedata[m.offset:m.offset + m.nbytes].view(np.float64)
+    for (r, v, e) in [(0, 0, 0), (3, 2, 17), (6, 4, 36), (5, 1, 8)]:
+        if blocks:
+            # [n/csub][nrow][csub/k][nvar][k]
+            b, ee = divmod(e, csub)
+            ix = (b*m.blocksz + r*m.leaddim + (ee // k)*nvar*k + v*k + ee % k)
+        else:
+            # [nrow][n/k][nvar][k]
+            ix = r*m.leaddim + (e // k)*nvar*k + v*k + e % k
+        assert flat[ix] == a[r, v, e]
+
+
+def test_view_mapping_formula():
+    """mapping = offset + block displacement + row*leaddim + SoA column
+    (pyfr/backends/base/types.py:294-320)."""
+    cfg, _ = cases.make('tgv', 2)
+    cfg.set('backend-oracle', 'blocks', 1)
+    be = OracleBackend(cfg)
+
+    nrow, nvar, n, k = 6, 5, 20, be.soasz
+    m = be.matrix((nrow, nvar, n), tags={'align'}, extent='x')
+    m2 = be.matrix((nrow, nvar, n), tags={'align'}, extent='x')
+    be.commit()
+
+    rng = np.random.default_rng(2)
+    rmap, cmap = rng.integers(0, nrow, 50), rng.integers(0, n, 50)
+    mats = np.where(rng.integers(0, 2, 50) == 0, m.mid, m2.mid)
+    v = be.view(mats, rmap, cmap, vshape=(nvar,))
+    be.commit()
+
+    got = v.mapping.get()[0]
+    it = m.itemsize
+    for i in range(50):
+        mm = m if mats[i] == m.mid else m2
+        b, e = divmod(cmap[i], be.csubsz)
+        exp = (mm.offset//it + b*mm.blocksz + rmap[i]*mm.leaddim +
+               (e // k)*nvar*k + e % k)
+        assert got[i] == exp
+
+
+# -- what the B200 backend plans (no device needed) ---------------------------
+def _dry_plan(case, n, opts={}, nparts=1, **kw):
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box = cases.make(case, n, **kw)
+    for k, v in opts.items():
+        cfg.set('backend-b200', k, v)
+
+    be = B200Backend(cfg, dry=True)
+    parts = (2,) + (1,)*(box.ndims - 1)
+    vparts = box.brick_partition(parts) if nparts > 1 else None
+    comm = type('C', (), dict(rank=0, size=nparts))()
+    s = get_system(be, box.local_mesh(vparts, 0), cfg, 2, comm=comm)
+
+    return be, [[(w, getattr(k, 'kind', None) if w == 'kernel' else
+                  [r.kind for r in k]) for w, k in g.plan]
+                for g in s.rhs_graphs(0, 1)]
+
+
+def test_b200_ns_rhs_is_five_launches(built):
+    be, plan = _dry_plan('tgv', 2, order=4)
+    kinds = [[k for w, k in g] for g in plan]
+
+    assert kinds == [['mul', 'intconu'], ['gradflux', None],
+                     ['mul+negdivconf']]
+
+
+def test_b200_unfused_plan_keeps_reference_decomposition(built):
+    be, plan = _dry_plan('tgv', 2, {'fusion': 0}, order=2)
+    kinds = [k for g in plan for w, k in g]
+
+    assert kinds.count('mul') == 8          # disu, 2 grad, 3 fpts, 2 div
+    assert 'copy' in kinds and 'gradflux' not in kinds
+
+
+def test_b200_partitioned_plan_exchanges_once_per_graph(built):
+    be, plan = _dry_plan('tgv', (4, 2, 2), nparts=2, order=2)
+    xch = [[k for w, k in g if w == 'xchg'] for g in plan]
+
+    # scal_fpts in the first graph, vect_fpts in the second, none after
+    assert [len(x) for x in xch] == [1, 1, 0]
+    assert sorted(xch[0][0]) == ['recv', 'send']
+
+
+def test_b200_has_no_cpu_path(built):
+    from pyfr_b200.backend import B200Backend
+    from pyfr_b200.lib import B200NoDevice
+
+    cfg, box = cases.make('tgv', 2, order=2)
+    be = B200Backend(cfg, dry=True)
+    s = get_system(be, box.local_mesh(), cfg, 2)
+
+    with pytest.raises(B200NoDevice):
+        s.rhs(0.0, 0, 1)
+
+
+@pytest.mark.parametrize('beta,dead', [(0.5, True), (-0.5, True),
+                                       (0.0, False)])
+def test_b200_dead_gradient_rows(built, beta, dead):
+    """With a one-sided LDG flux only one side of every interface reads
+    the flux-point gradients; the fused kernel is then specialised not to
+    compute or store the other half (and says so in its traffic count)."""
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box = cases.make('tgv', 3, order=2, beta=beta)
+    be = B200Backend(cfg, dry=True)
+    s = get_system(be, box.local_mesh(), cfg, 2)
+    gf, = [k for g in s.rhs_graphs(0, 1) for w, k in g.plan
+           if w == 'kernel' and k.kind == 'gradflux']
+
+    assert gf.info['dead_rows'] == dead
+
+    nu, nf, LD, nb = 27, 54, 5*be.csubsz, -(-27 // be.csubsz)
+    full = (2*nu + nf + 3*nf)*LD*nb*8
+    assert gf.traffic == (full - 3*(nf // 2)*LD*nb*8 if dead else full)

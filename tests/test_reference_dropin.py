@@ -1,0 +1,73 @@
+"""The backend as a drop-in under the REFERENCE's own classes.
+
+Runs only where /root/reference exists (build container).  In a
+subprocess with ``PYFR_B200_BASE=pyfr.backends.base`` the B200 backend
+derives from the reference's ``BaseBackend``/``Matrix``/``View``/``Graph``
+and is driven by the reference's unmodified ``NavierStokesSystem`` /
+``EulerSystem`` (``pyfr/solvers/*``): every ``backend.kernel(...)`` call,
+view, exchange registration and ``Graph.group`` hint then comes from the
+reference's host code.  Without a GPU nothing can execute (dry runtime), so
+the check is that set-up, kernel generation, fusion and graph commit all
+succeed and yield the same launch plan as with this repository's host
+mirror."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_script = r'''
+import json, os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+sys.path.insert(0, %(root)r)
+from types import SimpleNamespace
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+rh.install_stubs()
+rh.set_rank(LocalComm(0, 1))
+from pyfr.inifile import Inifile
+from pyfr.backends.base import BaseBackend
+from pyfr.solvers.euler import EulerSystem
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr.util import subclass_where
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+assert subclass_where(BaseBackend, name='b200') is B200Backend
+
+out = {}
+for case, n, kw in [('tgv', 3, dict(order=4)), ('tgv', 3, dict(order=2, beta=0.0)),
+                    ('vortex', 4, dict(order=3))]:
+    txt = (cases.tgv_cfg(**kw) if case == 'tgv' else cases.vortex_cfg(**kw))
+    cfg = Inifile(txt)
+    _, box = cases.make(case, n, **kw)
+    be = B200Backend(cfg, dry=True)
+    regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+    s = cls(be, rh.ref_mesh(box.local_mesh()), None, regs, cfg, None)
+    s.commit()
+    out[f'{case}{kw}'] = [[getattr(k, 'kind', None) for w, k in g.plan if w == 'kernel']
+                          for g in s._rhs_graphs(0, 1)]
+print('RESULT ' + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_b200_backend_under_reference_host(built):
+    res = subprocess.run([sys.executable, '-c', _script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+    line, = [l for l in res.stdout.splitlines() if l.startswith('RESULT ')]
+    plans = json.loads(line[7:])
+
+    ns4, ns2, eu = plans.values()
+    assert ns4 == [['mul', 'intconu'], ['gradflux', None], ['mul+negdivconf']]
+    assert ns2 == [['mul', 'intconu'], ['gradflux', None], ['mul+negdivconf']]
+    assert [k for g in eu for k in g].count(None) >= 1      # intcflux
+    assert eu[-1][0] == 'tflux' and 'negdivconf' in eu[-1][-1]

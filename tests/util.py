@@ -55,3 +55,25 @@ def assert_parity(out, ref64, ref_ext, tol=1e-12, slack=4.0):
 
     assert err <= max(tol, slack*floor), (err, floor)
     return err, floor
+
+
+def conservation_defect(cfg, mesh, rhs):
+    """|sum over elements and points of w_p |J| RHS| per variable, relative
+    to sum w_p |J| |RHS|.  On a periodic domain the flux-reconstruction RHS
+    integrates to zero exactly (equal and opposite common fluxes, exact
+    quadrature of the flux divergence), whatever the partitioning, the
+    Riemann solver or the LDG parameters -- a size-independent parity
+    property that needs no reference evaluation."""
+    from pyfr_b200.host.elements import EulerElements, NavierStokesElements
+    from pyfr_b200.host.shapes import shape_map
+
+    cls = {'euler': EulerElements, 'navier-stokes': NavierStokesElements}[
+        cfg.get('solver', 'system')]
+    (et, spts), = mesh.spts.items()
+    e = cls(shape_map[et], spts, cfg)
+
+    wj = e.basis.upts_wts[:, None]/e.rcpdjac_at_np('upts')
+    tot = np.einsum('pe,pve->v', wj, rhs)
+    mag = np.einsum('pe,pve->v', wj, np.abs(rhs))
+
+    return tot, mag
