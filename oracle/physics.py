@@ -8,11 +8,14 @@ operating on lists of NumPy arrays, one array per variable.
 
 PARITY STATUS: *unpinned by the reference's own tests* -- the reference
 ships no golden vectors for flux, Riemann, gradient or RHS values
-(only operator matrices, see tests/test_shapes.py), and its kernels are
-Mako templates that cannot be rendered in this environment (no ``mako``).
-The restatement is therefore checked by analytic properties instead
-(tests/test_oracle_physics.py: free-stream preservation, Rusanov/HLLC
-consistency f(u,u,n) = F(u).n, conservation, order of accuracy).
+(only operator matrices, see tests/test_oracle_golden.py), and its kernels
+are Mako templates that cannot be rendered in this environment (no
+``mako``).  The restatement is therefore checked by analytic properties
+instead (tests/test_host_logic.py: free-stream preservation, Riemann-solver
+consistency f(u,u,n) = F(u).n and symmetry, discrete conservation, design
+order of accuracy of the Euler RHS, convergence of the viscous RHS to an
+exact solution) and by the reference's own host code driving it
+(tests/golden/make_golden.py).
 """
 
 import numpy as np

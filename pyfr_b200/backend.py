@@ -69,7 +69,7 @@ class B200Backend(base.BaseBackend):
         self.gradflux_threads = cfg.getint(sect, 'gradflux-threads', 0)
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
-        self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 2)
+        self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

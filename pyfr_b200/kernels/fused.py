@@ -522,7 +522,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None):
                                True)
 
     K = ConstPool(isz == 8)
-    em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 2))
+    em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 1))
 
     # Phase 1: G = A1 @ U + M6 @ C
     p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],

@@ -337,3 +337,36 @@ def test_b200_dead_gradient_rows(built, beta, dead):
     nu, nf, LD, nb = 27, 54, 5*be.csubsz, -(-27 // be.csubsz)
     full = (2*nu + nf + 3*nf)*LD*nb*8
     assert gf.traffic == (full - 3*(nf // 2)*LD*nb*8 if dead else full)
+
+
+@pytest.mark.parametrize('rs', ['rusanov', 'hllc'])
+@pytest.mark.parametrize('ndims', [2, 3])
+def test_riemann_solver_consistency_and_symmetry(rs, ndims):
+    """f(u, u, n) = F(u).n and f(l, r, n) = -f(r, l, -n)."""
+    from oracle import physics as ph
+
+    rng = np.random.default_rng(5)
+    nv, m = ndims + 2, 64
+    c = {'gamma': 1.4}
+
+    def state():
+        rho = rng.uniform(0.5, 2.0, m)
+        vel = rng.uniform(-1.0, 1.0, (ndims, m))
+        p = rng.uniform(0.5, 3.0, m)
+        E = p/(c['gamma'] - 1) + 0.5*rho*(vel**2).sum(axis=0)
+        return [rho, *(rho*v for v in vel), E]
+
+    n = rng.standard_normal((ndims, m))
+    n = list(n/np.sqrt((n**2).sum(axis=0)))
+    ul, ur = state(), state()
+
+    f, _, _ = ph.inviscid_flux(ul, ndims, nv, c)
+    fn = ph.rsolvers[rs](ul, ul, n, ndims, nv, c)
+    for i in range(nv):
+        exact = sum(n[j]*f[j][i] for j in range(ndims))
+        assert np.abs(fn[i] - exact).max() < 1e-12
+
+    a = ph.rsolvers[rs](ul, ur, n, ndims, nv, c)
+    b = ph.rsolvers[rs](ur, ul, [-x for x in n], ndims, nv, c)
+    for i in range(nv):
+        assert np.abs(a[i] + b[i]).max() < 1e-12
