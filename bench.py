@@ -266,7 +266,8 @@ def main():
 
     vparts = box.brick_partition(parts) if world > 1 else None
     t0 = time.time()
-    sysm = get_system(be, box.local_mesh(vparts, rank), cfg, 2, comm=comm)
+    nregs = 2 if args.no_e2e else 4
+    sysm = get_system(be, box.local_mesh(vparts, rank), cfg, nregs, comm=comm)
     setup_s = time.time() - t0
     ndof_local = sum(sysm.ele_ndofs)
     ndof = ndof_local*world
@@ -346,7 +347,7 @@ def main():
     nrep = min(args.steps, 10)
     acc = [0.0]*len(kernels)
 
-    if world == 1:
+    if True:
         for _ in range(nrep):
             for (a, b), (gi, i, k) in zip(evs, kernels):
                 rt.event_record(a, be.stream)
@@ -376,6 +377,18 @@ def main():
     peak_gbs = peaks.get('hbm_gbs', 6650.0)
     peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
 
+    # DRAM traffic per launch from the committed ncu --set full capture of
+    # this same workload (profiles/ncu_traffic.json), when there is one
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            tj = json.load(f)
+        if tj['workload'] == (f'tgv n={args.n} order={args.order} '
+                              f'{args.precision} {args.rsolver}'):
+            traffic = {k: v['dram_bytes'] for k, v in tj['kernels'].items()}
+    except (OSError, KeyError, ValueError):
+        pass
+
     if kt:
         dom = max(kt, key=lambda n: kt[n]['ms'])
         d = kt[dom]
@@ -383,7 +396,8 @@ def main():
         ksum = sum(v['ms'] for v in kt.values())
         roof = {
             'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak_gbs,
-            'unit': 'GB/s', 'frac': ach/peak_gbs, 'traffic': None,
+            'unit': 'GB/s', 'frac': ach/peak_gbs,
+            'traffic': traffic.get(dom), 'algorithmic_bytes': d['bytes'],
             'peak_source': peak_src, 'kernel_ms': d['ms'],
             'kernel_share_of_step': d['ms']/ksum,
             'sum_kernel_ms': ksum
@@ -400,33 +414,74 @@ def main():
     }
 
     # ---- end to end: host buffers in, host buffers out ---------------------
+    # Every step uploads its solution from pinned host memory, evaluates
+    # the RHS and downloads the result to pinned host memory.  Steps are
+    # software-pipelined over two bank pairs (0->1, 2->3) and three streams
+    # (upload / compute / download): step i+1's upload and step i-1's
+    # download overlap step i's RHS, each ordered by events, so the
+    # steady-state step time is the slowest of the three legs (PCIe).
     e2e = None
     if not args.no_e2e:
-        bank_in = sysm.ele_banks[0][0]
-        bank_out = sysm.ele_banks[0][1]
-        nb = bank_in.nbytes
-        hin = rt.new_ptr(rt.malloc_host, nb)
-        hout = rt.new_ptr(rt.malloc_host, nb)
-        rt.memcpy(hin, bank_in.data, nb)
+        banks = sysm.ele_banks[0]
+        nb = banks[0].nbytes
+        npair = 2 if len(banks) >= 4 else 1
+        hin = [rt.new_ptr(rt.malloc_host, nb) for _ in range(npair)]
+        hout = [rt.new_ptr(rt.malloc_host, nb) for _ in range(npair)]
+        for h in hin:
+            rt.memcpy(h, banks[0].data, nb)
+
+        s_in, s_out = (rt.new_ptr(rt.stream_create) for _ in range(2))
+        evn = lambda: [rt.new_ptr(rt.event_create) for _ in range(npair)]
+        ev_up, ev_rhs, ev_down = evn(), evn(), evn()
+        for p in range(npair):
+            rt.event_record(ev_rhs[p], be.stream)
+            rt.event_record(ev_down[p], be.stream)
+        ctr = [0]
 
         def step_e2e():
-            bank_in.upload_packed(hin)
-            sysm.rhs(0.0, 0, 1)
-            bank_out.download_packed(hout)
+            p = ctr[0] % npair
+            ctr[0] += 1
+            uin, fout = 2*p, 2*p + 1
 
-        for _ in range(2):
-            step_e2e()
+            # upload once the RHS that last read this input bank is done
+            rt.stream_wait_event(s_in, ev_rhs[p])
+            banks[uin].upload_packed(hin[p], s_in)
+            rt.event_record(ev_up[p], s_in)
+
+            # RHS after its upload and after the previous download of fout
+            rt.stream_wait_event(be.stream, ev_up[p])
+            rt.stream_wait_event(be.stream, ev_down[p])
+            sysm.rhs(0.0, uin, fout)
+            rt.event_record(ev_rhs[p], be.stream)
+
+            rt.stream_wait_event(s_out, ev_rhs[p])
+            banks[fout].download_packed(hout[p], s_out)
+            rt.event_record(ev_down[p], s_out)
+
+        def run_e2e(n):
+            # nothing may start before the start event ...
+            rt.event_record(ev_up[0], be.stream)
+            rt.stream_wait_event(s_in, ev_up[0])
+            for _ in range(n):
+                step_e2e()
+            # ... and the stop event follows the last downloads
+            for p in range(npair):
+                rt.stream_wait_event(be.stream, ev_down[p])
+
+        run_e2e(4)
         rt.device_sync()
 
-        esteps = max(3, min(args.steps, 10))
-        ems = timed(step_e2e, esteps)/esteps
+        esteps = max(4, min(args.steps, 10))
+        ems = timed(lambda: run_e2e(esteps), 1)/esteps
         e2e = {'value': ndof/(ems*1e-3)/1e9, 'unit': 'GDoF/s',
                'h2d_bytes_per_step': nb*world, 'd2h_bytes_per_step': nb*world,
                'ms_per_step': ems,
                'api': 'Matrix.upload_packed -> system.rhs -> '
-                      'Matrix.download_packed, pinned host memory'}
-        rt.free_host(hin)
-        rt.free_host(hout)
+                      'Matrix.download_packed, pinned host memory; steps '
+                      f'pipelined over {npair} bank pair(s) on separate '
+                      'upload/compute/download streams'}
+        for h in hin + hout:
+            rt.free_host(h)
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------
     cpu = None
@@ -455,8 +510,11 @@ def main():
                           indent=1)
 
     if world > 1:
+        # Leave the communicator to process exit (ncclCommDestroy blocks
+        # while the captured RHS graphs are alive)
         barrier()
-        be.comm.close()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -47,6 +47,9 @@ int b200_memcpy2d_async(void *dst, size_t dpitch, const void *src,
 /* -- streams & events  (driver.py:162-171; CUDAStream :258-277,
  *    CUDAEvent :280-304) -------------------------------------------------- */
 int b200_stream_create(void **stream);
+/* high != 0: greatest priority, so that exchange kernels launched beside a
+ * long-running grid are dispatched as soon as SM resources free up */
+int b200_stream_create_priority(void **stream, int high);
 int b200_stream_destroy(void *stream);
 int b200_stream_sync(void *stream);
 int b200_device_sync(void);

@@ -423,6 +423,53 @@ def _evalsrcmacros(be, tplargs, dims, extrns={}, ploc=None, u=None, **kw):
     return be.kernel_cls(run, rtnames=('t',))
 
 
+def _fieldeval(be, tplargs, dims, extrns={}, u=None, gradu=None, ploc=None,
+               wts=None, out=None, **kw):
+    """pyfr/plugins/kernels/fieldeval.mako (sum reduction) with
+    con_to_pri / grad_con_to_pri of pyfr/solvers/euler/kernels/eos.mako."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    gm1 = tplargs['c']['gamma'] - 1
+    exprs = tplargs['exprs']
+
+    if tplargs['reduceop'] != 'sum' or ploc is not None:
+        raise NotImplementedError('oracle fieldeval: weighted sums only')
+
+    fns = {'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'sin': np.sin,
+           'cos': np.cos, 'tan': np.tan, 'tanh': np.tanh, 'pow': np.power,
+           'fabs': np.abs, 'fmin': np.minimum, 'fmax': np.maximum}
+
+    def run(t=0.0):
+        cons = list(_stacked(u, nv))
+        invrho = 1.0/cons[0]
+        rhov = cons[1:nd + 1]
+        vel = [invrho*r for r in rhov]
+        pri = [cons[0], *vel,
+               gm1*(cons[nv - 1] - 0.5*invrho*sum(r*r for r in rhov))]
+        env = dict(fns, pri=pri, t=t)
+
+        if tplargs['has_grads']:
+            gc = _stacked(gradu, nv, nlead=nd)          # [d][v]
+            gp = [[None]*nd for _ in range(nv)]
+            for d in range(nd):
+                gp[0][d] = gc[d][0]
+            for i in range(nd):
+                for d in range(nd):
+                    gp[i + 1][d] = invrho*(gc[d][i + 1] - vel[i]*gc[d][0])
+            for d in range(nd):
+                term = 0
+                for i in range(nd):
+                    term = term + (vel[i]*gc[d][i + 1]
+                                   + rhov[i]*gp[i + 1][d])
+                gp[nv - 1][d] = gm1*(gc[d][nv - 1] - 0.5*term)
+            env['grad_pri'] = gp
+
+        w, o = _plain(wts), _plain(out)
+        for j, e in enumerate(exprs):
+            o[:, j] = (w*eval(e, {'__builtins__': {}}, env)).sum(axis=1)
+
+    return be.kernel_cls(run, rtnames=('t',))
+
+
 def _mpi_rows(xm, n):
     """A received halo matrix as its ``[nvrow*nvcol][n]`` rows: 'mpi'
     arguments are tightly packed and addressed ``(nv*i + v)*_nx + x``
@@ -560,6 +607,7 @@ _pointwise_impls = {
     'pyfr.solvers.navstokes.kernels.mpiconu': _mpiconu,
     'pyfr.solvers.navstokes.kernels.intcflux': _cflux_ns(False),
     'pyfr.solvers.navstokes.kernels.mpicflux': _cflux_ns(True),
+    'pyfr.plugins.kernels.fieldeval': _fieldeval,
 }
 
 

@@ -80,7 +80,7 @@ class B200Backend(base.BaseBackend):
 
         # Compute stream, communication stream and fork/join events
         self.stream = rt.new_ptr(rt.stream_create)
-        self.comm_stream = rt.new_ptr(rt.stream_create)
+        self.comm_stream = rt.new_ptr(rt.stream_create_priority, 1)
         self.fork_event = rt.new_ptr(rt.event_create)
         self.join_event = rt.new_ptr(rt.event_create)
 

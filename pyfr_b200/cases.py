@@ -85,9 +85,9 @@ p = pow(1 - S*S*M*M*(gamma - 1)*exp(2*(1 - x*x - y*y)/(2*R*R))/(8*pi*pi), gamma/
 '''
 
 
-def tgv_mesh(n, warp=0.0):
+def tgv_mesh(n, warp=0.0, curved=0.0):
     n = (n,)*3 if np.isscalar(n) else n
-    return BoxMesh(n, -np.pi, np.pi, periodic=True, warp=warp)
+    return BoxMesh(n, -np.pi, np.pi, periodic=True, warp=warp, curved=curved)
 
 
 def vortex_mesh(n=40):
@@ -97,8 +97,8 @@ def vortex_mesh(n=40):
 
 def make(case, n, **kw):
     if case == 'tgv':
-        warp = kw.pop('warp', 0.0)
-        return Config(tgv_cfg(**kw)), tgv_mesh(n, warp)
+        warp, curved = kw.pop('warp', 0.0), kw.pop('curved', 0.0)
+        return Config(tgv_cfg(**kw)), tgv_mesh(n, warp, curved)
     elif case == 'vortex':
         return Config(vortex_cfg(**kw)), vortex_mesh(n)
     else:

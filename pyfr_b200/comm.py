@@ -98,7 +98,15 @@ class NCCLComm:
         self.rt.nccl_allreduce(self._handle, ptr, ptr, count, dtype_code, op,
                                stream)
 
-    def close(self):
-        if self._handle:
+    def close(self, destroy=False):
+        """Release the communicator.
+
+        ``ncclCommDestroy`` blocks for as long as CUDA graphs that captured
+        operations on the communicator are alive (observed on NCCL 2.27:
+        every rank hangs in it while the RHS graphs exist), and the RHS
+        graphs live as long as the system object.  The default is therefore
+        to leave the communicator to process exit; pass ``destroy=True``
+        only after every graph that used it has been destroyed."""
+        if self._handle and destroy:
             self.rt.nccl_destroy(self._handle)
-            self._handle = None
+        self._handle = None

@@ -257,6 +257,15 @@ int b200_stream_create(void **stream) {
     return 0;
 }
 
+int b200_stream_create_priority(void **stream, int high) {
+    int lo = 0, hi = 0;
+    RT(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s;
+    RT(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo));
+    *stream = s;
+    return 0;
+}
+
 int b200_stream_destroy(void *stream) { RT(cudaStreamDestroy(S(stream))); return 0; }
 int b200_stream_sync(void *stream) { RT(cudaStreamSynchronize(S(stream))); return 0; }
 int b200_device_sync(void) { RT(cudaDeviceSynchronize()); return 0; }

@@ -337,6 +337,28 @@ def elide_copy_fpts(be, program):
 
             npts += vin.n
 
+    # Partition-boundary points are stored by ``mpiconu`` kernels, which
+    # write their output for every beta (navstokes/kernels/mpiconu.mako)
+    # but run in a later graph, after the halo has arrived: count the
+    # points of every other view the backend has bound for *writing* into
+    # the common-solution buffer
+    here = {id(getattr(v, 'view', v)) for k in conus
+            for v in (k.info['ulout'], k.info['urout']) if v is not None}
+    lo = dst.offset // dst.itemsize
+    hi = lo + (dst.nblocks - 1)*dst.blocksz + dst.nrow*dst.leaddim
+    seen = set()
+    for v, mode in be.view_uses:
+        if mode != 'w' or id(v) in here or id(v) in seen or \
+           int(v.basedata) != int(dst.basedata):
+            continue
+        seen.add(id(v))
+
+        m = v.mapping.get()[0]
+        if v.n and (m.min() < lo or m.max() >= hi):
+            return program
+
+        npts += v.n
+
     nele = src.ioshape[-1] if hasattr(src, 'ioshape') else None
     if nele is None or npts != src.nrow*nele:
         return program

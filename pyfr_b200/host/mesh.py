@@ -78,7 +78,7 @@ class BoxMesh:
     boundaries named ``'<axis>lo'`` / ``'<axis>hi'``.
     """
 
-    def __init__(self, n, lo, hi, periodic=True, warp=0.0):
+    def __init__(self, n, lo, hi, periodic=True, warp=0.0, curved=0.0):
         self.n = n = tuple(int(v) for v in n)
         self.ndims = nd = len(n)
         self.etype = 'quad' if nd == 2 else 'hex'
@@ -87,6 +87,10 @@ class BoxMesh:
         self.periodic = ((periodic,)*nd if isinstance(periodic, bool)
                          else tuple(periodic))
         self.warp = warp
+        # Fraction of each partition's elements flagged as curved (they
+        # then take the stored-metric kernel path; geometrically they are
+        # the same multilinear cells)
+        self.curved = curved
         self.neles = int(np.prod(n))
 
         nfaces = 2*nd
@@ -182,7 +186,7 @@ class BoxMesh:
                     cidxmap=self.cidxmap)
         mesh.eidxs[et] = gidx
         mesh.spts[et] = self.vertices(gidx)
-        mesh.spts_curved[et] = np.zeros(nloc, dtype=bool)
+        mesh.spts_curved[et] = np.arange(nloc) < int(round(self.curved*nloc))
 
         # Global -> local numbering for this partition
         g2l = np.full(self.neles, -1, dtype=np.int64)

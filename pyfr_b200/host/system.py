@@ -106,8 +106,17 @@ class BaseSystem:
         self._gen_kernels()
         self.backend.commit()
 
+        # What the post-step field integrator needs of the elements
+        # (reference: intg.system.ele_map / eles_vect_upts)
+        self.eles_vect_upts = [getattr(e, '_grad_upts', None)
+                               for e in self.ele_map.values()]
+        self.ele_quad = [(e.basis.upts_wts, e.rcpdjac_at_np('upts'),
+                          e.privars, e.ndims, e.nvars, e.nupts, e.neles)
+                         for e in self.ele_map.values()]
+
         del self.ele_map, self._int_inters, self._mpi_inters
         self._graphs = {}
+        self._ggraphs = {}
 
     def _gen_kernels(self):
         self._kernels = kernels = defaultdict(list)
@@ -340,6 +349,47 @@ class NavierStokesSystem(BaseSystem):
         g3.commit()
 
         return g1, g2, g3
+
+
+    def _compute_grads_graph(self, uin):
+        """Physical gradients of bank ``uin`` at the solution points, left
+        in ``eles_vect_upts`` (pyfr/solvers/baseadvecdiff/system.py:233-286;
+        used by post-step plugins such as ``integrate``)."""
+        m, k = self._mpireqs, self._get_kernels(uin, None)
+        deps = lambda dk, *names: self._kdeps(k, dk, *names)
+        be = self.backend
+
+        g1 = be.graph()
+        g1.add_mpi_reqs(m['scal_fpts_recv'])
+        g1.add_all(k['eles/disu'])
+        g1.add_all(k['mpiint/scal_fpts_pack'], deps=k['eles/disu'])
+        for send, pack in zip(m['scal_fpts_send'],
+                              k['mpiint/scal_fpts_pack']):
+            g1.add_mpi_req(send, deps=[pack])
+        for l in k['eles/copy_fpts']:
+            g1.add(l, deps=deps(l, 'eles/disu'))
+        kd = k['eles/copy_fpts'] or k['eles/disu']
+        g1.add_all(k['iint/con_u'], deps=kd)
+        g1.add_all(k['eles/tgradpcoru_upts'], deps=k['iint/con_u'])
+        g1.commit()
+
+        g2 = be.graph()
+        g2.add_all(k['mpiint/scal_fpts_unpack'])
+        for l in k['mpiint/con_u']:
+            g2.add(l, deps=deps(l, 'mpiint/scal_fpts_unpack'))
+        g2.add_all(k['eles/tgradcoru_upts'], deps=k['mpiint/con_u'])
+        for l in k['eles/gradcoru_u']:
+            g2.add(l, deps=deps(l, 'eles/tgradcoru_upts'))
+        g2.commit()
+
+        return g1, g2
+
+    def compute_grads(self, t, uinbank):
+        if uinbank not in self._ggraphs:
+            self._ggraphs[uinbank] = self._compute_grads_graph(uinbank)
+
+        for g in self._ggraphs[uinbank]:
+            self.backend.run_graph(g)
 
 
 system_map = {'euler': EulerSystem, 'navier-stokes': NavierStokesSystem}

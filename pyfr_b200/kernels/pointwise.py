@@ -216,3 +216,109 @@ negdivconf({', '.join(args)})
 }}
 '''
     return src, 'negdivconf', [a.split()[-1].lstrip('*') for a in args]
+
+
+def fieldeval_source(be, tplargs, npts):
+    """``fieldeval`` (``pyfr/plugins/kernels/fieldeval.mako``, sum
+    reduction): per element, the weighted sum over its points of each
+    expression in the primitive variables (``pri[i]``), their physical
+    gradients (``grad_pri[i][d]``, ``con_to_pri``/``grad_con_to_pri`` of
+    ``pyfr/solvers/euler/kernels/eos.mako:17-45``) and the time ``t``.
+
+    The expressions arrive as C text (the reference compiles them the same
+    way, ``pyfr/plugins/fieldeval.py:12-22``) and are pasted into the
+    kernel.  One thread owns one element and walks its points, so the
+    per-element result needs no inter-thread reduction."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    exprs, grads = tplargs['exprs'], tplargs['has_grads']
+
+    if tplargs['reduceop'] != 'sum' or tplargs.get('use_views'):
+        raise NotImplementedError('fieldeval: only the sum reduction over '
+                                  'element matrices is on the b200 path')
+
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', npts),
+            ('NEXPRS', len(exprs)),
+            ('C_GM1', ph.fpconst(tplargs['c']['gamma'] - 1))]
+
+    args = ['int neles', 'const fpdtype_t* __restrict__ u', 'long long u_bsz']
+    if grads:
+        args += ['const fpdtype_t* __restrict__ gradu', 'long long gradu_bsz']
+    args += ['const fpdtype_t* __restrict__ wts', 'long long wts_bsz',
+             'int wts_ld', 'fpdtype_t* __restrict__ out',
+             'long long out_bsz', 'int out_ld', 'fpdtype_t t']
+
+    gsrc = r'''
+        fpdtype_t grad_pri[NVARS][NDIMS];
+        {
+            fpdtype_t gc[NDIMS][NVARS], vel[NDIMS], rhov[NDIMS];
+            UNROLL for (int d = 0; d < NDIMS; d++)
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    gc[d][v] = gradu[blk*gradu_bsz
+                                     + (long long) (d*NPTS + p)*LD
+                                     + COFF(e, v, NVARS)];
+            UNROLL for (int i = 0; i < NDIMS; i++)
+            {
+                rhov[i] = cons[i + 1];
+                vel[i] = invrho*rhov[i];
+            }
+            UNROLL for (int d = 0; d < NDIMS; d++)
+                grad_pri[0][d] = gc[d][0];
+            UNROLL for (int i = 0; i < NDIMS; i++)
+                UNROLL for (int d = 0; d < NDIMS; d++)
+                    grad_pri[i + 1][d] = invrho*(gc[d][i + 1]
+                                                 - vel[i]*gc[d][0]);
+            UNROLL for (int d = 0; d < NDIMS; d++)
+            {
+                fpdtype_t term = 0;
+                UNROLL for (int i = 0; i < NDIMS; i++)
+                    term += vel[i]*gc[d][i + 1] + rhov[i]*grad_pri[i + 1][d];
+                grad_pri[NVARS - 1][d] = C_GM1*(gc[d][NVARS - 1]
+                                                - FP(0.5)*term);
+            }
+        }
+''' if grads else ''
+
+    esrc = '\n'.join(f'        acc[{j}] += w*({e});'
+                     for j, e in enumerate(exprs))
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+#define LD (NVARS*C_SUB)
+
+extern "C" __global__ void __launch_bounds__(128)
+fieldeval({', '.join(args)})
+{{
+    const long long gid = (long long) blockIdx.x*blockDim.x + threadIdx.x;
+    const int e = (int) (gid % C_SUB);
+    const long long blk = gid / C_SUB;
+
+    if (blk*C_SUB + e >= neles)
+        return;
+
+    fpdtype_t acc[NEXPRS] = {{}};
+
+    for (int p = 0; p < NPTS; p++)
+    {{
+        fpdtype_t cons[NVARS], pri[NVARS];
+        UNROLL for (int v = 0; v < NVARS; v++)
+            cons[v] = u[blk*u_bsz + (long long) p*LD + COFF(e, v, NVARS)];
+
+        const fpdtype_t invrho = FP(1.0)/cons[0];
+        fpdtype_t ke = 0;
+        pri[0] = cons[0];
+        UNROLL for (int i = 0; i < NDIMS; i++)
+        {{
+            pri[i + 1] = invrho*cons[i + 1];
+            ke += cons[i + 1]*cons[i + 1];
+        }}
+        pri[NVARS - 1] = C_GM1*(cons[NVARS - 1] - FP(0.5)*invrho*ke);
+{gsrc}
+        const fpdtype_t w = __ldg(wts + blk*wts_bsz + (long long) p*wts_ld + e);
+{esrc}
+    }}
+
+    UNROLL for (int j = 0; j < NEXPRS; j++)
+        out[blk*out_bsz + (long long) j*out_ld + e] = acc[j];
+}}
+'''
+    return src, 'fieldeval', [a.split()[-1].lstrip('*') for a in args]

@@ -45,6 +45,7 @@ _functions = [
     (c_int, 'b200_memcpy2d_async', _vp, c_size_t, _vp, c_size_t, c_size_t,
      c_size_t, _vp),
     (c_int, 'b200_stream_create', _vpp),
+    (c_int, 'b200_stream_create_priority', _vpp, c_int),
     (c_int, 'b200_stream_destroy', _vp),
     (c_int, 'b200_stream_sync', _vp),
     (c_int, 'b200_device_sync'),
@@ -179,7 +180,8 @@ class DryRuntime:
         return 1
 
     def __getattr__(self, name):
-        if name in ('malloc', 'stream_create', 'event_create'):
+        if name in ('malloc', 'stream_create', 'event_create',
+                    'stream_create_priority'):
             return name
         if name in ('free', 'stream_destroy', 'event_destroy',
                     'module_unload', 'graph_destroy', 'free_host'):

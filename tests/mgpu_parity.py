@@ -32,13 +32,17 @@ def main():
     parts = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
     n = tuple(3*p for p in parts)
     ok = True
+    comm = None
 
     for case, kw in [('tgv', dict(order=3, rsolver='hllc')),
                      ('tgv', dict(order=4)), ('tgv', dict(order=2, beta=0.0))]:
         cfg, box = cases.make(case, n, warp=0.1, **kw)
         cfg.set('backend-b200', 'device-id', os.environ.get('LOCAL_RANK', 0))
         be = B200Backend(cfg)
-        be.comm = comm = NCCLComm(be.rt, rank, world)
+        # One communicator for the whole run (NCCL bring-up takes ~30 s)
+        if comm is None:
+            comm = NCCLComm(be.rt, rank, world)
+        be.comm = comm
 
         vparts = box.brick_partition(parts)
         mesh = box.local_mesh(vparts, rank)
@@ -61,9 +65,10 @@ def main():
         print(f'[rank {rank}/{world}] {case} {kw}: neles={len(gidx)} '
               f'nbrs={sorted(mesh.con_p)} err={err:.2e} floor={floor:.2e} '
               f'{"PASS" if good else "FAIL"}', flush=True)
-        comm.close()
 
-    sys.exit(0 if ok else 1)
+    # No ncclCommDestroy: it blocks while captured graphs are alive
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == '__main__':

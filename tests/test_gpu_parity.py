@@ -39,7 +39,8 @@ def b200_rhs(case, n, opts={}, **kw):
 @pytest.mark.parametrize('kw', [
     dict(order=2), dict(order=2, rsolver='hllc'), dict(order=2, beta=0.0),
     dict(order=2, beta=-0.5), dict(order=3, rsolver='hllc'), dict(order=4),
-    dict(order=4, rsolver='hllc')
+    dict(order=4, rsolver='hllc'), dict(order=3, curved=0.5),
+    dict(order=2, curved=1.0, rsolver='hllc')
 ], ids=str)
 @pytest.mark.parametrize('variant', list(VARIANTS))
 def test_tgv_rhs_matches_oracle(built, kw, variant):
@@ -107,3 +108,23 @@ def test_free_stream_preserved(built):
     sysm.rhs(0.0, 0, 1)
 
     assert np.abs(sysm.ele_scal_upts(1)[0]).max() < 1e-11
+
+
+@pytest.mark.parametrize('kw', [dict(order=2), dict(order=4),
+                                dict(order=3, rsolver='hllc', beta=0.0)],
+                         ids=str)
+def test_tgv_rhs_fp32(built, kw):
+    """Single precision (the layout doubles the SoA width to 16): held to
+    the fp32 oracle's own distance from the fp64 oracle -- at M = 0.1 the
+    RHS is a cancellation of O(1/M^2) terms, so fp32 round-off alone is
+    1e-4..1e-3 of the field maximum."""
+    n = (4, 3, 3)
+    _, r64 = oracle_rhs('tgv', n, warp=0.1, **kw)
+    _, r32 = oracle_rhs('tgv', n, warp=0.1, precision='single', **kw)
+    _, out = b200_rhs('tgv', n, {}, warp=0.1, precision='single', **kw)
+
+    assert out.dtype == np.float32
+    floor = rel_err(r32[0].astype(float), r64[0])
+    err = rel_err(out.astype(float), r64[0])
+
+    assert err <= max(4*floor, 1e-5), (err, floor)

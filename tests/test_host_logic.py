@@ -305,6 +305,11 @@ def test_b200_partitioned_plan_exchanges_once_per_graph(built):
     assert [len(x) for x in xch] == [1, 1, 0]
     assert sorted(xch[0][0]) == ['recv', 'send']
 
+    # copy_fpts is elided here too: interior points are stored by intconu
+    # (both sides), partition-boundary points by mpiconu in the next graph
+    kinds = [k for g in plan for w, k in g if w == 'kernel']
+    assert 'copy' not in kinds and 'mpiconu' in kinds
+
 
 def test_b200_has_no_cpu_path(built):
     from pyfr_b200.backend import B200Backend
