@@ -13,6 +13,7 @@ the backend's communication stream, directly on the device buffers.
 import ctypes as ct
 import os
 import socket
+import sys
 import time
 
 import numpy as np
@@ -70,7 +71,18 @@ class NCCLComm:
             rt.nccl_unique_id(uid)
 
         raw = _rendezvous(rank, size, uid.raw, addr, port)
-        self._handle = rt.new_ptr(rt.nccl_init, size, rank, raw)
+
+        # NCCL may print its version banner on stdout (NCCL_DEBUG set in
+        # the environment); keep this process's stdout clean for callers
+        # that parse it by pointing fd 1 at stderr while it initialises
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            self._handle = rt.new_ptr(rt.nccl_init, size, rank, raw)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     @classmethod
     def from_env(cls, rt):

@@ -181,11 +181,32 @@ class B200Graph(base.Graph):
         if reqs:
             last = max((i for i, (w, r) in enumerate(self.program)
                         if w == 'xchg'), default=-1)
+
+            # A graph that only receives has no pack kernel to anchor the
+            # exchange to and the base scheduler lists its receives first.
+            # Posting them there would park the NCCL kernel's CTAs on some
+            # SMs, spinning until the peer sends (which it does only after
+            # *its* element kernel), and the persistent element kernel of
+            # this rank -- one CTA per SM, all of the shared memory -- could
+            # not be co-resident with them: it would run in two waves.  So
+            # a receive-only exchange is issued where the sending side
+            # issues its half: just before the last kernel of the graph.
+            if all(r.kind == 'recv' for r in reqs) and kerns:
+                last = max(i for i, (w, k) in enumerate(self.program)
+                           if w == 'kernel' and k is kerns[-1]) - 1
+                while last >= 0 and self.program[last][0] != 'kernel':
+                    last -= 1
+
+            issued = False
             for i, (what, obj) in enumerate(self.program):
+                if last < 0 and not issued:
+                    plan.append(('xchg', reqs))
+                    issued = True
                 if what == 'kernel':
                     plan.append(('kernel', obj))
-                if i == last:
+                if i == last and not issued:
                     plan.append(('xchg', reqs))
+                    issued = True
         else:
             plan = [('kernel', k) for k in kerns]
 
