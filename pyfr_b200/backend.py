@@ -70,6 +70,7 @@ class B200Backend(base.BaseBackend):
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
+        self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

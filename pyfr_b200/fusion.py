@@ -97,6 +97,39 @@ def row_need_classes(be, mat, nrows, nblocks, maxclasses=15):
     return cls.ravel(), masks
 
 
+def region_is_affine(verts, tol=1e-12):
+    """Do all elements of a linear-element vertex matrix ``(nverts, ndims,
+    neles)`` have a constant Jacobian?  True when every non-constant
+    monomial coefficient of the multilinear map vanishes, i.e. the
+    elements are parallelograms / parallelepipeds."""
+    # ``verts`` may be the column slice of the linear region
+    root = _root(verts)
+    V = root.get()
+    if root is not verts:
+        nv = V.shape[1]
+        V = V[..., verts.ca // nv:verts.cb // nv]
+    nverts, nd, ne = V.shape
+
+    if nverts != 2**nd or ne == 0:
+        return False
+
+    # Vertex n sits at (+-1, ..) with sign bit e of n along axis e; the
+    # coefficient of monomial m is sum_n prod_{e in m} sign_e(n) V[n]/2^nd
+    sg = np.array([[1.0 if (n >> e) & 1 else -1.0 for e in range(nd)]
+                   for n in range(nverts)])
+    scale = np.abs(V - V.mean(axis=0)).max()
+
+    for m in range(1, 2**nd):
+        axes = [e for e in range(nd) if (m >> e) & 1]
+        if len(axes) < 2:
+            continue
+        w = np.prod(sg[:, axes], axis=1)
+        if np.abs(np.einsum('n,nie->ie', w, V)).max() > tol*scale*nverts:
+            return False
+
+    return True
+
+
 def fuse_gradflux(be, kerns, subs):
     """tgradpcoru .. tdivtpcorf of one element type -> ``gradflux``."""
     from pyfr_b200.providers import B200Kernel
@@ -171,9 +204,11 @@ def fuse_gradflux(be, kerns, subs):
         nblocks = -(-neles // be.csubsz)
         pts = ti['upts'].get() if ti['upts'] is not None else None
 
+        affine = ('linear' in ktype and be.affine_fastpath and
+                  region_is_affine(ti['verts']))
         src, name, meta = kfused.gradflux_source(
             be, ops, ti['tplargs'], pts, LD,
-            rowcls=None if rneed is None else rneed[0]
+            rowcls=None if rneed is None else rneed[0], affine=affine
         )
         fn = be.pointwise._function(src, name)
         fn.set_smem(meta['smem'])
@@ -213,7 +248,8 @@ def fuse_gradflux(be, kerns, subs):
             (meta['nthreads'], 1, 1), meta['smem'], args,
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
             traffic=words*isz, kind='gradflux',
-            info=dict(replaces=kerns, dead_rows=rneed is not None)
+            info=dict(replaces=kerns, dead_rows=rneed is not None,
+                      affine=affine)
         ))
 
     return out

@@ -474,13 +474,20 @@ def find_planes(blocks, maxsize=36):
     return comps
 
 
-def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None):
+def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
+                    affine=False):
     """Source of the fused kernel.
 
     ``rowcls``: optional class index (< 16) per flux-point row; the kernel
     then takes a per-block bit mask ``fmask`` and neither computes nor
     stores the gradients of rows whose class bit is clear (rows no
     interface kernel ever reads, see fusion.row_need_classes).
+
+    ``affine``: every element of the region has a constant Jacobian (the
+    caller has checked the vertices); the metric terms are then formed once
+    per block by each thread for the one element it works on and kept in
+    registers, instead of being re-evaluated from shared memory at every
+    point in phases 2 and 4.
 
     ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
     ``M6`` (ndims*nupts x nfpts), ``M0`` (nfpts x nupts) and ``A5``
@@ -609,7 +616,40 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None):
         mj = (ph.multilinear_jacobian(tplargs['jac_exprs'], nd, nverts)
               if getattr(be, 'gradflux_monojac', True) else None)
 
-        if mj is not None:
+        if mj is not None and affine and nthreads % csub == 0:
+            # Constant Jacobian: only the constant monomial survives
+            monos, W = mj
+            k0 = monos.index(())
+            jl = []
+            for d in range(nd):
+                for i in range(nd):
+                    terms = ' '.join(
+                        f'{"+" if W[d, k0, n] > 0 else "-"} '
+                        f'{ph.fpconst(abs(W[d, k0, n]))}*'
+                        f'VS[{n}*(NDIMS*C_SUB) + COFF(ea, {i}, NDIMS)]'
+                        for n in range(nverts) if W[d, k0, n] != 0)
+                    jl.append(f'jm[{d}][{i}] = {terms or "FP(0.0)"};')
+
+            gsrc = (f'static __device__ const fpdtype_t c_pts[2] = '
+                    '{FP(0.0), FP(0.0)};\n' + ph.smats_from_jac_src(nd))
+            geo_elem = (r'''
+        // Affine elements: one Jacobian per element, held in registers
+        // (this thread only ever works on element tid % C_SUB of a block)
+        fpdtype_t sA[NDIMS][NDIMS], rjA;
+        {
+            const int ea = tid % C_SUB;
+            fpdtype_t jm[NDIMS][NDIMS], djac;
+            ''' + '\n            '.join(jl) + r'''
+            smats_detj_from_jac(jm, sA, djac);
+            rjA = FP(1.0)/djac;
+        }
+''')
+            geom = r'''
+            const fpdtype_t (&s)[NDIMS][NDIMS] = sA;
+            const fpdtype_t rcpdjac_v = rjA;
+'''
+            npt_words, q_words = 2, 0
+        elif mj is not None:
             # Per element: Q[q][i] = sum_n W[d][k][n] V[n][i] for every
             # (d, monomial k) with a non-zero coefficient; per point: the
             # monomial values.  j[d][i] = sum_k mono_k(x_p) Q[(d,k)][i].

@@ -128,3 +128,28 @@ def test_tgv_rhs_fp32(built, kw):
     err = rel_err(out.astype(float), r64[0])
 
     assert err <= max(4*floor, 1e-5), (err, floor)
+
+
+@pytest.mark.parametrize('kw', [dict(order=2), dict(order=4),
+                                dict(order=3, rsolver='hllc', beta=0.0),
+                                dict(order=4, precision='single')],
+                         ids=str)
+@pytest.mark.parametrize('opts', [{}, {'gradflux-threads': 640}], ids=str)
+def test_tgv_rhs_affine_mesh(built, kw, opts):
+    """Uniform (parallelepiped) elements take the constant-Jacobian fast
+    path of the fused kernel: the metric terms live in registers."""
+    n = (4, 3, 3)
+    _, ref = oracle_rhs('tgv', n, **kw)
+    sysm, out = b200_rhs('tgv', n, opts, **kw)
+
+    gf, = [k for g in sysm.rhs_graphs(0, 1) for w, k in g.plan
+           if w == 'kernel' and k.kind == 'gradflux']
+    assert gf.info['affine']
+
+    if kw.get('precision') == 'single':
+        _, r64 = oracle_rhs('tgv', n, **{**kw, 'precision': 'double'})
+        floor = rel_err(ref[0].astype(float), r64[0])
+        assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
+    else:
+        _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+        assert_parity(out, ref[0], ext[0], TOL64)

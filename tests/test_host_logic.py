@@ -375,3 +375,17 @@ def test_riemann_solver_consistency_and_symmetry(rs, ndims):
     b = ph.rsolvers[rs](ur, ul, [-x for x in n], ndims, nv, c)
     for i in range(nv):
         assert np.abs(a[i] + b[i]).max() < 1e-12
+
+
+def test_affine_regions_are_detected(built):
+    from pyfr_b200.backend import B200Backend
+
+    def modes(**kw):
+        cfg, box = cases.make('tgv', 3, order=2, **kw)
+        s = get_system(B200Backend(cfg, dry=True), box.local_mesh(), cfg, 2)
+        return [k.info['affine'] for g in s.rhs_graphs(0, 1)
+                for w, k in g.plan if w == 'kernel' and k.kind == 'gradflux']
+
+    assert modes() == [True]
+    assert modes(warp=0.1) == [False]
+    assert modes(curved=0.5) == [False, True]      # curved region, linear
