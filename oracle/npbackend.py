@@ -36,7 +36,7 @@ def _stacked(m, nvar, nlead=None):
     """View with the variable (and leading stack) axes in front:
     ``[nlead,] nvar, nblocks, npts, nchunks, k``."""
     k = m.backend.soasz
-    a = _mat3(m)
+    a = _mat3(m, padto=nvar*k)
     nb, nrow, w = a.shape
     a = a.reshape(nb, nrow, w // (nvar*k), nvar, k)
 
@@ -595,6 +595,56 @@ def _cflux_ns(mpi):
     return build
 
 
+def _bc_env(ploc, t):
+    env = {'t': t}
+    if ploc is not None:
+        env['ploc'] = list(ploc.get())
+    return env
+
+
+def _bcconu(be, tplargs, dims, extrns={}, ulin=None, ulout=None, nlin=None,
+            ploc=None, **kw):
+    """pyfr/solvers/navstokes/kernels/bcconu.mako"""
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    vi, vo, nl = _ViewRef(ulin), _ViewRef(ulout), list(nlin.get())
+
+    def run(t=0.0):
+        l = [vi.load(i) for i in range(nv)]
+        mag = np.sqrt(sum(x*x for x in nl))
+        n = [(1/mag)*x for x in nl]
+        ur = ph.bc_ldg_state(tplargs['bctype'], l, n, nd, nv, c,
+                             _bc_env(ploc, t))
+        for i in range(nv):
+            vo.store(ur[i] + 0*l[0], i)
+
+    return be.kernel_cls(run, rtnames=('t',))
+
+
+def _bccflux(viscous):
+    def build(be, tplargs, dims, extrns={}, ul=None, gradul=None,
+              artvisc=None, nl=None, ploc=None, **kw):
+        """euler/kernels/bccflux.mako, navstokes/kernels/bccflux.mako"""
+        nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+        vl, n = _ViewRef(ul), list(nl.get())
+        gl = _ViewRef(gradul) if viscous else None
+
+        def run(t=0.0):
+            l = [vl.load(i) for i in range(nv)]
+            g = ([[gl.load(j, d) for j in range(nv)] for d in range(nd)]
+                 if viscous else None)
+            fn = ph.bc_common_flux(
+                tplargs['bctype'], tplargs.get('bccfluxstate'), l, g, n, nd,
+                nv, c, tplargs['rsolver'], _bc_env(ploc, t), viscous,
+                tplargs.get('visc_corr', 'none')
+            )
+            for i in range(nv):
+                vl.store(fn[i], i)
+
+        return be.kernel_cls(run, rtnames=('t',))
+
+    return build
+
+
 _pointwise_impls = {
     'pyfr.solvers.euler.kernels.tflux': _tflux_euler,
     'pyfr.solvers.navstokes.kernels.tflux': _tflux_ns,
@@ -608,6 +658,9 @@ _pointwise_impls = {
     'pyfr.solvers.navstokes.kernels.intcflux': _cflux_ns(False),
     'pyfr.solvers.navstokes.kernels.mpicflux': _cflux_ns(True),
     'pyfr.plugins.kernels.fieldeval': _fieldeval,
+    'pyfr.solvers.navstokes.kernels.bcconu': _bcconu,
+    'pyfr.solvers.navstokes.kernels.bccflux': _bccflux(True),
+    'pyfr.solvers.euler.kernels.bccflux': _bccflux(False),
 }
 
 

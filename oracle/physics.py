@@ -253,3 +253,170 @@ def ldg_common_solution(ul, ur, beta):
     else:
         com = [r*(0.5 + beta) + l*(0.5 - beta) for l, r in zip(ul, ur)]
         return com, com
+
+
+# -- boundary conditions --------------------------------------------------------
+def _bcval(c, key, env):
+    """A BC constant: a number, or a C expression string (already
+    substituted by the host, pyfr/solvers/baseadvec/inters.py:98-119) in
+    terms of ``ploc[i]`` and ``t``."""
+    v = c[key]
+    if isinstance(v, str):
+        fns = {'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'sin': np.sin,
+               'cos': np.cos, 'tan': np.tan, 'tanh': np.tanh, 'pow': np.power,
+               'fabs': np.abs}
+        return eval(v, {'__builtins__': {}}, dict(fns, **env))
+    return v
+
+
+def _ke2(u, ndims):
+    return sum(u[i + 1]*u[i + 1] for i in range(ndims))
+
+
+def bc_rsolve_state(bctype, ul, nl, ndims, nvars, c, env):
+    """``bc_rsolve_state`` of pyfr/solvers/{euler,navstokes}/kernels/bcs/
+    <bctype>.mako: the ghost state handed to the Riemann solver."""
+    gamma = c['gamma']
+    gmo = gamma - 1.0
+    uvw = 'uvw'[:ndims]
+
+    if bctype == 'no-slp-adia-wall':
+        return [ul[0], *(-ul[i + 1] for i in range(ndims)), ul[nvars - 1]]
+    elif bctype == 'slp-adia-wall':
+        nor = sum(ul[i + 1]*nl[i] for i in range(ndims))
+        return [ul[0], *(ul[i + 1] - 2*nor*nl[i] for i in range(ndims)),
+                ul[nvars - 1]]
+    elif bctype == 'no-slp-isot-wall':
+        ur = [ul[0]] + [-ul[i + 1] + 2*_bcval(c, v, env)*ul[0]
+                        for i, v in enumerate(uvw)]
+        ur.append((c['cpTw']/gamma)*ur[0] + 0.5*(1.0/ur[0])*_ke2(ur, ndims))
+        return ur
+    elif bctype == 'sup-out-fn':
+        return list(ul)
+    elif bctype == 'sup-in-fa':
+        rho = _bcval(c, 'rho', env)
+        ur = [rho + 0*ul[0]] + [rho*_bcval(c, v, env) + 0*ul[0] for v in uvw]
+        ur.append(_bcval(c, 'p', env)/gmo + 0.5*(1.0/ur[0])*_ke2(ur, ndims))
+        return ur
+    elif bctype == 'sub-in-frv':
+        rho = _bcval(c, 'rho', env)
+        ur = [rho + 0*ul[0]] + [rho*_bcval(c, v, env) + 0*ul[0] for v in uvw]
+        ur.append(ul[nvars - 1] - 0.5*(1.0/ul[0])*_ke2(ul, ndims)
+                  + 0.5*(1.0/ur[0])*_ke2(ur, ndims))
+        return ur
+    elif bctype == 'sub-out-fp':
+        return [*ul[:nvars - 1],
+                _bcval(c, 'p', env)/gmo + 0.5*(1.0/ul[0])*_ke2(ul, ndims)]
+    elif bctype == 'char-riem-inv':
+        pe, rhoe = _bcval(c, 'p', env), _bcval(c, 'rho', env)
+        ve = [_bcval(c, v, env) for v in uvw]
+
+        cs = np.sqrt(gamma*pe/rhoe)
+        s = pe*rhoe**(-gamma)
+        ratio = cs*(2.0/gmo)
+
+        inv = 1.0/ul[0]
+        V_e = sum(ve[i]*nl[i] for i in range(ndims))
+        V_i = inv*sum(ul[i + 1]*nl[i] for i in range(ndims))
+        p_i = gmo*ul[nvars - 1] - (0.5*gmo)*inv*_ke2(ul, ndims)
+        c_i = np.sqrt(gamma*p_i*inv)
+
+        sup = np.abs(V_e) >= cs
+        R_e = np.where(sup & (V_i >= 0), V_i - c_i*(2.0/gmo), V_e - ratio)
+        R_i = np.where(sup & (V_i < 0), V_e + ratio, V_i + c_i*(2.0/gmo))
+        V_b = 0.5*(R_e + R_i)
+        c_b = (0.25*gmo)*(R_i - R_e)
+        rho_b = np.where(
+            V_i < 0, ((1.0/(gamma*s))*c_b*c_b)**(1.0/gmo),
+            ul[0]*(ul[0]*c_b*c_b/(gamma*p_i))**(1.0/gmo)
+        )
+        p_b = (1.0/gamma)*rho_b*c_b*c_b
+
+        ur = [rho_b]
+        for i in range(ndims):
+            ur.append(np.where(
+                V_i >= 0, rho_b*(ul[i + 1]*inv + (V_b - V_i)*nl[i]),
+                rho_b*(ve[i] + (V_b - V_e)*nl[i])
+            ))
+        ur.append(p_b*(1.0/gmo) + 0.5*(1.0/ur[0])*_ke2(ur, ndims))
+        return ur
+    else:
+        raise NotImplementedError(f'oracle: boundary type {bctype!r}')
+
+
+def bc_ldg_state(bctype, ul, nl, ndims, nvars, c, env):
+    """``bc_ldg_state`` (navstokes/kernels/bcs/<bctype>.mako): the state
+    the LDG common solution / viscous ghost flux is built from."""
+    if bctype == 'no-slp-adia-wall':
+        return [ul[0], *(0.0*ul[0] for _ in range(ndims)),
+                ul[nvars - 1] - (0.5/ul[0])*_ke2(ul, ndims)]
+    elif bctype == 'no-slp-isot-wall':
+        ur = [ul[0]] + [_bcval(c, v, env)*ul[0] for v in 'uvw'[:ndims]]
+        ur.append((c['cpTw']/c['gamma'])*ur[0]
+                  + 0.5*(1.0/ur[0])*_ke2(ur, ndims))
+        return ur
+    else:
+        # aliased to bc_rsolve_state for every other type
+        return bc_rsolve_state(bctype, ul, nl, ndims, nvars, c, env)
+
+
+def bc_ldg_grad_state(bctype, ur, nl, gul, ndims, nvars):
+    """``bc_ldg_grad_state``: gradient used on the ghost side."""
+    if bctype in ('char-riem-inv', 'sup-in-fa', 'sub-in-frv', 'sub-out-fp'):
+        return [[0.0*g for g in row] for row in gul]
+    elif bctype in ('sup-out-fn', 'no-slp-isot-wall'):
+        return [list(row) for row in gul]
+    elif bctype == 'no-slp-adia-wall':
+        # no-slp-adia-wall.mako:22-75: remove the wall-normal temperature
+        # gradient from the copied gradients
+        rcprho = 1.0/ur[0]
+        vel = [rcprho*ur[i + 1] for i in range(ndims)]
+        dv = [[gul[d][i + 1] - vel[i]*gul[d][0] for d in range(ndims)]
+              for i in range(ndims)]
+        Tl = [gul[d][nvars - 1] - _lsum(rcprho*gul[d][0]*ur[nvars - 1],
+                                        *(vel[i]*dv[i][d]
+                                          for i in range(ndims)))
+              for d in range(ndims)]
+
+        gur = [list(row) for row in gul]
+        for d in range(ndims):
+            gur[d][nvars - 1] = gur[d][nvars - 1] - _lsum(
+                *(nl[d]*nl[e]*Tl[e] for e in range(ndims))
+            )
+        return gur
+    else:
+        raise NotImplementedError(f'oracle: boundary type {bctype!r}')
+
+
+def bc_common_flux(bctype, cflux_state, ul, gul, nl, ndims, nvars, c,
+                   rsolver, env, viscous, visc_corr='none'):
+    """bccflux kernels: euler/kernels/bccflux.mako and, for the viscous
+    system, ``bc_common_flux_state`` of navstokes/kernels/bcs/{ghost,
+    ghost-imperm}.mako or of the type's own template (slp-adia-wall)."""
+    mag = np.sqrt(sum(x*x for x in nl))
+    n = [(1/mag)*x for x in nl]
+
+    if not viscous or cflux_state is None:
+        ur = bc_rsolve_state(bctype, ul, n, ndims, nvars, c, env)
+        fn = rsolvers[rsolver](ul, ur, n, ndims, nvars, c)
+        return [mag*f for f in fn]
+
+    ur = bc_ldg_state(bctype, ul, n, ndims, nvars, c, env)
+    # ghost.mako passes ul, ghost-imperm.mako ur, as the state argument
+    gur = bc_ldg_grad_state(bctype, ul if cflux_state == 'ghost' else ur,
+                            n, gul, ndims, nvars)
+
+    fvr = [[0.0]*nvars for _ in range(ndims)]
+    viscous_flux_add(ur, gur, fvr, ndims, nvars, c, visc_corr)
+
+    ur = bc_rsolve_state(bctype, ul, n, ndims, nvars, c, env)
+    fi = rsolvers[rsolver](ul, ur, n, ndims, nvars, c)
+
+    out = []
+    for i in range(nvars):
+        fv = sum(n[j]*fvr[j][i] for j in range(ndims))
+        if cflux_state == 'ghost' and c['ldg-tau'] != 0.0:
+            fv = fv + c['ldg-tau']*(ul[i] - ur[i])
+        out.append(mag*(fi[i] + fv))
+
+    return out

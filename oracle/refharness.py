@@ -49,6 +49,17 @@ class StubComm:
     def recv_init(self, xm, pid, tag):
         return self.local.recv_init(xm, pid, tag)
 
+    # Per-boundary communicators (pyfr/solvers/base/system.py:275-278);
+    # only their existence matters on this path
+    handle = 0
+
+    def Split(self, color, key=0):
+        return self
+
+    @staticmethod
+    def fromhandle(handle):
+        return SimpleNamespace(free=lambda: None)
+
 
 def install_stubs():
     if 'pyfr' in sys.modules:

@@ -95,6 +95,59 @@ def vortex_mesh(n=40):
     return BoxMesh(n, -20.0, 20.0, periodic=True)
 
 
+# Boundary sections used by the wall-bounded parity cases
+BC_SECTIONS = {
+    'no-slp-adia-wall': 'type = no-slp-adia-wall\n',
+    'slp-adia-wall': 'type = slp-adia-wall\n',
+    'no-slp-isot-wall': 'type = no-slp-isot-wall\ncpTw = 250.0\nu = 0.1\n',
+    'char-riem-inv': ('type = char-riem-inv\nrho = 1.0\nu = 0.2\nv = 0.1\n'
+                      'w = 0.0\np = 71.0\n'),
+    'sup-out-fn': 'type = sup-out-fn\n',
+    'sup-in-fa': ('type = sup-in-fa\nrho = 1.0\nu = 0.2\nv = 0.1\nw = 0.0\n'
+                  'p = 71.0\n'),
+    'sub-in-frv': 'type = sub-in-frv\nrho = 1.0\nu = 0.2\nv = 0.1\nw = 0.0\n',
+    'sub-out-fp': 'type = sub-out-fp\np = 71.0\n',
+}
+
+
+def box_case(system, n, bcs, order=3, rsolver='rusanov', beta=0.5,
+             precision='double', warp=0.0):
+    """A box with boundaries: ``bcs`` maps boundary names (``'xlo'``,
+    ``'yhi'`` ...) to boundary types; axes without an entry stay periodic.
+    Navier-Stokes in 3-D (TGV initial condition), Euler in 2-D (vortex)."""
+    nd = 3 if system == 'navier-stokes' else 2
+    n = (n,)*nd if np.isscalar(n) else n
+    periodic = tuple(not any(b.startswith('xyz'[a]) for b in bcs)
+                     for a in range(nd))
+
+    # A smooth field with a mean flow through every face: boundary types
+    # that switch on the sign of the normal velocity (char-riem-inv) are
+    # then evaluated away from their discontinuity
+    if nd == 3:
+        txt = tgv_cfg(order=order, precision=precision, rsolver=rsolver,
+                      beta=beta)
+        ics = ('rho = 1 + 0.1*sin(x)*cos(y)\nu = 0.3 + 0.1*cos(x + y)\n'
+               'v = 0.15 + 0.1*sin(y)*cos(z)\nw = 0.1 + 0.05*sin(z + x)\n'
+               'p = 71*(1 + 0.02*cos(x)*sin(z))\n')
+        box = BoxMesh(n, -np.pi, np.pi, periodic=periodic, warp=warp)
+    else:
+        txt = vortex_cfg(order=order, precision=precision, rsolver=rsolver)
+        ics = ('rho = 1 + 0.1*sin(0.3*x)*cos(0.2*y)\n'
+               'u = 0.3 + 0.1*cos(0.2*(x + y))\nv = 0.15 + 0.1*sin(0.3*y)\n'
+               'p = 4.5*(1 + 0.02*cos(0.2*x))\n')
+        box = BoxMesh(n, -20.0, 20.0, periodic=periodic, warp=warp)
+
+    txt = txt[:txt.index('[soln-ics]')] + '[soln-ics]\n' + ics
+
+    for name, btype in bcs.items():
+        sect = BC_SECTIONS[btype]
+        if nd == 2:
+            sect = sect.replace('w = 0.0\n', '')
+        txt += f'\n[soln-bcs-{name}]\n{sect}'
+
+    return Config(txt), box, txt
+
+
 def make(case, n, **kw):
     if case == 'tgv':
         warp, curved = kw.pop('warp', 0.0), kw.pop('curved', 0.0)

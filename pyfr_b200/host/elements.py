@@ -330,6 +330,10 @@ class BaseElements:
         rows = self.srtd_face_fpts[fidx][eidxs]
         return self._pnorm_fpts[rows, eidxs[:, None]].reshape(-1, self.ndims)
 
+    def get_ploc_for_inters(self, eidxs, fidx):
+        rows = self.srtd_face_fpts[fidx][eidxs]
+        return self.plocfpts[rows, eidxs[:, None]].reshape(-1, self.ndims)
+
     def get_scal_fpts_for_inters(self, eidxs, fidx):
         return self._scal_fpts.mid, self.srtd_face_fpts[fidx][eidxs], None
 

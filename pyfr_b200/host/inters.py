@@ -8,10 +8,13 @@ Host-side counterpart of ``pyfr/solvers/base/inters.py:6-119``,
 over the element buffers for each side of each interface, the scaled
 normals, the memory-order permutation of interior interfaces, and declares
 the ``intconu/intcflux/mpiconu/mpicflux`` kernels with the reference's
-keyword arguments.  Boundary conditions are not part of this round's path.
+keyword arguments, and -- for boundaries -- the ``bcconu/bccflux`` kernels
+with the per-type template arguments of ``pyfr/solvers/euler/inters.py:
+50-110`` and ``pyfr/solvers/navstokes/inters.py:68-210``.
 """
 
 import itertools as it
+import math
 
 import numpy as np
 
@@ -256,3 +259,147 @@ class NavierStokesMPIInters(MPIInters):
             gradul=self._vect_lhs, gradur=self._vect_rhs,
             artvisc=None, nl=self._pnorm_lhs
         )
+
+
+class BCInters(BaseInters):
+    """Boundary interfaces: only a left-hand (interior) state exists; the
+    ghost state is a function of it, the normal and the section's
+    parameters (``pyfr/solvers/baseadvec/inters.py:52-119``)."""
+
+    type = None
+    cflux_state = None
+    # (option names, defaults) turned into C expressions / numbers
+    expr_opts, expr_defaults, eval_opts = (), {}, ()
+
+    def __init__(self, be, lhs, elemap, cfgsect, cfg):
+        super().__init__(be, lhs, elemap, cfg)
+        self.cfgsect = cfgsect
+        self.name = cfgsect.removeprefix('soln-bcs-')
+
+        self._perm = self._memory_order_perm(lhs)
+        self._pnorm_lhs = self._pnorms(lhs)
+        self.scal_lhs = self._scal_view(lhs, 'get_scal_fpts_for_inters')
+
+        self._external_args = {'t': 'scalar fpdtype_t'}
+        self._external_vals = {}
+
+        nd = self.ndims
+        if self.eval_opts:
+            from pyfr_b200.host.exprs import npeval
+            cc = cfg.items_as('constants', float)
+            for k in self.eval_opts:
+                self.c[k] = float(npeval(cfg.getexpr(cfgsect, k), cc))
+
+        opts = [o for o in self.expr_opts
+                if o not in 'uvw' or 'uvw'.index(o) < nd]
+        if opts:
+            self.c |= self._exp_opts(opts, lhs, self.expr_defaults)
+
+    def _exp_opts(self, opts, lhs, default={}):
+        cfg, sect = self.cfg, self.cfgsect
+
+        subs = cfg.items('constants')
+        subs |= dict(x='ploc[0]', y='ploc[1]', z='ploc[2]')
+        subs |= dict(abs='fabs', pi=str(math.pi))
+
+        exprs = {}
+        for k in opts:
+            if k in default:
+                exprs[k] = cfg.getexpr(sect, k, default[k], subs=subs)
+            else:
+                exprs[k] = cfg.getexpr(sect, k, subs=subs)
+
+        if any('ploc' in ex for ex in exprs.values()) and \
+           'ploc' not in self._external_args:
+            pl = side_const(lhs, self.elemap, 'get_ploc_for_inters',
+                            self.ndims)[self._perm]
+            self._external_args['ploc'] = f'in fpdtype_t[{self.ndims}]'
+            self._external_vals['ploc'] = self._be.const_matrix(
+                np.atleast_2d(pl.T))
+
+        return exprs
+
+    def _tplargs(self):
+        return self._rsolver_tplargs() | dict(bctype=self.type,
+                                              ninters=self.ninters)
+
+
+class EulerBCInters(BCInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be = self._be
+        be.pointwise.register('pyfr.solvers.euler.kernels.bccflux')
+        tplargs = self._tplargs()
+
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'bccflux', tplargs=tplargs, dims=[self.ninterfpts],
+            extrns=self._external_args, ul=self.scal_lhs,
+            nl=self._pnorm_lhs, **self._external_vals
+        )
+
+
+class NavierStokesBCInters(BCInters):
+    def __init__(self, *args):
+        super().__init__(*args)
+        be, lhs = self._be, self.lhs
+
+        self._vect_lhs = self._vect_view(lhs, 'get_vect_fpts_for_inters')
+        self._comm_lhs = self._scal_view(lhs, 'get_comm_fpts_for_inters')
+        self.c |= self.cfg.items_as('solver-interfaces', float)
+
+        tplargs = self._tplargs() | dict(
+            bccfluxstate=self.cflux_state,
+            visc_corr=self.cfg.get('solver', 'viscosity-correction', 'none'),
+            shock_capturing=self.cfg.get('solver', 'shock-capturing', 'none')
+        )
+
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.bcconu')
+        be.pointwise.register('pyfr.solvers.navstokes.kernels.bccflux')
+
+        self.kernels['con_u'] = lambda: be.kernel(
+            'bcconu', tplargs=tplargs, dims=[self.ninterfpts],
+            extrns=self._external_args, ulin=self.scal_lhs,
+            ulout=self._comm_lhs, nlin=self._pnorm_lhs,
+            **self._external_vals
+        )
+        self.kernels['comm_flux'] = lambda: be.kernel(
+            'bccflux', tplargs=tplargs, dims=[self.ninterfpts],
+            extrns=self._external_args, ul=self.scal_lhs,
+            gradul=self._vect_lhs, nl=self._pnorm_lhs, artvisc=None,
+            **self._external_vals
+        )
+
+
+def _bc(base, btype, cflux_state=None, expr_opts=(), expr_defaults={},
+        eval_opts=()):
+    return type(f'{base.__name__}_{btype}', (base,), dict(
+        type=btype, cflux_state=cflux_state, expr_opts=expr_opts,
+        expr_defaults=expr_defaults, eval_opts=eval_opts
+    ))
+
+
+_zero_vel = {'u': 0, 'v': 0, 'w': 0}
+
+euler_bc_map = {c.type: c for c in [
+    _bc(EulerBCInters, 'slp-adia-wall'),
+    _bc(EulerBCInters, 'sup-out-fn'),
+    _bc(EulerBCInters, 'sup-in-fa', expr_opts=('rho', 'p', 'u', 'v', 'w')),
+    _bc(EulerBCInters, 'char-riem-inv',
+        expr_opts=('rho', 'p', 'u', 'v', 'w')),
+]}
+
+navstokes_bc_map = {c.type: c for c in [
+    _bc(NavierStokesBCInters, 'no-slp-adia-wall', 'ghost-imperm'),
+    _bc(NavierStokesBCInters, 'no-slp-isot-wall', 'ghost-imperm',
+        expr_opts=('u', 'v', 'w'), expr_defaults=_zero_vel,
+        eval_opts=('cpTw',)),
+    _bc(NavierStokesBCInters, 'slp-adia-wall', None),
+    _bc(NavierStokesBCInters, 'char-riem-inv', 'ghost',
+        expr_opts=('rho', 'p', 'u', 'v', 'w')),
+    _bc(NavierStokesBCInters, 'sup-in-fa', 'ghost',
+        expr_opts=('rho', 'p', 'u', 'v', 'w')),
+    _bc(NavierStokesBCInters, 'sup-out-fn', 'ghost'),
+    _bc(NavierStokesBCInters, 'sub-in-frv', 'ghost',
+        expr_opts=('rho', 'u', 'v', 'w'), expr_defaults=_zero_vel),
+    _bc(NavierStokesBCInters, 'sub-out-fp', 'ghost', expr_opts=('p',)),
+]}

@@ -19,7 +19,8 @@ from pyfr_b200.base import NullKernel
 from pyfr_b200.host.elements import EulerElements, NavierStokesElements
 from pyfr_b200.host.inters import (EulerIntInters, EulerMPIInters,
                                    NavierStokesIntInters,
-                                   NavierStokesMPIInters)
+                                   NavierStokesMPIInters, euler_bc_map,
+                                   navstokes_bc_map)
 from pyfr_b200.host.shapes import shape_map
 
 
@@ -30,6 +31,7 @@ class SerialComm:
 class BaseSystem:
     name = None
     elementscls = intinterscls = mpiinterscls = None
+    bcmap = {}
     _nonces = it.count()
 
     def __init__(self, backend, mesh, initsoln, nregs, cfg, comm=None):
@@ -78,6 +80,20 @@ class BaseSystem:
             for p, con in mesh.con_p.items()
         ]
 
+        # Boundaries, in codec order (pyfr/solvers/base/system.py:262-306)
+        self._bc_inters = []
+        for c in mesh.codec:
+            if c.startswith('bc/') and c[3:] in mesh.bcon:
+                sect = f'soln-bcs-{c[3:]}'
+                cls = self.bcmap.get(cfg.get(sect, 'type'))
+                if cls is None:
+                    raise NotImplementedError(
+                        f'Boundary type {cfg.get(sect, "type")!r} is not on '
+                        'this path (see DESIGN.md)'
+                    )
+                self._bc_inters.append(cls(be, mesh.bcon[c[3:]], elemap,
+                                           sect, cfg))
+
     # -- exchange registration -------------------------------------------
     def register_mpi_exchange(self, name, views, send=None, recv=None):
         be, comm = self.backend, self.comm
@@ -115,6 +131,7 @@ class BaseSystem:
                          for e in self.ele_map.values()]
 
         del self.ele_map, self._int_inters, self._mpi_inters
+        del self._bc_inters
         self._graphs = {}
         self._ggraphs = {}
 
@@ -124,7 +141,7 @@ class BaseSystem:
         self._mpireqs = mpireqs = defaultdict(list)
 
         groups = [('eles', self.ele_map.values()), ('iint', self._int_inters),
-                  ('mpiint', self._mpi_inters)]
+                  ('mpiint', self._mpi_inters), ('bcint', self._bc_inters)]
 
         for pn, provs in groups:
             for p in provs:
@@ -205,6 +222,7 @@ class EulerSystem(BaseSystem):
     elementscls = EulerElements
     intinterscls = EulerIntInters
     mpiinterscls = EulerMPIInters
+    bcmap = euler_bc_map
 
     def _rhs_graphs(self, uin, fout):
         m, k = self._mpireqs, self._get_kernels(uin, fout)
@@ -220,6 +238,7 @@ class EulerSystem(BaseSystem):
             g1.add_mpi_req(send, deps=[pack])
         g1.add_all(k['iint/comm_flux'],
                    deps=k['eles/disu'] + k['mpiint/scal_fpts_pack'])
+        g1.add_all(k['bcint/comm_flux'], deps=k['eles/disu'])
         g1.commit()
 
         g2 = be.graph()
@@ -250,6 +269,7 @@ class NavierStokesSystem(BaseSystem):
     elementscls = NavierStokesElements
     intinterscls = NavierStokesIntInters
     mpiinterscls = NavierStokesMPIInters
+    bcmap = navstokes_bc_map
 
     def commit(self):
         self.register_mpi_exchange(
@@ -280,6 +300,7 @@ class NavierStokesSystem(BaseSystem):
             g1.add(l, deps=deps(l, 'eles/disu'))
         kd = k['eles/copy_fpts'] or k['eles/disu']
         g1.add_all(k['iint/con_u'], deps=kd + k['mpiint/scal_fpts_pack'])
+        g1.add_all(k['bcint/con_u'], deps=kd)
         g1.commit()
 
         # Gradients, flux, partial divergence
@@ -306,6 +327,8 @@ class NavierStokesSystem(BaseSystem):
             g2.add_mpi_req(send, deps=[pack])
 
         g2.add_all(k['iint/comm_flux'], deps=ideps,
+                   pdeps=k['mpiint/vect_fpts_pack'])
+        g2.add_all(k['bcint/comm_flux'], deps=ideps,
                    pdeps=k['mpiint/vect_fpts_pack'])
 
         for l in k['eles/tdisf']:
@@ -370,7 +393,9 @@ class NavierStokesSystem(BaseSystem):
             g1.add(l, deps=deps(l, 'eles/disu'))
         kd = k['eles/copy_fpts'] or k['eles/disu']
         g1.add_all(k['iint/con_u'], deps=kd)
-        g1.add_all(k['eles/tgradpcoru_upts'], deps=k['iint/con_u'])
+        g1.add_all(k['bcint/con_u'], deps=kd)
+        g1.add_all(k['eles/tgradpcoru_upts'],
+                   deps=k['iint/con_u'] + k['bcint/con_u'])
         g1.commit()
 
         g2 = be.graph()

@@ -609,7 +609,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         except NotFusable:
             em.tables = em.tables[:mark]
 
-    geo_elem = ''
+    geo_elem = geo_post = ''
     if linear:
         nverts = tplargs['nverts']
         gargs = 'const fpdtype_t* __restrict__ verts, long long verts_bsz'
@@ -633,22 +633,38 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             gsrc = (f'static __device__ const fpdtype_t c_pts[2] = '
                     '{FP(0.0), FP(0.0)};\n' + ph.smats_from_jac_src(nd))
             geo_elem = (r'''
-        // Affine elements: one Jacobian per element, held in registers
-        // (this thread only ever works on element tid % C_SUB of a block)
-        fpdtype_t sA[NDIMS][NDIMS], rjA;
+        // Affine elements: one Jacobian per element.  C_SUB threads form
+        // the metric terms of the block's elements; after the next barrier
+        // every thread picks up those of the one element it works on
+        // (tid % C_SUB, the same in every round) and keeps them in
+        // registers through phases 2 and 4.
+        if (tid < C_SUB)
         {
-            const int ea = tid % C_SUB;
-            fpdtype_t jm[NDIMS][NDIMS], djac;
+            const int ea = tid;
+            fpdtype_t jm[NDIMS][NDIMS], sm[NDIMS][NDIMS], djac;
             ''' + '\n            '.join(jl) + r'''
-            smats_detj_from_jac(jm, sA, djac);
-            rjA = FP(1.0)/djac;
+            smats_detj_from_jac(jm, sm, djac);
+            UNROLL for (int i = 0; i < NDIMS; i++)
+                UNROLL for (int j = 0; j < NDIMS; j++)
+                    QS[ea*(NDIMS*NDIMS + 1) + i*NDIMS + j] = sm[i][j];
+            QS[ea*(NDIMS*NDIMS + 1) + NDIMS*NDIMS] = FP(1.0)/djac;
         }
 ''')
+            geo_post = r'''
+        fpdtype_t sA[NDIMS][NDIMS], rjA;
+        {
+            const fpdtype_t *q = QS + (tid % C_SUB)*(NDIMS*NDIMS + 1);
+            UNROLL for (int i = 0; i < NDIMS; i++)
+                UNROLL for (int j = 0; j < NDIMS; j++)
+                    sA[i][j] = q[i*NDIMS + j];
+            rjA = q[NDIMS*NDIMS];
+        }
+'''
             geom = r'''
             const fpdtype_t (&s)[NDIMS][NDIMS] = sA;
             const fpdtype_t rcpdjac_v = rjA;
 '''
-            npt_words, q_words = 2, 0
+            npt_words, q_words = 2, (nd*nd + 1)*csub
         elif mj is not None:
             # Per element: Q[q][i] = sum_n W[d][k][n] V[n][i] for every
             # (d, monomial k) with a non-zero coefficient; per point: the
@@ -880,7 +896,7 @@ gradflux(int nblocks, int neles,
             }}
         }}
         __syncthreads();
-
+{geo_post}
         // u and ucomm are consumed: fetch the next block's behind the
         // remaining phases
         if (tid == 0 && nxt < nblocks)

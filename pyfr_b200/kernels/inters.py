@@ -265,3 +265,264 @@ pack_view({', '.join(args)})
 }}
 '''
     return src, 'pack_view', _names(args)
+
+
+# -- boundary conditions --------------------------------------------------------
+def _bc_states_src(tplargs):
+    """Device functions ``bc_rsolve_state`` / ``bc_ldg_state`` /
+    ``bc_ldg_grad_state`` of one boundary type
+    (``pyfr/solvers/{euler,navstokes}/kernels/bcs/<type>.mako``).  Section
+    parameters arrive as C expressions in ``ploc[i]`` and ``t`` (built by
+    the host exactly like the reference's ``_exp_opts``) or as numbers."""
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    bt = tplargs['bctype']
+    uvw = 'uvw'[:nd]
+
+    def val(k):
+        v = c[k]
+        return f'FP({v})' if isinstance(v, str) else ph.fpconst(v)
+
+    ke = lambda a: ' + '.join(f'{a}[{i + 1}]*{a}[{i + 1}]' for i in range(nd))
+    sig = ('(const fpdtype_t ul[NVARS], const fpdtype_t nl[NDIMS], '
+           'fpdtype_t ur[NVARS], const fpdtype_t ploc[NDIMS], '
+           'const fpdtype_t t)')
+    L = []
+
+    def fn(name, body):
+        L.append(f'__device__ __forceinline__ void {name}{sig}\n{{\n'
+                 + '\n'.join('    ' + b for b in body) + '\n}\n')
+
+    def alias(name, target):
+        fn(name, [f'{target}(ul, nl, ur, ploc, t);'])
+
+    if bt == 'no-slp-adia-wall':
+        fn('bc_rsolve_state',
+           ['ur[0] = ul[0];'] + [f'ur[{i + 1}] = -ul[{i + 1}];'
+                                 for i in range(nd)]
+           + ['ur[NVARS - 1] = ul[NVARS - 1];'])
+        fn('bc_ldg_state',
+           ['ur[0] = ul[0];'] + [f'ur[{i + 1}] = FP(0.0);' for i in range(nd)]
+           + [f'ur[NVARS - 1] = ul[NVARS - 1] - (FP(0.5)/ul[0])*({ke("ul")});'])
+    elif bt == 'slp-adia-wall':
+        nor = ' + '.join(f'ul[{i + 1}]*nl[{i}]' for i in range(nd))
+        fn('bc_rsolve_state',
+           [f'const fpdtype_t nor = {nor};', 'ur[0] = ul[0];']
+           + [f'ur[{i + 1}] = ul[{i + 1}] - FP(2.0)*nor*nl[{i}];'
+              for i in range(nd)] + ['ur[NVARS - 1] = ul[NVARS - 1];'])
+        alias('bc_ldg_state', 'bc_rsolve_state')
+    elif bt == 'no-slp-isot-wall':
+        ct = ph.fpconst(c['cpTw']/c['gamma'])
+        tail = [f'ur[NVARS - 1] = {ct}*ur[0] + FP(0.5)*(FP(1.0)/ur[0])*'
+                f'({ke("ur")});']
+        fn('bc_rsolve_state',
+           ['ur[0] = ul[0];']
+           + [f'ur[{i + 1}] = -ul[{i + 1}] + FP(2.0)*{val(v)}*ul[0];'
+              for i, v in enumerate(uvw)] + tail)
+        fn('bc_ldg_state',
+           ['ur[0] = ul[0];'] + [f'ur[{i + 1}] = {val(v)}*ul[0];'
+                                 for i, v in enumerate(uvw)] + tail)
+    elif bt == 'sup-out-fn':
+        fn('bc_rsolve_state', ['UNROLL for (int i = 0; i < NVARS; i++)',
+                               '    ur[i] = ul[i];'])
+        alias('bc_ldg_state', 'bc_rsolve_state')
+    elif bt in ('sup-in-fa', 'sub-in-frv'):
+        body = [f'ur[0] = {val("rho")};'] + [
+            f'ur[{i + 1}] = ({val("rho")})*({val(v)});'
+            for i, v in enumerate(uvw)]
+        if bt == 'sup-in-fa':
+            body.append(f'ur[NVARS - 1] = {val("p")}/C_GM1 + FP(0.5)*'
+                        f'(FP(1.0)/ur[0])*({ke("ur")});')
+        else:
+            body.append('ur[NVARS - 1] = ul[NVARS - 1] - FP(0.5)*'
+                        f'(FP(1.0)/ul[0])*({ke("ul")}) + FP(0.5)*'
+                        f'(FP(1.0)/ur[0])*({ke("ur")});')
+        fn('bc_rsolve_state', body)
+        alias('bc_ldg_state', 'bc_rsolve_state')
+    elif bt == 'sub-out-fp':
+        fn('bc_rsolve_state',
+           ['UNROLL for (int i = 0; i < NVARS - 1; i++)', '    ur[i] = ul[i];',
+            f'ur[NVARS - 1] = {val("p")}/C_GM1 + FP(0.5)*(FP(1.0)/ul[0])*'
+            f'({ke("ul")});'])
+        alias('bc_ldg_state', 'bc_rsolve_state')
+    elif bt == 'char-riem-inv':
+        Ve = ' + '.join(f'({val(v)})*nl[{i}]' for i, v in enumerate(uvw))
+        Vi = ' + '.join(f'ul[{i + 1}]*nl[{i}]' for i in range(nd))
+        body = [
+            f'const fpdtype_t pe = {val("p")}, rhoe = {val("rho")};',
+            'const fpdtype_t cs = sqrt(C_GAMMA*pe/rhoe);',
+            'const fpdtype_t s = pe*pow(rhoe, -C_GAMMA);',
+            'const fpdtype_t ratio = cs*(FP(2.0)/C_GM1);',
+            'const fpdtype_t inv = FP(1.0)/ul[0];',
+            f'const fpdtype_t V_e = {Ve};',
+            f'const fpdtype_t V_i = inv*({Vi});',
+            'const fpdtype_t p_i = C_GM1*ul[NVARS - 1] - (FP(0.5)*C_GM1)*inv*'
+            f'({ke("ul")});',
+            'const fpdtype_t c_i = sqrt(C_GAMMA*p_i*inv);',
+            'const fpdtype_t R_e = (fabs(V_e) >= cs && V_i >= 0) '
+            '? V_i - c_i*(FP(2.0)/C_GM1) : V_e - ratio;',
+            'const fpdtype_t R_i = (fabs(V_e) >= cs && V_i < 0) '
+            '? V_e + ratio : V_i + c_i*(FP(2.0)/C_GM1);',
+            'const fpdtype_t V_b = FP(0.5)*(R_e + R_i);',
+            'const fpdtype_t c_b = (FP(0.25)*C_GM1)*(R_i - R_e);',
+            'const fpdtype_t rho_b = (V_i < 0) '
+            '? pow((FP(1.0)/(C_GAMMA*s))*c_b*c_b, FP(1.0)/C_GM1) '
+            ': ul[0]*pow(ul[0]*c_b*c_b/(C_GAMMA*p_i), FP(1.0)/C_GM1);',
+            'const fpdtype_t p_b = (FP(1.0)/C_GAMMA)*rho_b*c_b*c_b;',
+            'ur[0] = rho_b;'
+        ]
+        body += [f'ur[{i + 1}] = (V_i >= 0) '
+                 f'? rho_b*(ul[{i + 1}]*inv + (V_b - V_i)*nl[{i}]) '
+                 f': rho_b*(({val(v)}) + (V_b - V_e)*nl[{i}]);'
+                 for i, v in enumerate(uvw)]
+        body.append('ur[NVARS - 1] = p_b*(FP(1.0)/C_GM1) + FP(0.5)*'
+                    f'(FP(1.0)/ur[0])*({ke("ur")});')
+        fn('bc_rsolve_state', body)
+        alias('bc_ldg_state', 'bc_rsolve_state')
+    else:
+        raise NotImplementedError(f'Boundary type {bt!r} is not on the b200 '
+                                  'path (see DESIGN.md)')
+
+    # Ghost-side gradient
+    gsig = ('(const fpdtype_t ur[NVARS], const fpdtype_t nl[NDIMS], '
+            'const fpdtype_t gul[NDIMS][NVARS], fpdtype_t gur[NDIMS][NVARS])')
+    if bt in ('char-riem-inv', 'sup-in-fa', 'sub-in-frv', 'sub-out-fp'):
+        gbody = ['UNROLL for (int d = 0; d < NDIMS; d++)',
+                 '    UNROLL for (int v = 0; v < NVARS; v++)',
+                 '        gur[d][v] = FP(0.0);']
+    elif bt == 'no-slp-adia-wall':
+        # remove the wall-normal temperature gradient
+        # (no-slp-adia-wall.mako:22-75)
+        gbody = [
+            'const fpdtype_t rcprho = FP(1.0)/ur[0];',
+            'fpdtype_t vel[NDIMS], Tl[NDIMS];',
+            'UNROLL for (int i = 0; i < NDIMS; i++)',
+            '    vel[i] = rcprho*ur[i + 1];',
+            'UNROLL for (int d = 0; d < NDIMS; d++)', '{',
+            '    fpdtype_t acc = rcprho*gul[d][0]*ur[NVARS - 1];',
+            '    UNROLL for (int i = 0; i < NDIMS; i++)',
+            '        acc += vel[i]*(gul[d][i + 1] - vel[i]*gul[d][0]);',
+            '    Tl[d] = gul[d][NVARS - 1] - acc;', '}',
+            'UNROLL for (int d = 0; d < NDIMS; d++)',
+            '    UNROLL for (int v = 0; v < NVARS; v++)',
+            '        gur[d][v] = gul[d][v];',
+            'UNROLL for (int d = 0; d < NDIMS; d++)', '{',
+            '    fpdtype_t acc = 0;',
+            '    UNROLL for (int e = 0; e < NDIMS; e++)',
+            '        acc += nl[d]*nl[e]*Tl[e];',
+            '    gur[d][NVARS - 1] -= acc;', '}']
+    else:
+        gbody = ['UNROLL for (int d = 0; d < NDIMS; d++)',
+                 '    UNROLL for (int v = 0; v < NVARS; v++)',
+                 '        gur[d][v] = gul[d][v];']
+
+    L.append(f'__device__ __forceinline__ void bc_ldg_grad_state{gsig}\n{{\n'
+             + '\n'.join('    ' + b for b in gbody) + '\n}\n')
+
+    return '\n'.join(L)
+
+
+def bc_source(be, tplargs, viscous, kind, has_ploc):
+    """``bcconu`` (``pyfr/solvers/navstokes/kernels/bcconu.mako``) and
+    ``bccflux`` (``pyfr/solvers/euler/kernels/bccflux.mako``,
+    ``pyfr/solvers/navstokes/kernels/bccflux.mako`` with the flux-state
+    templates ``bcs/ghost.mako`` / ``bcs/ghost-imperm.mako``)."""
+    nd, nv, c = tplargs['ndims'], tplargs['nvars'], tplargs['c']
+    cfs = tplargs.get('bccfluxstate')
+
+    defs = [('NDIMS', nd), ('NVARS', nv),
+            ('C_GM1', ph.fpconst(c['gamma'] - 1))]
+    defs += ph.physics_defines(c, tplargs.get('visc_corr', 'none'), viscous)
+
+    head = _head + _normal_src()
+    if has_ploc:
+        head += r'''
+    fpdtype_t ploc[NDIMS];
+    UNROLL for (int d = 0; d < NDIMS; d++)
+        ploc[d] = __ldg(plocp + (long long) d*ploc_ld + i);
+'''
+    else:
+        head += '    const fpdtype_t ploc[NDIMS] = {};\n'
+
+    tail_args = ['const fpdtype_t* __restrict__ nl', 'long long nl_ld']
+    if has_ploc:
+        tail_args += ['const fpdtype_t* __restrict__ plocp',
+                      'long long ploc_ld']
+    tail_args += ['fpdtype_t t']
+
+    if kind == 'bcconu':
+        args = (['ixdtype_t n'] + _view_arg('ulin')
+                + _view_arg('ulout', const=False) + tail_args)
+        body = head + r'''
+    fpdtype_t l[NVARS], r[NVARS];
+    UNROLL for (int v = 0; v < NVARS; v++)
+        l[v] = ulin[ulin_map[i] + K_SOA*v];
+
+    bc_ldg_state(l, nrm, r, ploc, t);
+
+    UNROLL for (int v = 0; v < NVARS; v++)
+        ulout[ulout_map[i] + K_SOA*v] = r[v];
+'''
+    else:
+        args = ['ixdtype_t n'] + _view_arg('ul', const=False)
+        if viscous:
+            args += _view_arg('gradul', strided=True)
+        args += tail_args
+
+        body = head + r'''
+    const ixdtype_t lix = ul_map[i];
+    fpdtype_t l[NVARS], r[NVARS], fn[NVARS];
+    UNROLL for (int v = 0; v < NVARS; v++)
+        l[v] = ul[lix + K_SOA*v];
+'''
+        if viscous and cfs is not None:
+            state = 'l' if cfs == 'ghost' else 'r'
+            tau = c['ldg-tau'] if cfs == 'ghost' else 0.0
+            body += rf'''
+    fpdtype_t gl[NDIMS][NVARS], gr[NDIMS][NVARS], fvr[NDIMS][NVARS] = {{}};
+    {{
+        const ixdtype_t gix = gradul_map[i], gst = gradul_str[i];
+        UNROLL for (int d = 0; d < NDIMS; d++)
+            UNROLL for (int v = 0; v < NVARS; v++)
+                gl[d][v] = gradul[gix + gst*d + K_SOA*v];
+    }}
+
+    // Viscous ghost state and flux
+    bc_ldg_state(l, nrm, r, ploc, t);
+    bc_ldg_grad_state({state}, nrm, gl, gr);
+    viscous_flux_add(r, gr, fvr);
+
+    // Inviscid ghost state and Riemann solve
+    bc_rsolve_state(l, nrm, r, ploc, t);
+    rsolve(l, r, nrm, fn);
+
+    UNROLL for (int v = 0; v < NVARS; v++)
+    {{
+        fpdtype_t fv = {' + '.join(f'nrm[{j}]*fvr[{j}][v]'
+                                   for j in range(nd))};
+        {f'fv += {ph.fpconst(tau)}*(l[v] - r[v]);' if tau != 0.0 else ''}
+        ul[lix + K_SOA*v] = mag_nl*(fn[v] + fv);
+    }}
+'''
+        else:
+            body += r'''
+    bc_rsolve_state(l, nrm, r, ploc, t);
+    rsolve(l, r, nrm, fn);
+
+    UNROLL for (int v = 0; v < NVARS; v++)
+        ul[lix + K_SOA*v] = mag_nl*fn[v];
+'''
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+{ph.flux_src}
+{ph.visc_src if viscous else ''}
+{ph.rsolve_src[tplargs['rsolver']] if kind == 'bccflux' else ''}
+{_bc_states_src(tplargs)}
+
+extern "C" __global__ void __launch_bounds__(128)
+{kind}({', '.join(args)})
+{{
+{body}
+}}
+'''
+    return src, kind, _names(args)

@@ -61,6 +61,26 @@ HOST_CASES = {
                                        'csubsz': 16}),
 }
 
+# Wall-bounded / open-boundary cases: name -> box_case arguments
+BC_CASES = {
+    'bc_ns_wall_farfield': ('navier-stokes', (3, 3, 2),
+                            {'ylo': 'no-slp-adia-wall',
+                             'yhi': 'char-riem-inv'},
+                            dict(order=2, warp=0.1)),
+    'bc_ns_inout_walls': ('navier-stokes', (3, 2, 3),
+                          {'xlo': 'sub-in-frv', 'xhi': 'sub-out-fp',
+                           'zlo': 'slp-adia-wall',
+                           'zhi': 'no-slp-isot-wall'},
+                          dict(order=2, rsolver='hllc')),
+    'bc_ns_supersonic': ('navier-stokes', (2, 3, 3),
+                         {'xlo': 'sup-in-fa', 'xhi': 'sup-out-fn'},
+                         dict(order=1, beta=0.0)),
+    'bc_euler_all': ('euler', (5, 4),
+                     {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
+                      'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},
+                     dict(order=3)),
+}
+
 OPMAT_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
                 ('hex', 3, 'gauss-legendre'), ('hex', 4, 'gauss-legendre'),
                 ('hex', 4, 'gauss-legendre-lobatto'),
@@ -109,7 +129,12 @@ def record_consts(becls):
 
 def consts_digest(rec):
     """Constant tables in a creation-order independent order."""
-    return sorted(rec, key=lambda a: (a.shape, float(np.abs(a).sum())))
+    def key(a):
+        w = np.arange(1, a.size + 1).reshape(a.shape)/a.size
+        return (a.shape, round(float(np.abs(a).sum()), 6),
+                round(float(a.sum()), 6), round(float((a*w).sum()), 6))
+
+    return sorted(rec, key=key)
 
 
 def trace_digest(trace):
@@ -151,9 +176,14 @@ def ref_opmats():
 
 
 def ref_host_case(name):
-    case, n, kw, parts, beopts = HOST_CASES[name]
-    txt = cfg_text(case, kw, beopts)
-    _, box = cases.make(case, n, **kw)
+    if name in BC_CASES:
+        system, n, bcs, kw = BC_CASES[name]
+        _, box, txt = cases.box_case(system, n, bcs, **kw)
+        parts = (1,)*box.ndims
+    else:
+        case, n, kw, parts, beopts = HOST_CASES[name]
+        txt = cfg_text(case, kw, beopts)
+        _, box = cases.make(case, n, **kw)
     nparts = int(np.prod(parts))
     vparts = box.brick_partition(parts) if nparts > 1 else None
 
@@ -214,7 +244,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'opmats.npz'), **ref_opmats())
     print('opmats.npz written')
 
-    for name in HOST_CASES:
+    for name in list(HOST_CASES) + list(BC_CASES):
         np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
                             **ref_host_case(name))
         print(f'host_{name}.npz written')

@@ -153,3 +153,50 @@ def test_tgv_rhs_affine_mesh(built, kw, opts):
     else:
         _, ext = oracle_rhs('tgv', n, extended=True, **kw)
         assert_parity(out, ref[0], ext[0], TOL64)
+
+
+BC_CASES = [
+    ('navier-stokes', (4, 3, 3), {'ylo': 'no-slp-adia-wall',
+                                  'yhi': 'char-riem-inv'},
+     dict(order=3, warp=0.1)),
+    ('navier-stokes', (3, 4, 3), {'xlo': 'sub-in-frv', 'xhi': 'sub-out-fp',
+                                  'zlo': 'slp-adia-wall',
+                                  'zhi': 'no-slp-isot-wall'},
+     dict(order=2, rsolver='hllc')),
+    ('navier-stokes', (3, 3, 4), {'xlo': 'sup-in-fa', 'xhi': 'sup-out-fn',
+                                  'ylo': 'no-slp-adia-wall',
+                                  'yhi': 'no-slp-adia-wall'},
+     dict(order=2, beta=0.0, warp=0.05)),
+    ('euler', (9, 8), {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
+                       'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},
+     dict(order=3)),
+    ('euler', (8, 8), {'ylo': 'slp-adia-wall', 'yhi': 'slp-adia-wall'},
+     dict(order=2, rsolver='hllc')),
+]
+
+
+@pytest.mark.parametrize('system,n,bcs,kw', BC_CASES, ids=str)
+def test_boundary_conditions_match_oracle(built, system, n, bcs, kw):
+    """bcconu / bccflux for every boundary type on the path, wall-bounded
+    and open boxes, against the oracle driven by the same host code."""
+    from pyfr_b200.backend import B200Backend
+    from util import OracleBackend
+
+    def run(cls, extended=False):
+        cfg, box, _ = cases.box_case(system, n, bcs, **kw)
+        cfg.set('backend-oracle', 'extended-mul', extended)
+        sysm = get_system(cls(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.25, 0, 1)
+        if hasattr(sysm.backend, 'wait'):
+            sysm.backend.wait()
+        return sysm, sysm.ele_scal_upts(1)[0]
+
+    _, ref = run(OracleBackend)
+    _, ext = run(OracleBackend, extended=True)
+    sysm, out = run(B200Backend)
+
+    assert_parity(out, ref, ext, TOL64)
+
+    kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
+             for w, k in g.plan if w == 'kernel']
+    assert 'bccflux' in kinds and 'copy' not in kinds

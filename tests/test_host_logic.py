@@ -389,3 +389,31 @@ def test_affine_regions_are_detected(built):
     assert modes() == [True]
     assert modes(warp=0.1) == [False]
     assert modes(curved=0.5) == [False, True]      # curved region, linear
+
+
+def test_b200_boundary_plan(built):
+    """Wall-bounded Navier-Stokes box: boundary kernels join the graphs
+    where the reference puts them and copy_fpts stays elided (boundary
+    points are stored by bcconu)."""
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box, _ = cases.box_case('navier-stokes', (3, 3, 2),
+                                 {'ylo': 'no-slp-adia-wall',
+                                  'yhi': 'char-riem-inv'}, order=2)
+    s = get_system(B200Backend(cfg, dry=True), box.local_mesh(), cfg, 2)
+    kinds = [[getattr(k, 'kind', None) for w, k in g.plan if w == 'kernel']
+             for g in s.rhs_graphs(0, 1)]
+
+    assert kinds == [['mul', 'intconu', 'bcconu', 'bcconu'],
+                     ['gradflux', None, 'bccflux', 'bccflux'],
+                     ['mul+negdivconf']]
+
+
+def test_unknown_boundary_type_is_refused():
+    cfg, box, txt = cases.box_case('navier-stokes', (2, 2, 2),
+                                   {'ylo': 'no-slp-adia-wall',
+                                    'yhi': 'no-slp-adia-wall'}, order=1)
+    cfg.set('soln-bcs-ylo', 'type', 'sub-in-ftpttang')
+
+    with pytest.raises(NotImplementedError, match='DESIGN.md'):
+        get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)

@@ -77,14 +77,21 @@ def test_reference_known_answer_hex_p3(opmats):
 def _host_case(name, extended=False):
     """This repository's host code on the oracle backend; returns what
     make_golden.ref_host_case records for the reference's host code."""
-    case, n, kw, parts, beopts = mg.HOST_CASES[name]
+    if name in mg.BC_CASES:
+        system, n, bcs, kw = mg.BC_CASES[name]
+        parts, beopts = (1,), {}
+        mk = lambda: cases.box_case(system, n, bcs, **kw)[:2]
+    else:
+        case, n, kw, parts, beopts = mg.HOST_CASES[name]
+        mk = lambda: cases.make(case, n, **kw)
+
     beopts = beopts | ({'extended-mul': 1} if extended else {})
     nparts = int(np.prod(parts))
     world = LocalComm(0, nparts)
     systems, traces, consts = [], [], []
 
     for r in range(nparts):
-        cfg, box = cases.make(case, n, **kw)
+        cfg, box = mk()
         for k, v in beopts.items():
             cfg.set('backend-oracle', k, v)
 
@@ -112,7 +119,7 @@ def _host_case(name, extended=False):
     return out, nparts
 
 
-@pytest.mark.parametrize('name', list(mg.HOST_CASES))
+@pytest.mark.parametrize('name', list(mg.HOST_CASES) + list(mg.BC_CASES))
 def test_host_mirror_matches_reference_host(name):
     gold = np.load(os.path.join(GOLDEN, f'host_{name}.npz'))
     out, nparts = _host_case(name)
@@ -150,7 +157,8 @@ def test_host_mirror_matches_reference_host(name):
 
 @pytest.mark.skipif(not mg.rh.available(), reason='needs /root/reference')
 @pytest.mark.parametrize('name', ['tgv_p2_beta0_2parts',
-                                  'vortex_p3_hllc_2parts'])
+                                  'vortex_p3_hllc_2parts',
+                                  'bc_ns_wall_farfield'])
 def test_fixtures_are_current(name):
     """Where the reference is present, regenerate a fixture from it and
     check the committed copy is what the reference produces today."""
