@@ -18,6 +18,7 @@ the individual (still GPU) kernels.
 import numpy as np
 
 from pyfr_b200.kernels import fused as kfused
+from pyfr_b200.kernels import fused_euler as keuler
 from pyfr_b200.kernels import mul as kmul
 
 
@@ -304,7 +305,88 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     return [k]
 
 
-_group_fusers = [fuse_gradflux, fuse_tdivtconf_negdivconf]
+def fuse_fluxdiv(be, kerns, subs):
+    """tdisf, tdivtpcorf, tdivtconf, negdivconf of one element type of an
+    advection (Euler) system -> ``fluxdiv``."""
+    from pyfr_b200.providers import B200Kernel
+
+    if len(kerns) != 4 or not be.euler_fusion:
+        return None
+
+    k0, k1, k2, k3 = kerns
+    g0, g3 = leaves(k0), leaves(k3)
+
+    if not (all(k.kind == 'tflux' and not k.info['viscous'] for k in g0) and
+            getattr(k1, 'kind', None) == 'mul' and
+            getattr(k2, 'kind', None) == 'mul' and
+            len(g3) == 1 and g3[0].kind == 'negdivconf'):
+        return None
+
+    i1, i2, i3 = k1.info, k2.info, g3[0].info
+    F, FOUT, C = i1['b'], i1['out'], i2['b']
+
+    if (i1['beta'] != 0 or i1['alpha'] != 1 or i2['beta'] != 1 or
+        i2['alpha'] != 1 or not _same(i2['out'], FOUT) or
+        not _same(i3['tdivtconf'], FOUT) or i3['tplargs']['src_macros']):
+        return None
+
+    tpl = g0[0].info['tplargs']
+    nd = tpl['ndims']
+    nu, nf = FOUT.nrow, C.nrow
+    U = _root(g0[0].info['u'])
+    LD = U.leaddim
+
+    if (F.nrow != nd*nu or U.nrow != nu or C.leaddim != LD or
+        FOUT.leaddim != LD or F.leaddim != LD or
+        any(_root(k.info['f']) is not _root(F) or
+            _root(k.info['u']) is not U for k in g0)):
+        return None
+
+    isz = U.itemsize
+    ops = dict(A5=i1['A'], M3=i2['A'])
+    out = []
+
+    for kt in g0:
+        ti = kt.info
+        ktype = ti['tplargs']['ktype']
+        npts, neles = ti['dims']
+        b0 = _block_off(ti['u'])
+        nblocks = -(-neles // be.csubsz)
+        pts = ti['upts'].get() if ti['upts'] is not None else None
+
+        src, name, meta = keuler.fluxdiv_source(be, ops, ti['tplargs'], pts,
+                                                LD)
+        fn = be.pointwise._function(src, name)
+        fn.set_smem(meta['smem'])
+
+        off = lambda m: m.data + b0*m.blocksz*isz
+        args = [('i', nblocks), ('i', neles),
+                ('p', off(U)), ('l', U.blocksz),
+                ('p', off(C)), ('l', C.blocksz),
+                ('p', off(FOUT)), ('l', FOUT.blocksz)]
+
+        if 'linear' in ktype:
+            v = ti['verts']
+            args += [('p', v.data), ('l', v.blocksz)]
+            geo = [v]
+        else:
+            s, r = ti['smats'], i3['rcpdjac']
+            args += [('p', s.data), ('l', s.blocksz),
+                     ('p', r.data + b0*r.blocksz*isz), ('l', r.blocksz)]
+            geo = [s, r]
+
+        out.append(B200Kernel(
+            be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
+            (meta['nthreads'], 1, 1), meta['smem'], args,
+            mats=[U, C, FOUT, F] + geo, misc=[meta],
+            traffic=meta['words_per_block']*nblocks*isz, kind='fluxdiv',
+            info=dict(replaces=kerns)
+        ))
+
+    return out
+
+
+_group_fusers = [fuse_gradflux, fuse_fluxdiv, fuse_tdivtconf_negdivconf]
 
 
 def fuse_group(be, kerns, subs):

@@ -232,3 +232,44 @@ def test_full_size_conservation_and_symmetry(built):
     assert abs(mag[1]/mag[2] - 1) < 1e-10
     # no mass sources at t = 0 beyond discretisation error of div u
     assert np.abs(rhs[:, 0]).max() < 1e-4*np.abs(rhs[:, 1]).max()
+
+
+@pytest.mark.parametrize('kw', [dict(order=3), dict(order=2, rsolver='hllc'),
+                                dict(order=4, precision='single')], ids=str)
+def test_vortex_rhs_fused_euler_kernel(built, kw):
+    """The fused Euler element kernel (flux + divergence + correction +
+    scaling in one launch): three launches per RHS."""
+    _, ref = oracle_rhs('vortex', 12, **kw)
+    sysm, out = b200_rhs('vortex', 12, {'euler-fusion': 1}, **kw)
+
+    kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
+             for w, k in g.plan if w == 'kernel']
+    assert kinds.count('fluxdiv') == 1 and 'tflux' not in kinds
+
+    if kw.get('precision') == 'single':
+        _, r64 = oracle_rhs('vortex', 12, **{**kw, 'precision': 'double'})
+        floor = rel_err(ref[0].astype(float), r64[0])
+        assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
+    else:
+        _, ext = oracle_rhs('vortex', 12, extended=True, **kw)
+        assert_parity(out, ref[0], ext[0], TOL64)
+
+
+def test_euler_boundaries_fused_kernel(built):
+    from pyfr_b200.backend import B200Backend
+    from util import OracleBackend
+
+    system, n, bcs, kw = BC_CASES[3]
+    outs = []
+    for cls, ext in ((OracleBackend, False), (OracleBackend, True),
+                     (B200Backend, False)):
+        cfg, box, _ = cases.box_case(system, n, bcs, warp=0.1, **kw)
+        cfg.set('backend-oracle', 'extended-mul', ext)
+        cfg.set('backend-b200', 'euler-fusion', 1)
+        sysm = get_system(cls(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.0, 0, 1)
+        if hasattr(sysm.backend, 'wait'):
+            sysm.backend.wait()
+        outs.append(sysm.ele_scal_upts(1)[0])
+
+    assert_parity(outs[2], outs[0], outs[1], TOL64)

@@ -417,3 +417,14 @@ def test_unknown_boundary_type_is_refused():
 
     with pytest.raises(NotImplementedError, match='DESIGN.md'):
         get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+
+
+def test_b200_euler_fused_plan(built):
+    """With euler-fusion the Euler RHS is three launches: interpolation,
+    interface flux, fused element kernel."""
+    be, plan = _dry_plan('vortex', 6, {'euler-fusion': 1}, order=3)
+    assert [[k for w, k in g] for g in plan] == [['mul', None], ['fluxdiv']]
+
+    be, plan = _dry_plan('vortex', 6, {'euler-fusion': 0}, order=3)
+    assert [k for w, k in plan[1]] == ['tflux', 'mul', 'mul+negdivconf'] or \
+        [k for w, k in plan[1]] == ['tflux', 'mul', 'mul', 'negdivconf']
