@@ -71,7 +71,7 @@ class B200Backend(base.BaseBackend):
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
         self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
-        self.euler_fusion = cfg.getbool(sect, 'euler-fusion', False)
+        self.euler_fusion = cfg.getbool(sect, 'euler-fusion', True)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 
