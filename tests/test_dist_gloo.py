@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize('nranks', [2])
+@pytest.mark.parametrize('nranks', [2, 4])
 def test_two_process_halo_exchange(nranks):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            f'--nproc-per-node={nranks}', '--master-addr', '127.0.0.1',
