@@ -238,8 +238,141 @@ def ref_host_case(name):
     return out
 
 
+# Connectivity cases: name -> (mesh size, bounds, periodic axes, nparts)
+CONN_CASES = {
+    'conn_hex_periodic_3parts': ((5, 4, 3), (-1.0, 1.0), True, 3),
+    'conn_hex_walls_4parts': ((4, 4, 4), (0.0, 2.0), (True, False, False), 4),
+    'conn_quad_walls_5parts': ((9, 7), (0.0, 1.0), (False, True), 5),
+}
+
+
+def ref_connectivity_case(name):
+    """Partition a synthetic box with the reference's own
+    ``BaselinePartitioner`` (pyfr/partitioners/baseline.py) and derive each
+    rank's interior / boundary / inter-partition connectivity with the
+    reference's own ``NativeReader._construct_con`` (pyfr/readers/native.py:
+    445-534), every rank in a thread with an in-process stand-in for the
+    MPI neighbourhood collectives.  What is fed in is the mesh in the form
+    the reader would find in a ``.pyfrm`` file: per element, per face, the
+    ``(codec index, global element)`` of the neighbour."""
+    import threading
+    from types import SimpleNamespace
+
+    rh.install_stubs()
+    import pyfr.readers.native as rnative
+    from pyfr.partitioners.base import Graph
+    from pyfr.partitioners.baseline import BaselinePartitioner
+
+    from pyfr_b200.host.mesh import BoxMesh
+
+    n, (lo, hi), periodic, nparts = CONN_CASES[name]
+    box = BoxMesh(n, lo, hi, periodic=periodic)
+    et, ne, nfaces = box.etype, box.neles, box.roff.shape[1]
+
+    # Dual graph (unit weights) -> the reference's partitioner
+    nbr = [np.unique(r[(r >= 0) & (r != g)]) for g, r in enumerate(box.roff)]
+    vtab = np.concatenate(([0], np.cumsum([len(x) for x in nbr])))
+    etab = np.concatenate(nbr)
+    graph = Graph(vtab, etab, np.ones(ne, dtype=np.int32),
+                  np.ones(len(etab), dtype=np.int32))
+    part = BaselinePartitioner([1]*nparts, elewts={et: 1})
+    vparts = np.asarray(part._partition_graph(graph, [1.0]*nparts),
+                        dtype=np.int32)
+    assert len(np.unique(vparts)) == nparts
+
+    order = box.partition_order(vparts)
+
+    # In-process neighbourhood collectives
+    tls = threading.local()
+    barrier = threading.Barrier(nparts)
+    mail = {}
+
+    class NComm:
+        handle = 0
+
+        def __init__(self, nbrs):
+            self.nbrs = nbrs
+
+        @staticmethod
+        def fromhandle(h):
+            return SimpleNamespace(free=lambda: None)
+
+        def neighbor_allgather(self, obj):
+            mail['g', tls.rank] = obj
+            barrier.wait()
+            out = [mail['g', p] for p in self.nbrs]
+            barrier.wait()
+            return out
+
+        def neighbor_alltoall(self, objs):
+            for p, o in zip(self.nbrs, objs):
+                mail['a', tls.rank, p] = o
+            barrier.wait()
+            out = [mail['a', p, tls.rank] for p in self.nbrs]
+            barrier.wait()
+            return out
+
+    class Comm:
+        def Create_dist_graph_adjacent(self, src, dst):
+            return NComm(list(src))
+
+    rnative.get_comm_rank_root = lambda: (Comm(), tls.rank, 0)
+
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            tls.rank = rank
+            gidx = order[rank]
+            faces = np.empty((len(gidx), nfaces),
+                             dtype=[('cidx', np.int16), ('off', np.int64)])
+            faces['cidx'], faces['off'] = box.rcidx[gidx], box.roff[gidx]
+
+            rd = rnative.NativeReader.__new__(rnative.NativeReader)
+            rd.mesh = SimpleNamespace(codec=list(box.codec), etypes=[et],
+                                      eidxs={et: gidx}, bcon={}, con_p={})
+            rd.eles = {et: {'faces': faces}}
+            rd.f = {f'eles/{et}': np.empty(ne)}
+
+            nb = vparts[box.roff[gidx][box.roff[gidx] >= 0]]
+            rd.neighbours = sorted(set(nb.tolist()) - {rank})
+            rd._construct_con()
+            results[rank] = rd.mesh
+        except Exception as e:                          # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(nparts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+    out = {'vparts': vparts}
+    for r, m in results.items():
+        out[f'r{r}_eidxs'] = order[r]
+        for side, c in zip('lr', m.con):
+            out[f'r{r}_con_{side}_cidxs'] = c.cidxs
+            out[f'r{r}_con_{side}_eidxs'] = c.eidxs
+        for p, c in m.con_p.items():
+            out[f'r{r}_conp{p}_cidxs'] = c.cidxs
+            out[f'r{r}_conp{p}_eidxs'] = c.eidxs
+        for b, c in m.bcon.items():
+            out[f'r{r}_bcon_{b}_cidxs'] = c.cidxs
+            out[f'r{r}_bcon_{b}_eidxs'] = c.eidxs
+
+    return out
+
+
 def main():
     rh.install_stubs()
+
+    for name in CONN_CASES:
+        np.savez_compressed(os.path.join(HERE, f'{name}.npz'),
+                            **ref_connectivity_case(name))
+        print(f'{name}.npz written')
 
     np.savez_compressed(os.path.join(HERE, 'opmats.npz'), **ref_opmats())
     print('opmats.npz written')

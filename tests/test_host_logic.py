@@ -428,3 +428,23 @@ def test_b200_euler_fused_plan(built):
     be, plan = _dry_plan('vortex', 6, {'euler-fusion': 0}, order=3)
     assert [k for w, k in plan[1]] == ['tflux', 'mul', 'mul+negdivconf'] or \
         [k for w, k in plan[1]] == ['tflux', 'mul', 'mul', 'negdivconf']
+
+
+def test_irregular_partition_reproduces_single_partition():
+    """Three irregular partitions made by the reference's partitioner
+    (fixture conn_hex_periodic_3parts: uneven neighbour sets, several
+    faces per neighbour pair) reproduce the single-partition RHS."""
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                'golden', 'conn_hex_periodic_3parts.npz'))
+    vparts, n = gold['vparts'], (5, 4, 3)
+    kw = dict(order=2, beta=0.0, warp=0.1, rsolver='hllc')
+
+    _, ref = oracle_rhs('tgv', n, **kw)
+    _, out = oracle_rhs('tgv', n, vparts=vparts, nparts=3, **kw)
+
+    _, box = cases.make('tgv', n, **kw)
+    for r, o in enumerate(out):
+        gidx = box.local_mesh(vparts, r).eidxs['hex']
+        assert rel_err(o, ref[0][..., gidx]) < 5e-13

@@ -168,3 +168,52 @@ def test_fixtures_are_current(name):
     assert set(new) == set(gold.files)
     for k in new:
         assert np.array_equal(new[k], gold[k]), k
+
+
+@pytest.mark.parametrize('name', list(mg.CONN_CASES))
+def test_connectivity_matches_reference_reader(name):
+    """Interior / boundary / inter-partition connectivity of irregular
+    partitions (made by the reference's BaselinePartitioner) against what
+    the reference's own NativeReader._construct_con derives from the same
+    face records: bit-exact, including the ordering both ranks of an
+    inter-partition interface agree on."""
+    from pyfr_b200.host.mesh import BoxMesh
+
+    gold = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    n, (lo, hi), periodic, nparts = mg.CONN_CASES[name]
+    box = BoxMesh(n, lo, hi, periodic=periodic)
+    vparts = gold['vparts']
+
+    for r in range(nparts):
+        m = box.local_mesh(vparts, r)
+        et = box.etype
+
+        assert np.array_equal(m.eidxs[et], gold[f'r{r}_eidxs'])
+        for side, c in zip('lr', m.con):
+            assert np.array_equal(c.cidxs, gold[f'r{r}_con_{side}_cidxs'])
+            assert np.array_equal(c.eidxs, gold[f'r{r}_con_{side}_eidxs'])
+
+        pkeys = {k for k in gold.files if k.startswith(f'r{r}_conp')}
+        assert pkeys == {f'r{r}_conp{p}_{w}' for p in m.con_p
+                         for w in ('cidxs', 'eidxs')}
+        for p, c in m.con_p.items():
+            assert np.array_equal(c.cidxs, gold[f'r{r}_conp{p}_cidxs'])
+            assert np.array_equal(c.eidxs, gold[f'r{r}_conp{p}_eidxs'])
+
+        bkeys = {k for k in gold.files if k.startswith(f'r{r}_bcon_')}
+        assert bkeys == {f'r{r}_bcon_{b}_{w}' for b in m.bcon
+                         for w in ('cidxs', 'eidxs')}
+        for b, c in m.bcon.items():
+            assert np.array_equal(c.cidxs, gold[f'r{r}_bcon_{b}_cidxs'])
+            assert np.array_equal(c.eidxs, gold[f'r{r}_bcon_{b}_eidxs'])
+
+
+@pytest.mark.skipif(not mg.rh.available(), reason='needs /root/reference')
+def test_connectivity_fixture_is_current():
+    name = 'conn_hex_walls_4parts'
+    gold = np.load(os.path.join(GOLDEN, f'{name}.npz'))
+    new = mg.ref_connectivity_case(name)
+
+    assert set(new) == set(gold.files)
+    for k in new:
+        assert np.array_equal(new[k], gold[k]), k
