@@ -152,7 +152,8 @@ def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1):
 
     n = args.cpu_n
     cfg, box = cases.make('tgv', n, order=args.order, rsolver=args.rsolver)
-    be = cbackend.make_cbackend(base, fast=True)(cfg)
+    be = cbackend.make_cbackend(base, fast=True,
+                                nthreads=os.cpu_count())(cfg)
     sysm = get_system(be, box.local_mesh(), cfg, 2)
     ndof = sum(sysm.ele_ndofs)
 

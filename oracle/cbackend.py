@@ -91,11 +91,16 @@ def _root(m):
     return getattr(m, 'parent', m)
 
 
-def make_cbackend(base, fast=False, name='oracle-c'):
+def make_cbackend(base, fast=False, name='oracle-c', nthreads=None):
+    """``nthreads``: OpenMP threads to use (default: what the environment
+    says; launchers such as torchrun export OMP_NUM_THREADS=1, so the
+    benchmark passes the host's core count explicitly)."""
     build()
     lib = ct.CDLL(os.path.join(_here, '_build',
                                'libcrhs_fast.so' if fast else 'libcrhs.so'))
     lib.crhs_num_threads.restype = ct.c_int
+    if nthreads:
+        lib.crhs_set_num_threads(ct.c_int(int(nthreads)))
 
     NP = make_backend(base, name=name)
     NPKernel = NP.kernel_cls

@@ -656,6 +656,14 @@ crhs_copy_rows(int nblocks, long nelem, double *dst, long dbs,
         memcpy(dst + b*dbs, src + b*sbs, nelem*sizeof(double));
 }
 
+void
+crhs_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+}
+
 int
 crhs_num_threads(void)
 {
