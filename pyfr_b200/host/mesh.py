@@ -134,8 +134,11 @@ class BoxMesh:
 
         if self.warp:
             # Smooth, box-periodic displacement -> non-affine linear cells
+            # (phase offsets keep the vertices of coarse meshes -- two or
+            # three cells per direction -- away from the zeros of the sines)
             L = (self.hi - self.lo)[:, None, None]
             ph = 2*np.pi*(x - self.lo[:, None, None])/L
+            ph = ph + np.array([0.5, 0.9, 1.3][:nd])[:, None, None]
             s = np.prod(np.sin(ph), axis=0)
             x = x + self.warp*h[:, None, None]*s*np.array(
                 [1.0, -0.7, 0.5][:nd])[:, None, None]
