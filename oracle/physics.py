@@ -11,10 +11,14 @@ ships no golden vectors for flux, Riemann, gradient or RHS values
 (only operator matrices, see tests/test_oracle_golden.py), and its kernels
 are Mako templates that cannot be rendered in this environment (no
 ``mako``).  The restatement is therefore checked by analytic properties
-instead (tests/test_host_logic.py: free-stream preservation, Riemann-solver
-consistency f(u,u,n) = F(u).n and symmetry, discrete conservation, design
-order of accuracy of the Euler RHS, convergence of the viscous RHS to an
-exact solution) and by the reference's own host code driving it
+instead (tests/test_oracle_physics.py: the viscous flux against the
+analytic Newtonian stress tensor and Fourier heat flux, the inviscid flux
+against the Euler flux, exact upwinding of HLLC for supersonic states,
+impermeable and adiabatic walls, far-field transparency; tests/
+test_host_logic.py: free-stream preservation, Riemann-solver consistency
+f(u,u,n) = F(u).n and symmetry, discrete conservation, design order of
+accuracy of the Euler RHS, convergence of the viscous RHS to an exact
+solution) and by the reference's own host code driving it
 (tests/golden/make_golden.py).
 """
 
