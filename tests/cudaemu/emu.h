@@ -1,0 +1,144 @@
+// TEST INFRASTRUCTURE -- a minimal host-side execution model for the
+// generated CUDA sources, so that the *actual kernel text* the product
+// generates can be executed (functionally, not fast) in the GPU-less test
+// suite.  One OS thread per CUDA thread, CTAs one after another,
+// __syncthreads as a barrier, shared memory as one static buffer, TMA bulk
+// copies as synchronous memcpy tracked by emulated mbarriers.  Never used
+// by the product: tests/ inject it through monkeypatching only.
+#pragma once
+
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __constant__ static const
+#define __shared__
+
+struct emu_dim3 { unsigned x, y, z; };
+struct int4 { int x, y, z, w; };
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+
+static thread_local emu_dim3 threadIdx, blockIdx;
+static emu_dim3 blockDim, gridDim;
+
+alignas(128) unsigned char smem_raw[256*1024];
+
+using std::fma;
+using std::sqrt;
+using std::fabs;
+using std::pow;
+using std::fmin;
+using std::fmax;
+
+template <class T> static inline T __ldg(const T *p) { return *p; }
+
+// ---- CTA-wide barrier ---------------------------------------------------------
+struct EmuBarrier
+{
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned n = 0, waiting = 0, gen = 0;
+
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = gen;
+        if (++waiting == n)
+        {
+            waiting = 0;
+            gen++;
+            cv.notify_all();
+        }
+        else
+            cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+static EmuBarrier emu_cta_barrier;
+static inline void __syncthreads() { emu_cta_barrier.wait(); }
+
+// ---- mbarrier + TMA bulk copy ---------------------------------------------------
+// The 8-byte shared-memory slot holds {completed phases, pending bytes}
+struct EmuMbar { std::atomic<unsigned> completed; std::atomic<unsigned> pending; };
+static_assert(sizeof(EmuMbar) == 8, "mbarrier slot");
+
+static inline unsigned smem_u32(const void *p) { return 0; }
+
+static inline void mbar_init(unsigned long long *bar, unsigned n)
+{
+    EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    b->completed.store(0);
+    b->pending.store(0);
+}
+
+static inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    reinterpret_cast<EmuMbar *>(bar)->pending.fetch_add(bytes);
+}
+
+static inline void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    while ((b->completed.load(std::memory_order_acquire) & 1) == parity)
+        std::this_thread::yield();
+}
+
+static inline void tma_load_1d(void *dst, const void *src, unsigned bytes,
+                               unsigned long long *bar)
+{
+    EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    std::memcpy(dst, src, bytes);
+    if (b->pending.fetch_sub(bytes) == bytes)
+        b->completed.fetch_add(1, std::memory_order_release);
+}
+
+// ---- launcher -----------------------------------------------------------------
+template <class F>
+static void emu_launch(F &&body, unsigned gx, unsigned gy, unsigned gz,
+                       unsigned bx, unsigned by, unsigned bz, bool threaded)
+{
+    gridDim = {gx, gy, gz};
+    blockDim = {bx, by, bz};
+    const unsigned nth = bx*by*bz;
+
+    for (unsigned cz = 0; cz < gz; cz++)
+    for (unsigned cy = 0; cy < gy; cy++)
+    for (unsigned cx = 0; cx < gx; cx++)
+    {
+        auto run = [&](unsigned t)
+        {
+            blockIdx = {cx, cy, cz};
+            threadIdx = {t % bx, (t / bx) % by, t / (bx*by)};
+            body();
+        };
+
+        if (!threaded)
+        {
+            for (unsigned t = 0; t < nth; t++)
+                run(t);
+        }
+        else
+        {
+            emu_cta_barrier.n = nth;
+            emu_cta_barrier.waiting = 0;
+            std::vector<std::thread> pool;
+            pool.reserve(nth);
+            for (unsigned t = 0; t < nth; t++)
+                pool.emplace_back(run, t);
+            for (auto &th : pool)
+                th.join();
+        }
+    }
+}

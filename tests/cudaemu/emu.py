@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE -- run the product's generated CUDA kernels on the
+CPU (see emu.h).  ``install(monkeypatch)`` swaps the backend's runtime for
+``EmuRuntime`` and the kernel compiler for a g++ build of the same source
+text, so ``B200Backend`` executes end to end without a GPU: same host
+code, same generators, same fusion decisions, same kernel text.  Only the
+execution substrate differs (OS threads instead of CUDA threads, memcpy
+instead of TMA), so what these tests establish is the *logic* of the
+kernels, not their performance.  Nothing in the product imports this."""
+
+import ctypes as ct
+import hashlib
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_cache = os.path.join(tempfile.gettempdir(), 'pyfr_b200_cudaemu')
+
+_sig_re = re.compile(
+    r'extern "C" __global__ void\s*(?:__launch_bounds__\([^)]*\))?\s*'
+    r'(\w+)\s*\(([^)]*)\)', re.S
+)
+
+
+def _wrapper(src):
+    name, params = _sig_re.search(src).groups()
+    params = [p.strip() for p in params.split(',') if p.strip()]
+    types = [re.sub(r'\w+$', '', p).strip() for p in params]
+
+    unpack = '\n'.join(f'    auto a{i} = *reinterpret_cast<{t} *>(args[{i}]);'
+                       for i, t in enumerate(types))
+    call = ', '.join(f'a{i}' for i in range(len(types)))
+    threaded = int('__syncthreads' in src)
+
+    return name, f'''
+extern "C" void emu_entry(void **args, unsigned gx, unsigned gy, unsigned gz,
+                          unsigned bx, unsigned by, unsigned bz)
+{{
+{unpack}
+    emu_launch([&] {{ {name}({call}); }}, gx, gy, gz, bx, by, bz, {threaded});
+}}
+'''
+
+
+def translate(src):
+    from pyfr_b200.kernels.mul import _pipeline_src
+
+    src = src.replace(_pipeline_src, '')
+    src = src.replace('asm volatile("fence.mbarrier_init.release.cluster;" '
+                      '::: "memory");', '')
+    src = re.sub(r'extern __shared__[^;]*;', '', src)
+    src = src.replace('static __device__ __align__(16) const int',
+                      'alignas(16) static const int')
+    src = src.replace('#define UNROLL _Pragma("unroll")', '#define UNROLL')
+
+    name, wrap = _wrapper(src)
+    return name, f'#include "{_here}/emu.h"\n{src}\n{wrap}'
+
+
+def compile_source(src):
+    name, text = translate(src)
+    key = hashlib.sha256(text.encode()).hexdigest()[:24]
+    os.makedirs(_cache, exist_ok=True)
+    so = os.path.join(_cache, f'{name}-{key}.so')
+
+    if not os.path.exists(so):
+        cpp = so[:-3] + '.cpp'
+        with open(cpp, 'w') as f:
+            f.write(text)
+        res = subprocess.run(
+            ['g++', '-std=c++17', '-O1', '-shared', '-fPIC', '-pthread',
+             '-w', '-o', so + '.tmp', cpp], capture_output=True, text=True
+        )
+        if res.returncode:
+            raise RuntimeError(f'g++ failed for {name}:\n{res.stderr[:3000]}')
+        os.replace(so + '.tmp', so)
+
+    return so
+
+
+class _Module:
+    def __init__(self, so):
+        self.lib = ct.CDLL(so)
+        self.entry = self.lib.emu_entry
+        self.entry.restype = None
+        self.entry.argtypes = [ct.c_void_p] + [ct.c_uint]*6
+
+
+class EmuRuntime:
+    """The subset of pyfr_b200.lib.Runtime the backend uses."""
+
+    dry = False
+    emulated = True
+
+    def __init__(self):
+        self._bufs = {}
+        self._mods = []
+        self.nlaunch = 0
+
+    # -- handles ------------------------------------------------------------
+    def new_ptr(self, fn, *args):
+        return fn(*args)
+
+    def malloc(self, nbytes):
+        buf = np.zeros(max(int(nbytes), 1) + 256, dtype=np.uint8)
+        ptr = (buf.ctypes.data + 255)//256*256
+        self._bufs[ptr] = buf
+        return ptr
+
+    malloc_host = malloc
+
+    def free(self, ptr):
+        self._bufs.pop(ptr, None)
+
+    free_host = free
+
+    def stream_create(self):
+        return 1
+
+    def stream_create_priority(self, high):
+        return 2
+
+    def event_create(self):
+        return 3
+
+    def _noop(self, *a):
+        return None
+
+    stream_destroy = stream_sync = device_sync = event_destroy = _noop
+    event_record = event_sync = stream_wait_event = _noop
+    module_unload = graph_destroy = function_set_dynamic_smem = _noop
+
+    def elapsed_ms(self, a, b):
+        return 0.0
+
+    # -- data movement ------------------------------------------------------
+    def memset(self, ptr, value, nbytes, stream):
+        ct.memset(ptr, value, nbytes)
+
+    def memcpy(self, dst, src, nbytes):
+        ct.memmove(dst, src, nbytes)
+
+    def memcpy_async(self, dst, src, nbytes, stream):
+        ct.memmove(dst, src, nbytes)
+
+    def memcpy2d_async(self, dst, dpitch, src, spitch, width, height, stream):
+        for r in range(height):
+            ct.memmove(dst + r*dpitch, src + r*spitch, width)
+
+    # -- kernels --------------------------------------------------------------
+    def module_load(self, image):
+        m = _Module(compile_source(bytes(image).decode()))
+        self._mods.append(m)
+        return m
+
+    def module_get_function(self, module, name):
+        return module
+
+    def function_attrs(self, func):
+        return dict(nregs=0, static_smem=0, local_bytes=0, max_threads=1024)
+
+    def launch(self, func, gx, gy, gz, bx, by, bz, smem, stream, argv):
+        if smem > 256*1024:
+            raise RuntimeError('emulated shared memory exceeded')
+        func.entry(ct.cast(argv, ct.c_void_p), *map(int, (gx, gy, gz, bx, by,
+                                                          bz)))
+        self.nlaunch += 1
+
+    def device_info(self):
+        return dict(sm_count=148, cc=(10, 0), total_mem=0, free_mem=0,
+                    smem_optin=232448)
+
+    def __getattr__(self, name):
+        def refuse(*a, **k):
+            raise RuntimeError(f'b200_{name}: not available under emulation')
+        return refuse
+
+
+def install(monkeypatch):
+    """Route B200Backend through the emulator (graphs off)."""
+    import pyfr_b200.backend as bk
+    import pyfr_b200.compiler as comp
+
+    monkeypatch.setattr(bk, 'load_runtime',
+                        lambda device=0, dry=False: EmuRuntime())
+    monkeypatch.setattr(comp.KernelCompiler, 'cubin',
+                        lambda self, src, name: src.encode())

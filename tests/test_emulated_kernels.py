@@ -1,0 +1,214 @@
+"""CPU tests that execute the product's *generated CUDA kernels* (the
+same source text that is compiled for sm_100a) on the host through the
+execution model in tests/cudaemu: B200Backend end to end -- host code,
+generators, fusion decisions, launch arguments, kernel bodies -- against
+the oracle.  Complements the -m gpu parity tests (which run the same
+kernels on the device through the C ABI): logic is checked here on every
+CPU run, the device-specific behaviour (TMA, occupancy, timing) there."""
+
+import ctypes as ct
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from pyfr_b200 import cases
+from pyfr_b200.host.system import get_system
+
+from util import OracleBackend, assert_parity, oracle_rhs, rel_err
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                'cudaemu'))
+import emu                                                   # noqa: E402
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    emu.install(monkeypatch)
+
+
+def _b200(cfg, box, vparts=None, rank=0, comm=None, nregs=2, opts={}):
+    from pyfr_b200.backend import B200Backend
+
+    cfg.set('backend-b200', 'graphs', 'false')
+    for k, v in opts.items():
+        cfg.set('backend-b200', k, v)
+
+    be = B200Backend(cfg, comm=comm)
+    assert getattr(be.rt, 'emulated', False)
+    return get_system(be, box.local_mesh(vparts, rank), cfg, nregs,
+                      comm=comm)
+
+
+def _kinds(sysm):
+    return [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
+            for w, k in g.plan if w == 'kernel']
+
+
+@pytest.mark.parametrize('kw,opts,expect', [
+    (dict(order=2, warp=0.1), {}, 'gradflux'),
+    (dict(order=2), {}, 'gradflux'),                           # affine path
+    (dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {}, 'gradflux'),
+    (dict(order=2, beta=-0.5, curved=0.5, warp=0.1), {}, 'gradflux'),
+    (dict(order=2, warp=0.1), {'fusion': 0}, 'tflux'),
+    (dict(order=2, warp=0.1), {'dead-rows': 0, 'gradflux-monojac': 0},
+     'gradflux'),
+    (dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux'),
+    (dict(order=3), {'n-soa': 4}, 'gradflux'),
+], ids=str)
+def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
+                                                     expect):
+    n = (3, 2, 2)
+    cfg, box = cases.make('tgv', n, **kw)
+    sysm = _b200(cfg, box, opts=opts)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs('tgv', n, **kw)
+    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+
+    assert expect in _kinds(sysm)
+    assert_parity(out, ref[0], ext[0], 1e-12)
+
+
+def test_fp32_kernels(emulated):
+    n, kw = (3, 2, 2), dict(order=2, warp=0.1)
+    cfg, box = cases.make('tgv', n, precision='single', **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, r64 = oracle_rhs('tgv', n, **kw)
+    _, r32 = oracle_rhs('tgv', n, precision='single', **kw)
+    floor = rel_err(r32[0].astype(float), r64[0])
+
+    assert out.dtype == np.float32
+    assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
+
+
+@pytest.mark.parametrize('kw,opts,expect', [
+    (dict(order=3), {}, 'fluxdiv'),
+    (dict(order=2, rsolver='hllc'), {'euler-fusion': 0}, 'tflux'),
+], ids=str)
+def test_euler_rhs_through_generated_kernels(emulated, kw, opts, expect):
+    cfg, box = cases.make('vortex', 5, **kw)
+    sysm = _b200(cfg, box, opts=opts)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs('vortex', 5, **kw)
+    _, ext = oracle_rhs('vortex', 5, extended=True, **kw)
+
+    assert expect in _kinds(sysm)
+    assert_parity(out, ref[0], ext[0], 1e-12)
+
+
+@pytest.mark.parametrize('system,n,bcs,kw', [
+    ('navier-stokes', (3, 3, 2), {'ylo': 'no-slp-adia-wall',
+                                  'yhi': 'char-riem-inv'},
+     dict(order=2, warp=0.1)),
+    ('navier-stokes', (2, 2, 3), {'xlo': 'sub-in-frv', 'xhi': 'sub-out-fp',
+                                  'zlo': 'slp-adia-wall',
+                                  'zhi': 'no-slp-isot-wall'},
+     dict(order=2, rsolver='hllc')),
+    ('euler', (5, 4), {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
+                       'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},
+     dict(order=2)),
+], ids=str)
+def test_boundary_kernels(emulated, system, n, bcs, kw):
+    outs = []
+    for which in ('oracle', 'oracle-ext', 'b200'):
+        cfg, box, _ = cases.box_case(system, n, bcs, **kw)
+        if which == 'b200':
+            sysm = _b200(cfg, box)
+        else:
+            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
+            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.5, 0, 1)
+        outs.append(sysm.ele_scal_upts(1)[0])
+
+    assert_parity(outs[2], outs[0], outs[1], 1e-12)
+
+
+class EmuWorld:
+    """In-process stand-in for the NCCL communicator: sends park a copy of
+    the device buffer, receives are filled when a graph stage closes."""
+
+    def __init__(self, size):
+        self.size, self.box, self.pending = size, {}, []
+
+    def peer(self, rank):
+        w = self
+
+        class Comm:
+            size = w.size
+
+            def exchange(self, reqs, stream):
+                for r in reqs:
+                    m = r.mat
+                    nb = m.nrow*m.ncol*m.itemsize
+                    if r.kind == 'send':
+                        w.box[rank, r.peer, r.tag] = ct.string_at(m.data, nb)
+                    else:
+                        w.pending.append(((r.peer, rank, r.tag), m.data, nb))
+
+        c = Comm()
+        c.rank = rank
+        return c
+
+    def deliver(self):
+        for key, ptr, nb in self.pending:
+            ct.memmove(ptr, self.box.pop(key), nb)
+        self.pending.clear()
+
+
+@pytest.mark.parametrize('kw', [dict(order=2, warp=0.1),
+                                dict(order=2, beta=0.0, rsolver='hllc')],
+                         ids=str)
+def test_partitioned_run_through_generated_kernels(emulated, kw):
+    """Two partitions, halo exchange through the backend's exchange
+    descriptors (pack kernels, mpiconu / mpicflux, receive-only graphs):
+    against the partitioned oracle."""
+    n, parts = (4, 2, 2), (2, 1, 1)
+    _, box = cases.make('tgv', n, **kw)
+    vparts = box.brick_partition(parts)
+    world = EmuWorld(2)
+
+    systems = []
+    for r in range(2):
+        cfg, box = cases.make('tgv', n, **kw)
+        systems.append(_b200(cfg, box, vparts, r, comm=world.peer(r)))
+
+    for stage in zip(*[s.rhs_graphs(0, 1) for s in systems]):
+        for g in stage:
+            g.run()
+        world.deliver()
+
+    _, ref = oracle_rhs('tgv', n, vparts=vparts, nparts=2, **kw)
+    _, ext = oracle_rhs('tgv', n, vparts=vparts, nparts=2, extended=True,
+                        **kw)
+
+    for r, s in enumerate(systems):
+        assert_parity(s.ele_scal_upts(1)[0], ref[r], ext[r], 1e-12)
+        assert 'mpiconu' in _kinds(s) and 'copy' not in _kinds(s)
+
+
+def test_rk4_and_integrals_through_generated_kernels(emulated):
+    from pyfr_b200.host.integrator import (FieldIntegrator, RK4Stepper,
+                                           TGV_EXPRS)
+
+    res = []
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make('tgv', (3, 2, 2), order=2, warp=0.1)
+        sysm = (_b200(cfg, box, nregs=3) if which == 'b200' else
+                get_system(OracleBackend(cfg), box.local_mesh(), cfg, 3))
+        fi, st = FieldIntegrator(sysm, cfg, TGV_EXPRS), RK4Stepper(sysm)
+        h = [fi(0.0, st.idxcurr)]
+        st.advance(3, 2e-3)
+        h.append(fi(st.tcurr, st.idxcurr))
+        res.append((np.array(h), st.soln[0]))
+
+    (ho, so), (hb, sb) = res
+    assert np.abs(hb/ho - 1).max() < 1e-12
+    assert rel_err(sb, so) < 1e-12
