@@ -66,13 +66,22 @@ def compile_source(src):
     os.makedirs(_cache, exist_ok=True)
     so = os.path.join(_cache, f'{name}-{key}.so')
 
+    # PYFR_B200_EMU_TSAN=1 builds the kernels with ThreadSanitizer (run the
+    # tests with LD_PRELOAD=$(gcc -print-file-name=libtsan.so)): accesses
+    # to shared/global memory by different CUDA threads that no barrier or
+    # mbarrier orders are reported as data races
+    tsan = bool(os.environ.get('PYFR_B200_EMU_TSAN'))
+    if tsan:
+        so = so[:-3] + '-tsan.so'
+
     if not os.path.exists(so):
         cpp = so[:-3] + '.cpp'
         with open(cpp, 'w') as f:
             f.write(text)
         res = subprocess.run(
             ['g++', '-std=c++17', '-O1', '-shared', '-fPIC', '-pthread',
-             '-w', '-o', so + '.tmp', cpp], capture_output=True, text=True
+             '-w', *(['-fsanitize=thread', '-g'] if tsan else []),
+             '-o', so + '.tmp', cpp], capture_output=True, text=True
         )
         if res.returncode:
             raise RuntimeError(f'g++ failed for {name}:\n{res.stderr[:3000]}')

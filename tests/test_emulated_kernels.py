@@ -212,3 +212,17 @@ def test_rk4_and_integrals_through_generated_kernels(emulated):
     (ho, so), (hb, sb) = res
     assert np.abs(hb/ho - 1).max() < 1e-12
     assert rel_err(sb, so) < 1e-12
+
+
+def test_standalone_driver(emulated, capsys, monkeypatch):
+    """python -m pyfr_b200: RK4 steps + integrals, end to end."""
+    from pyfr_b200.__main__ import main
+
+    main(['tgv', '--n', '2', '--order', '2', '--steps', '2', '--every', '1',
+          '--opt', 'graphs=false'])
+    lines = [l for l in capsys.readouterr().out.splitlines()
+             if l and not l.startswith('#')]
+
+    assert len(lines) == 3
+    ke0 = float(lines[0].split()[2])
+    assert abs(ke0/(2*np.pi)**3 - 0.125) < 2e-2
