@@ -121,5 +121,6 @@ class B200Backend(base.BaseBackend):
 
     def memory_info(self):
         info = self.rt.device_info()
-        return base.MemoryInfo(self._mem_now(), self._mem_peak,
-                               info['free_mem'], info['total_mem'])
+        cur = super().memory_info()
+        return base.MemoryInfo(cur.current, cur.peak, info['free_mem'],
+                               info['total_mem'])

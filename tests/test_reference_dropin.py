@@ -71,3 +71,94 @@ def test_b200_backend_under_reference_host(built):
     assert ns2 == [['mul', 'intconu'], ['gradflux', None], ['mul+negdivconf']]
     assert [k for g in eu for k in g].count(None) >= 1      # intcflux
     assert eu[-1] == ['fluxdiv']
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_memory_info_under_reference_base(built):
+    """memory_info() goes through whichever base class is in use."""
+    code = r'''
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+sys.path.insert(0, %(root)r)
+from oracle import refharness as rh
+rh.install_stubs()
+from pyfr.inifile import Inifile
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+be = B200Backend(Inifile(cases.tgv_cfg(order=2)), dry=True)
+be.matrix((4, 5, 8), tags={'align'})
+be.commit()
+mi = be.memory_info()
+assert mi.current >= 4*5*8*8 and mi.peak >= mi.current, mi
+print('OK')
+'''
+    res = subprocess.run([sys.executable, '-c', code % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and 'OK' in res.stdout, res.stderr[-1500:]
+
+
+_exec_script = r'''
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+from types import SimpleNamespace
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+rh.install_stubs()
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+from pyfr.inifile import Inifile
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr.solvers.euler import EulerSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+for case, n, kw in [('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
+                    ('vortex', 5, dict(order=3))]:
+    kw2 = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
+    txt += '\n[backend-b200]\ngraphs = false\n'
+    _, box = cases.make(case, n, **kw)
+    mesh = box.local_mesh()
+    world = LocalComm(0, 1)
+    rh.set_rank(world.peer(0))
+
+    be = B200Backend(Inifile(txt))
+    regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+    s = cls(be, rh.ref_mesh(mesh), None, regs, Inifile(txt), None)
+    s.commit()
+    s.rhs(0.0, 0, 1)
+    out = s.ele_scal_upts(1)[0]
+
+    rs, rbe = rh.ref_system(txt, mesh, 2, world.peer(0))
+    rs.rhs(0.0, 0, 1)
+    ref = rs.ele_scal_upts(1)[0]
+    print('RESULT', case, np.abs(out - ref).max()/np.abs(ref).max(),
+          be.rt.nlaunch)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_reference_host_executes_on_b200_backend(built):
+    """The complete drop-in, executed: the reference's unmodified systems
+    drive B200Backend (derived from the reference's base classes), whose
+    generated CUDA kernels run on the CPU execution model; the RHS equals
+    the reference host + oracle backend result, in 5 (Navier-Stokes) and
+    3 (Euler) launches."""
+    res = subprocess.run([sys.executable, '-c',
+                          _exec_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+    rows = [l.split() for l in res.stdout.splitlines()
+            if l.startswith('RESULT')]
+    assert [r[1] for r in rows] == ['tgv', 'vortex']
+    assert all(float(r[2]) < 1e-12 for r in rows)
+    assert [int(r[3]) for r in rows] == [5, 3]
