@@ -36,6 +36,7 @@ from pyfr_b200.host.system import get_system                 # noqa: E402
 
 runs = [('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
         ('tgv', (3, 2, 2), dict(order=2)),
+        ('tgv', 2, dict(order=4)),
         ('vortex', 5, dict(order=3))]
 if '--drop-barrier' in sys.argv:
     runs = runs[:1]

@@ -56,6 +56,9 @@ def _kinds(sysm):
      'gradflux'),
     (dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux'),
     (dict(order=3), {'n-soa': 4}, 'gradflux'),
+    # the benchmark's kernel variants (p = 4, 512 threads, 220 KB smem)
+    (dict(order=4), {}, 'gradflux'),
+    (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),
 ], ids=str)
 def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
                                                      expect):
