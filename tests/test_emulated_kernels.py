@@ -229,3 +229,32 @@ def test_standalone_driver(emulated, capsys, monkeypatch):
     assert len(lines) == 3
     ke0 = float(lines[0].split()[2])
     assert abs(ke0/(2*np.pi)**3 - 0.125) < 2e-2
+
+
+def test_bench_script_end_to_end(emulated, monkeypatch, capsys):
+    """bench.py's whole main path (timed loop, per-kernel timing, roofline
+    bookkeeping, pipelined end-to-end section, JSON line) on the emulated
+    runtime; event timings are faked, so only the structure is checked."""
+    import json
+    import runpy
+
+    monkeypatch.setattr(emu.EmuRuntime, 'elapsed_ms', lambda s, a, b: 1.0)
+    monkeypatch.setattr(sys, 'argv', [
+        'bench.py', '--n', '2', '--order', '2', '--steps', '3', '--warmup',
+        '1', '--no-cpu', '--no-clocks', '--no-graphs'
+    ])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, 'bench.py'), run_name='__main__')
+
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup',
+                'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+                'dtype', 'data', 'config', 'gpu_launches', 'roofline', 'e2e',
+                'clocks', 'cpu_baseline'):
+        assert key in line, key
+
+    assert line['launches_per_step'] == 5 and line['gpu_launches'] == 15
+    assert line['e2e']['h2d_bytes_per_step'] == 27*5*8*8
+    assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit',
+                                     'frac', 'traffic'}
