@@ -13,7 +13,7 @@ from pyfr_b200.host.mesh import BoxMesh
 
 
 def tgv_cfg(order=4, precision='double', rsolver='rusanov', beta=0.5,
-            extra=''):
+            extra='', antialias='none'):
     return f'''
 [backend]
 precision = {precision}
@@ -27,6 +27,7 @@ M = 0.1
 [solver]
 system = navier-stokes
 order = {order}
+anti-alias = {antialias}
 shock-capturing = none
 viscosity-correction = none
 
@@ -51,7 +52,8 @@ p = 1/(gamma*M*M) + (cos(2*x) + cos(2*y))*(cos(2*z) + 2)/16
 '''
 
 
-def vortex_cfg(order=3, precision='double', rsolver='rusanov', extra=''):
+def vortex_cfg(order=3, precision='double', rsolver='rusanov', extra='',
+               antialias='none'):
     return f'''
 [backend]
 precision = {precision}
@@ -65,6 +67,7 @@ R = 1.5
 [solver]
 system = euler
 order = {order}
+anti-alias = {antialias}
 shock-capturing = none
 
 [solver-interfaces]

@@ -70,6 +70,8 @@ class BaseElements:
         self.nupts, self.nfpts = basis.nupts, basis.nfpts
         self.nfacefpts = basis.nfacefpts
         self.nvars = self.ndims + 2
+        self.antialias = basis.antialias
+        self.nqpts = basis.nqpts if 'flux' in self.antialias else None
 
         self.kernels = {}
         self._be = None
@@ -219,7 +221,7 @@ class BaseElements:
         nd, nv, ne = self.ndims, self.nvars, self.neles
         nu, nf = self.nupts, self.nfpts
 
-        self.grad_fusion = not be.blocks
+        self.grad_fusion = not (be.blocks or 'flux' in self.antialias)
 
         if self.basis.order >= 2:
             self.linoff = -(-linoff // be.csubsz)*be.csubsz
@@ -233,8 +235,12 @@ class BaseElements:
 
         if 'scal_fpts' in bufs:
             self._scal_fpts = alloc('scal_fpts', (nf, nv, ne))
+        if 'scal_qpts' in bufs:
+            self._scal_qpts = alloc('scal_qpts', (self.nqpts, nv, ne))
         if 'vect_upts' in bufs:
             self._vect_upts = alloc('vect_upts', (nd, nu, nv, ne))
+        if 'vect_qpts' in bufs:
+            self._vect_qpts = alloc('vect_qpts', (nd, self.nqpts, nv, ne))
         if 'vect_fpts' in bufs:
             self._vect_fpts = alloc('vect_fpts', (nd, nf, nv, ne))
 
@@ -302,6 +308,10 @@ class BaseElements:
     def upts(self):
         return self._be.const_matrix(self.basis.upts)
 
+    @cached_property
+    def qpts(self):
+        return self._be.const_matrix(self.basis.qpts)
+
     def _const(self, key, fn, region=None):
         cache = self.__dict__.setdefault('_constcache', {})
 
@@ -359,7 +369,10 @@ class BaseElements:
 
 class AdvectionElements(BaseElements):
     def _scratch_bufs(self):
-        return {'scal_fpts', 'vect_upts'}
+        if 'flux' in self.antialias:
+            return {'scal_fpts', 'scal_qpts', 'vect_qpts'}
+        else:
+            return {'scal_fpts', 'vect_upts'}
 
     def set_backend(self, be, nonce, linoff):
         super().set_backend(be, nonce, linoff)
@@ -371,7 +384,20 @@ class AdvectionElements(BaseElements):
             'mul', self.opmat('M0'), self.scal_upts[uin], out=self._scal_fpts
         )
 
-        if order > 0:
+        # Flux anti-aliasing: flux evaluated at the quadrature points and
+        # projected back (pyfr/solvers/baseadvec/elements.py:78-94)
+        fluxaa = 'flux' in self.antialias
+
+        if fluxaa and order > 0:
+            k['qptsu'] = lambda uin: be.kernel(
+                'mul', self.opmat('M7'), self.scal_upts[uin],
+                out=self._scal_qpts
+            )
+            k['tdivtpcorf'] = lambda fout: be.kernel(
+                'mul', self.opmat('(M1 - M3*M2)*M9'), self._vect_qpts,
+                out=self.scal_upts[fout]
+            )
+        elif order > 0:
             k['tdivtpcorf'] = lambda fout: be.kernel(
                 'mul', self.opmat('M1 - M3*M2'), self._vect_upts,
                 out=self.scal_upts[fout]
@@ -413,6 +439,30 @@ class EulerElements(AdvectionElements):
         r, s = self.mesh_regions, self._slice_mat
 
         tdisf = []
+        if 'flux' in self.antialias:
+            # pyfr/solvers/euler/elements.py:180-206
+            if 'curved' in r:
+                tdisf.append(lambda: be.kernel(
+                    'tflux', tplargs=tplargs | {'ktype': 'curved'},
+                    dims=[self.nqpts, r['curved']],
+                    u=s(self._scal_qpts, 'curved'),
+                    f=s(self._vect_qpts, 'curved'),
+                    smats=self.curved_smat_at('qpts')
+                ))
+            if 'linear' in r:
+                tdisf.append(lambda: be.kernel(
+                    'tflux', tplargs=tplargs | {'ktype': 'linear'},
+                    dims=[self.nqpts, r['linear']],
+                    u=s(self._scal_qpts, 'linear'),
+                    f=s(self._vect_qpts, 'linear'),
+                    verts=self.ploc_at('linspts', 'linear'), upts=self.qpts
+                ))
+
+            self.kernels['tdisf'] = lambda: self._sliced_kernel(
+                k() for k in tdisf
+            )
+            return
+
         if 'curved' in r:
             tdisf.append(lambda uin: be.kernel(
                 'tflux', tplargs=tplargs | {'ktype': 'curved'},
@@ -441,7 +491,9 @@ class NavierStokesElements(AdvectionElements):
     def _scratch_bufs(self):
         bufs = {'scal_fpts', 'vect_fpts', 'vect_upts'}
 
-        if self.grad_fusion:
+        if 'flux' in self.antialias:
+            bufs |= {'scal_qpts', 'vect_qpts'}
+        elif self.grad_fusion:
             bufs |= {'grad_upts'}
 
         if self.basis.fpts_in_upts:
@@ -511,6 +563,22 @@ class NavierStokesElements(AdvectionElements):
         if not (self.basis.fpts_in_upts and self.grad_fusion):
             k['gradcoru_fpts'] = gradcoru_fpts
 
+        fluxaa = 'flux' in self.antialias
+
+        if fluxaa and order > 0:
+            # pyfr/solvers/baseadvecdiff/elements.py:103-116
+            def gradcoru_qpts():
+                nq = self.nqpts
+                vu, vq = self._vect_upts, self._vect_qpts
+                muls = [kernel('mul', self.opmat('M7'),
+                               vu.slice(i*nu, (i + 1)*nu),
+                               vq.slice(i*nq, (i + 1)*nq))
+                        for i in range(self.ndims)]
+
+                return be.unordered_meta_kernel(muls)
+
+            k['gradcoru_qpts'] = gradcoru_qpts
+
         if order == 0:
             return
 
@@ -528,6 +596,27 @@ class NavierStokesElements(AdvectionElements):
 
         fused = self.grad_fusion
         kname = 'tdisf_fused' if fused else 'tdisf'
+
+        if fluxaa:
+            # Flux at the quadrature points (navstokes/elements.py:64-128)
+            specs = []
+            for rgn in ('curved', 'linear'):
+                if rgn not in r:
+                    continue
+
+                kw = ({'smats': self.curved_smat_at('qpts')}
+                      if rgn == 'curved' else
+                      {'verts': self.ploc_at('linspts', 'linear')})
+                kw |= dict(upts=self.qpts, u=s(self._scal_qpts, rgn),
+                           f=s(self._vect_qpts, rgn))
+                specs.append((rgn, r[rgn], kw))
+
+            k['tdisf'] = lambda: self._sliced_kernel(
+                kernel('tflux', tplargs=tplargs | {'ktype': kt},
+                       dims=[self.nqpts, n], artvisc_vtx=None, **kw)
+                for kt, n, kw in specs
+            )
+            return
 
         specs = []
         for rgn in ('curved', 'linear'):

@@ -134,9 +134,9 @@ class TensorShape:
 
         aa = cfg.get('solver', 'anti-alias', 'none')
         self.antialias = {s.strip() for s in aa.split(',')} - {'none'}
-        if self.antialias:
-            raise NotImplementedError('anti-aliasing is outside the scope of '
-                                      'this host mirror')
+        if self.antialias - {'flux'}:
+            raise NotImplementedError('only flux anti-aliasing is within the '
+                                      'scope of this host mirror')
 
         n = self.order + 1
         urule = cfg.get(f'solver-elements-{self.name}', 'soln-pts')
@@ -176,6 +176,39 @@ class TensorShape:
     @cached_property
     def nupts(self):
         return (self.order + 1)**self.ndims
+
+    # Flux anti-aliasing: element quadrature rule (reference shapes.py:
+    # 144-192 -- Gauss-Legendre, (order + 2) points a direction unless
+    # quad-deg / quad-npts say otherwise)
+    @cached_property
+    def _q1d(self):
+        sect = f'solver-elements-{self.name}'
+        rule = self.cfg.get(sect, 'quad-pts', 'gauss-legendre')
+
+        if self.cfg.hasopt(sect, 'quad-deg'):
+            n = self.cfg.getint(sect, 'quad-deg')//2 + 1
+        elif self.cfg.hasopt(sect, 'quad-npts'):
+            n = round(self.cfg.getint(sect, 'quad-npts')**(1/self.ndims))
+        else:
+            n = self.order + 2
+
+        return _line_rules[rule](n)
+
+    @cached_property
+    def qpts(self):
+        return self._tensor_pts(self._q1d[0], self.ndims)
+
+    @cached_property
+    def qpts_wts(self):
+        w1 = self._q1d[1]
+        w = w1
+        for _ in range(self.ndims - 1):
+            w = np.multiply.outer(w1, w)
+        return w.ravel()
+
+    @property
+    def nqpts(self):
+        return len(self.qpts)
 
     @cached_property
     def _face_ref_pts(self):
@@ -333,6 +366,27 @@ class TensorShape:
     def m6(self):
         m = self.norm_fpts.T[:, None, :]*self.m3
         return m.reshape(-1, self.nfpts)
+
+    @cached_property
+    def m7(self):
+        # solution points -> quadrature points
+        return self.ubasis_at(self.qpts)
+
+    @cached_property
+    def m8(self):
+        # L2 projection from the quadrature points back onto the nodal
+        # basis (reference shapes.py:18-19, 130-131)
+        psi_u = self._ortho_at(self.upts)
+        psi_q = self._ortho_at(self.qpts)
+        return clean(psi_u @ (psi_q*self.qpts_wts[:, None]).T)
+
+    @property
+    def m9(self):
+        nd, (a, b) = self.ndims, self.m8.shape
+        m = np.zeros((nd*a, nd*b))
+        for d in range(nd):
+            m[d*a:(d + 1)*a, d*b:(d + 1)*b] = self.m8
+        return m
 
     def opmat(self, expr):
         expr = expr.lower().replace('*', '@')

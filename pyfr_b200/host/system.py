@@ -242,8 +242,9 @@ class EulerSystem(BaseSystem):
         g1.commit()
 
         g2 = be.graph()
+        g2.add_all(k['eles/qptsu'])
         for l in k['eles/tdisf']:
-            g2.add(l)
+            g2.add(l, deps=deps(l, 'eles/qptsu'))
         for l in k['eles/tdivtpcorf']:
             g2.add(l, deps=deps(l, 'eles/tdisf'))
         g2.add_all(k['mpiint/scal_fpts_unpack'])
@@ -254,10 +255,11 @@ class EulerSystem(BaseSystem):
         for l in k['eles/negdivconf']:
             g2.add(l, deps=deps(l, 'eles/tdivtconf'))
 
-        kgroup = [k['eles/tdisf'], k['eles/tdivtpcorf'], k['eles/tdivtconf'],
-                  k['eles/negdivconf']]
+        kgroup = [k['eles/qptsu'], k['eles/tdisf'], k['eles/tdivtpcorf'],
+                  k['eles/tdivtconf'], k['eles/negdivconf']]
         for ks in it.zip_longest(*kgroup):
-            self._group(g2, ks, subs=[[(ks[0], 'f'), (ks[1], 'b')]])
+            self._group(g2, ks, subs=[[(ks[0], 'out'), (ks[1], 'u')],
+                                      [(ks[1], 'f'), (ks[2], 'b')]])
 
         g2.commit()
 
@@ -331,8 +333,16 @@ class NavierStokesSystem(BaseSystem):
         g2.add_all(k['bcint/comm_flux'], deps=ideps,
                    pdeps=k['mpiint/vect_fpts_pack'])
 
+        for l in k['eles/gradcoru_qpts']:
+            g2.add(l, deps=deps(l, 'eles/gradcoru_upts'),
+                   pdeps=k['mpiint/vect_fpts_pack'])
+
+        g2.add_all(k['eles/qptsu'])
+
         for l in k['eles/tdisf']:
-            if k['eles/gradcoru_fpts']:
+            if k['eles/qptsu']:
+                ld = deps(l, 'eles/gradcoru_qpts', 'eles/qptsu')
+            elif k['eles/gradcoru_fpts']:
                 ld = deps(l, 'eles/gradcoru_fpts')
             else:
                 ld = deps(l, 'eles/gradcoru_upts')
@@ -343,10 +353,15 @@ class NavierStokesSystem(BaseSystem):
 
         kgroup = [k['eles/tgradpcoru_upts'], k['eles/tgradcoru_upts'],
                   k['eles/gradcoru_upts'], k['eles/tdisf_fused'],
-                  k['eles/gradcoru_fpts'], [], [], k['eles/tdisf'],
-                  k['eles/tdivtpcorf']]
+                  k['eles/gradcoru_fpts'], k['eles/gradcoru_qpts'],
+                  k['eles/qptsu'], k['eles/tdisf'], k['eles/tdivtpcorf']]
         for ks in it.zip_longest(*kgroup):
-            if k['eles/tdisf_fused']:
+            if k['eles/qptsu']:
+                subs = [[(ks[0], 'out'), (ks[1], 'out'), (ks[2], 'gradu'),
+                         (ks[4], 'b'), (ks[5], 'b')],
+                        [(ks[6], 'out'), (ks[7], 'u')],
+                        [(ks[5], 'out'), (ks[7], 'f'), (ks[8], 'b')]]
+            elif k['eles/tdisf_fused']:
                 subs = [[(ks[0], 'out'), (ks[1], 'out'), (ks[3], 'gradu'),
                          (ks[4], 'b')],
                         [(ks[3], 'f'), (ks[8], 'b')]]

@@ -59,6 +59,17 @@ HOST_CASES = {
                                                      rsolver='hllc'),
                               (2, 1), {'blocks': 1, 'soasz': 8,
                                        'csubsz': 16}),
+    # flux anti-aliasing (quadrature-point flux, M7 / M9 operators)
+    'tgv_p2_fluxaa': ('tgv', (3, 2, 2), dict(order=2, warp=0.1,
+                                             antialias='flux'),
+                      (1, 1, 1), {}),
+    'tgv_p3_fluxaa_blocked_2parts': ('tgv', (4, 2, 2),
+                                     dict(order=3, warp=0.1, rsolver='hllc',
+                                          beta=0.0, antialias='flux'),
+                                     (2, 1, 1), {'blocks': 1, 'soasz': 8,
+                                                 'csubsz': 8}),
+    'vortex_p3_fluxaa': ('vortex', 5, dict(order=3, antialias='flux'),
+                         (1, 1), {}),
 }
 
 # Wall-bounded / open-boundary cases: name -> box_case arguments
@@ -85,7 +96,8 @@ OPMAT_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
                 ('hex', 3, 'gauss-legendre'), ('hex', 4, 'gauss-legendre'),
                 ('hex', 4, 'gauss-legendre-lobatto'),
                 ('hex', 6, 'gauss-legendre')]
-OPMAT_EXPRS = ['M0', 'M4 - M6*M0', 'M6', 'M1 - M3*M2', 'M3']
+OPMAT_EXPRS = ['M0', 'M4 - M6*M0', 'M6', 'M1 - M3*M2', 'M3', 'M7',
+               '(M1 - M3*M2)*M9']
 
 
 def cfg_text(case, kw, beopts):

@@ -258,3 +258,25 @@ def test_bench_script_end_to_end(emulated, monkeypatch, capsys):
     assert line['e2e']['h2d_bytes_per_step'] == 27*5*8*8
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit',
                                      'frac', 'traffic'}
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, antialias='flux')),
+    ('vortex', 5, dict(order=3, antialias='flux', rsolver='hllc')),
+], ids=str)
+def test_flux_antialiasing_through_generated_kernels(emulated, case, n, kw):
+    """Flux anti-aliasing (solution interpolated to quadrature points with
+    M7, flux evaluated there, divergence through (M1 - M3*M2)*M9): generic
+    operator and flux kernels on other point sets."""
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+    _, noaa = oracle_rhs(case, n, **{**kw, 'antialias': 'none'})
+
+    assert_parity(out, ref[0], ext[0], 1e-12)
+    assert rel_err(ref[0], noaa[0]) > 1e-4          # it does something
+    assert 'tflux' in _kinds(sysm) and 'gradflux' not in _kinds(sysm)
