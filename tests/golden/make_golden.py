@@ -96,8 +96,11 @@ OPMAT_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
                 ('hex', 3, 'gauss-legendre'), ('hex', 4, 'gauss-legendre'),
                 ('hex', 4, 'gauss-legendre-lobatto'),
                 ('hex', 6, 'gauss-legendre')]
-OPMAT_EXPRS = ['M0', 'M4 - M6*M0', 'M6', 'M1 - M3*M2', 'M3', 'M7',
-               '(M1 - M3*M2)*M9']
+OPMAT_EXPRS = ['M0', 'M4 - M6*M0', 'M6', 'M1 - M3*M2', 'M3']
+# anti-aliasing operators, for the smaller shapes only (they are dense)
+OPMAT_AA_EXPRS = ['M7', '(M1 - M3*M2)*M9']
+OPMAT_AA_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
+                   ('hex', 3, 'gauss-legendre')]
 
 
 def cfg_text(case, kw, beopts):
@@ -175,7 +178,9 @@ def ref_opmats():
                       f'[solver-interfaces-{face}]\nflux-pts = {pts}\n')
         shape = {'quad': QuadShape, 'hex': HexShape}[et](None, cfg)
 
-        for expr in OPMAT_EXPRS:
+        exprs = OPMAT_EXPRS + (OPMAT_AA_EXPRS
+                               if (et, order, pts) in OPMAT_AA_SHAPES else [])
+        for expr in exprs:
             out[f'{et}|{order}|{pts}|{expr}'] = shape.opmat(expr)
 
         if (et, order, pts) == ('hex', 3, 'gauss-legendre'):

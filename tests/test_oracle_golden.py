@@ -54,7 +54,10 @@ def _our_shape(et, order, pts):
 def test_operator_matrices_match_reference(opmats, et, order, pts):
     shape = _our_shape(et, order, pts)
 
-    for expr in mg.OPMAT_EXPRS:
+    exprs = mg.OPMAT_EXPRS + (mg.OPMAT_AA_EXPRS
+                              if (et, order, pts) in mg.OPMAT_AA_SHAPES
+                              else [])
+    for expr in exprs:
         ref = opmats[f'{et}|{order}|{pts}|{expr}']
         out = shape.opmat(expr)
 
