@@ -13,7 +13,7 @@ from pyfr_b200.host.mesh import BoxMesh
 
 
 def tgv_cfg(order=4, precision='double', rsolver='rusanov', beta=0.5,
-            extra='', antialias='none'):
+            extra='', antialias='none', visc_corr='none'):
     return f'''
 [backend]
 precision = {precision}
@@ -23,13 +23,15 @@ gamma = 1.4
 mu = 6.25e-4
 Pr = 0.71
 M = 0.1
+cpTref = 250.0
+cpTs = 95.0
 
 [solver]
 system = navier-stokes
 order = {order}
 anti-alias = {antialias}
 shock-capturing = none
-viscosity-correction = none
+viscosity-correction = {visc_corr}
 
 [solver-interfaces]
 riemann-solver = {rsolver}

@@ -280,3 +280,18 @@ def test_flux_antialiasing_through_generated_kernels(emulated, case, n, kw):
     assert_parity(out, ref[0], ext[0], 1e-12)
     assert rel_err(ref[0], noaa[0]) > 1e-4          # it does something
     assert 'tflux' in _kinds(sysm) and 'gradflux' not in _kinds(sysm)
+
+
+def test_sutherland_viscosity_through_generated_kernels(emulated):
+    n, kw = (3, 2, 2), dict(order=2, warp=0.1, visc_corr='sutherland')
+    cfg, box = cases.make('tgv', n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs('tgv', n, **kw)
+    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+    _, const = oracle_rhs('tgv', n, **{**kw, 'visc_corr': 'none'})
+
+    assert_parity(out, ref[0], ext[0], 1e-12)
+    assert rel_err(ref[0], const[0]) > 1e-7

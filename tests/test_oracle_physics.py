@@ -188,3 +188,29 @@ def test_far_field_state_is_transparent_to_its_own_free_stream():
                                 {'t': 0.0})
         for a_, b_ in zip(ur, ul):
             assert np.abs(a_ - b_).max() < 1e-12
+
+
+def test_sutherland_law_scales_the_viscous_flux():
+    """With viscosity-correction = sutherland the viscous flux is the
+    constant-viscosity one scaled by mu(T)/mu_ref, mu(T) = mu_ref
+    (T/Tref)^(3/2) (Tref + Ts)/(T + Ts) (written in terms of c_p T)."""
+    ndims, nvars = 3, 5
+    prim, cons = _fields(ndims)
+    rng = np.random.default_rng(5)
+    x = [rng.uniform(-1, 1, 16) for _ in range(ndims)]
+    u, gu = cons(x), _grad(cons, x)
+    c = dict(C, cpTref=3.0, cpTs=1.2)
+
+    f0 = [[0.0*u[0] for _ in range(nvars)] for _ in range(ndims)]
+    f1 = [[0.0*u[0] for _ in range(nvars)] for _ in range(ndims)]
+    ph.viscous_flux_add(u, gu, f0, ndims, nvars, c)
+    ph.viscous_flux_add(u, gu, f1, ndims, nvars, c, 'sutherland')
+
+    rho, vel, p = prim(x)
+    cpT = c['gamma']/(c['gamma'] - 1)*p/rho
+    ratio = ((cpT/c['cpTref'])**1.5*(c['cpTref'] + c['cpTs'])
+             / (cpT + c['cpTs']))
+
+    for d in range(ndims):
+        for i in range(1, nvars):
+            assert np.abs(f1[d][i] - ratio*f0[d][i]).max() < 1e-12
