@@ -311,6 +311,17 @@ def bc_rsolve_state(bctype, ul, nl, ndims, nvars, c, env):
     elif bctype == 'sub-out-fp':
         return [*ul[:nvars - 1],
                 _bcval(c, 'p', env)/gmo + 0.5*(1.0/ul[0])*_ke2(ul, ndims)]
+    elif bctype == 'sub-in-ftpttang':
+        # navstokes/kernels/bcs/sub-in-ftpttang.mako: total pressure and
+        # temperature with a prescribed flow direction
+        pl = gmo*(ul[nvars - 1] - (0.5/ul[0])*_ke2(ul, ndims))
+        udotu = (2.0*c['cpTt'])*(1.0 - c['pt']**(-c['Rdcp'])*pl**c['Rdcp'])
+        udotu = np.maximum(0, udotu)
+
+        ur = [(1.0/c['Rdcp'])*pl/(c['cpTt'] - 0.5*udotu)]
+        ur += [v*ur[0]*np.sqrt(udotu) for v in c['vc']]
+        ur.append((1.0/gmo)*pl + 0.5*ur[0]*udotu)
+        return ur
     elif bctype == 'char-riem-inv':
         pe, rhoe = _bcval(c, 'p', env), _bcval(c, 'rho', env)
         ve = [_bcval(c, v, env) for v in uvw]
@@ -368,7 +379,7 @@ def bc_ldg_grad_state(bctype, ur, nl, gul, ndims, nvars):
     """``bc_ldg_grad_state``: gradient used on the ghost side."""
     if bctype in ('char-riem-inv', 'sup-in-fa', 'sub-in-frv', 'sub-out-fp'):
         return [[0.0*g for g in row] for row in gul]
-    elif bctype in ('sup-out-fn', 'no-slp-isot-wall'):
+    elif bctype in ('sup-out-fn', 'no-slp-isot-wall', 'sub-in-ftpttang'):
         return [list(row) for row in gul]
     elif bctype == 'no-slp-adia-wall':
         # no-slp-adia-wall.mako:22-75: remove the wall-normal temperature

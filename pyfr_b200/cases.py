@@ -112,6 +112,8 @@ BC_SECTIONS = {
                   'p = 71.0\n'),
     'sub-in-frv': 'type = sub-in-frv\nrho = 1.0\nu = 0.2\nv = 0.1\nw = 0.0\n',
     'sub-out-fp': 'type = sub-out-fp\np = 71.0\n',
+    'sub-in-ftpttang': ('type = sub-in-ftpttang\npt = 75.0\ncpTt = 260.0\n'
+                        'theta = 20.0\nphi = 80.0\n'),
 }
 
 

@@ -324,6 +324,10 @@ class BCInters(BaseInters):
                                               ninters=self.ninters)
 
 
+    def _extra_consts(self):
+        pass
+
+
 class EulerBCInters(BCInters):
     def __init__(self, *args):
         super().__init__(*args)
@@ -342,6 +346,7 @@ class NavierStokesBCInters(BCInters):
     def __init__(self, *args):
         super().__init__(*args)
         be, lhs = self._be, self.lhs
+        self._extra_consts()
 
         self._vect_lhs = self._vect_view(lhs, 'get_vect_fpts_for_inters')
         self._comm_lhs = self._scal_view(lhs, 'get_comm_fpts_for_inters')
@@ -368,6 +373,32 @@ class NavierStokesBCInters(BCInters):
             gradul=self._vect_lhs, nl=self._pnorm_lhs, artvisc=None,
             **self._external_vals
         )
+
+
+class NavierStokesSubInflowFtpttang(NavierStokesBCInters):
+    """Total pressure / total temperature inflow with a prescribed flow
+    angle (pyfr/solvers/navstokes/inters.py:170-196)."""
+
+    type = 'sub-in-ftpttang'
+    cflux_state = 'ghost'
+    eval_opts = ('cpTt', 'pt', 'theta')
+
+    def _extra_consts(self):
+        gamma = self.cfg.getfloat('constants', 'gamma')
+        self.c['Rdcp'] = (gamma - 1.0)/gamma
+
+        theta = self.c.pop('theta')*np.pi/180.0
+        vc = np.array([np.cos(theta), np.sin(theta), 1.0])
+
+        if self.ndims == 3:
+            from pyfr_b200.host.exprs import npeval
+            cc = self.cfg.items_as('constants', float)
+            phi = float(npeval(self.cfg.getexpr(self.cfgsect, 'phi'), cc))
+            phi *= np.pi/180.0
+            vc[:2] *= np.sin(phi)
+            vc[2] *= np.cos(phi)
+
+        self.c['vc'] = vc[:self.ndims]
 
 
 def _bc(base, btype, cflux_state=None, expr_opts=(), expr_defaults={},
@@ -402,4 +433,5 @@ navstokes_bc_map = {c.type: c for c in [
     _bc(NavierStokesBCInters, 'sub-in-frv', 'ghost',
         expr_opts=('rho', 'u', 'v', 'w'), expr_defaults=_zero_vel),
     _bc(NavierStokesBCInters, 'sub-out-fp', 'ghost', expr_opts=('p',)),
+    NavierStokesSubInflowFtpttang,
 ]}

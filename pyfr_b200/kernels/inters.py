@@ -344,6 +344,23 @@ def _bc_states_src(tplargs):
             f'ur[NVARS - 1] = {val("p")}/C_GM1 + FP(0.5)*(FP(1.0)/ul[0])*'
             f'({ke("ul")});'])
         alias('bc_ldg_state', 'bc_rsolve_state')
+    elif bt == 'sub-in-ftpttang':
+        rdcp = c['Rdcp']
+        body = [
+            f'const fpdtype_t pl = C_GM1*(ul[NVARS - 1] - (FP(0.5)/ul[0])*'
+            f'({ke("ul")}));',
+            f'fpdtype_t udotu = {ph.fpconst(2.0*c["cpTt"])}*(FP(1.0) - '
+            f'{ph.fpconst(c["pt"]**(-rdcp))}*pow(pl, {ph.fpconst(rdcp)}));',
+            'udotu = fmax(FP(0.0), udotu);',
+            f'ur[0] = {ph.fpconst(1.0/rdcp)}*pl/({ph.fpconst(c["cpTt"])} - '
+            'FP(0.5)*udotu);'
+        ]
+        body += [f'ur[{i + 1}] = {ph.fpconst(v)}*ur[0]*sqrt(udotu);'
+                 for i, v in enumerate(c['vc'])]
+        body.append('ur[NVARS - 1] = (FP(1.0)/C_GM1)*pl + '
+                    'FP(0.5)*ur[0]*udotu;')
+        fn('bc_rsolve_state', body)
+        alias('bc_ldg_state', 'bc_rsolve_state')
     elif bt == 'char-riem-inv':
         Ve = ' + '.join(f'({val(v)})*nl[{i}]' for i, v in enumerate(uvw))
         Vi = ' + '.join(f'ul[{i + 1}]*nl[{i}]' for i in range(nd))

@@ -86,6 +86,9 @@ BC_CASES = {
     'bc_ns_supersonic': ('navier-stokes', (2, 3, 3),
                          {'xlo': 'sup-in-fa', 'xhi': 'sup-out-fn'},
                          dict(order=1, beta=0.0)),
+    'bc_ns_total_inflow': ('navier-stokes', (3, 2, 2),
+                           {'xlo': 'sub-in-ftpttang', 'xhi': 'sub-out-fp'},
+                           dict(order=2, warp=0.1)),
     'bc_euler_all': ('euler', (5, 4),
                      {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
                       'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},

@@ -118,6 +118,9 @@ def test_euler_rhs_through_generated_kernels(emulated, kw, opts, expect):
     ('euler', (5, 4), {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
                        'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},
      dict(order=2)),
+    ('navier-stokes', (3, 2, 2), {'xlo': 'sub-in-ftpttang',
+                                  'xhi': 'sup-out-fn'},
+     dict(order=2, warp=0.1)),
 ], ids=str)
 def test_boundary_kernels(emulated, system, n, bcs, kw):
     outs = []

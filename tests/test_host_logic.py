@@ -413,7 +413,7 @@ def test_unknown_boundary_type_is_refused():
     cfg, box, txt = cases.box_case('navier-stokes', (2, 2, 2),
                                    {'ylo': 'no-slp-adia-wall',
                                     'yhi': 'no-slp-adia-wall'}, order=1)
-    cfg.set('soln-bcs-ylo', 'type', 'sub-in-ftpttang')
+    cfg.set('soln-bcs-ylo', 'type', 'char-riem-inv-mass-flow')
 
     with pytest.raises(NotImplementedError, match='DESIGN.md'):
         get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
