@@ -226,6 +226,43 @@ def make_backend(base, name='oracle-numpy'):
 
             return AxnpbyKernel(None)
 
+        def reduction(self, rop, expr, vvars, svars=[], pvars={}):
+            """pyfr/backends/base/blasext.py:21-46 evaluated over the
+            logical (point, variable, element) arrays: padding never
+            enters, per-variable constants broadcast along axis 1."""
+            vs = list(vvars.values())
+            if any(v.traits != vs[0].traits for v in vs[1:]):
+                raise ValueError('Incompatible matrix types')
+            if rop not in ('sum', 'max'):
+                raise ValueError('Invalid reduction operator')
+
+            fns = {'fabs': np.abs, 'sqrt': np.sqrt, 'fmax': np.maximum,
+                   'fmin': np.minimum, 'pow': np.power, 'exp': np.exp}
+            pv = {k: np.asarray(v, dtype=vs[0].dtype)[None, :, None]
+                  for k, v in pvars.items()}
+            red = np.sum if rop == 'sum' else np.max
+
+            class ReductionKernel(NPKernel):
+                _sv = ()
+
+                def bind(self, *consts):
+                    self._sv = consts
+
+                @property
+                def retval(self):
+                    return self._ret
+
+                def run(self, *args):
+                    ns = dict(fns, **pv, **dict(zip(svars, self._sv)),
+                              **{k: v.get() for k, v in vvars.items()})
+                    with np.errstate(all='ignore'):
+                        self._ret = np.array(
+                            [red(eval(e, {'__builtins__': {}}, ns))
+                             for e in expr], dtype=float
+                        )
+
+            return ReductionKernel(None)
+
         def pack(self, xv):
             v = _ViewRef(xv.view)
             nr, nc, n = xv.nvrow, xv.nvcol, xv.n
@@ -410,6 +447,35 @@ def _negdivconf(be, tplargs, dims, extrns={}, tdivtconf=None, rcpdjac=None,
             tt[i][:] = -r*tt[i]
 
     return be.kernel_cls(run, rtnames=('t',))
+
+
+def _rkvdh2(be, tplargs, dims, extrns={}, r1=None, r2=None, rold=None,
+            rerr=None, **kw):
+    """pyfr/integrators/explicit/kernels/rkvdh2.mako: one stage of a
+    two-register van der Houwen Runge-Kutta scheme (Kennedy, Carpenter &
+    Lewis 2000), optionally accumulating the embedded error estimate."""
+    a, b, e = tplargs['a'], tplargs['b'], tplargs['e']
+    stage, nstages = tplargs['stage'], tplargs['nstages']
+    errest = tplargs['errest']
+
+    def run(dt=0.0):
+        x1, x2 = _mat3(r1), _mat3(r2)
+        t1, t2 = x1.copy(), x2.copy()
+
+        if errest and stage == 0:
+            _mat3(rerr)[:] = dt*e[stage]*t2
+            _mat3(rold)[:] = t1
+        elif errest:
+            xe = _mat3(rerr)
+            xe[:] = xe + dt*e[stage]*t2
+
+        if stage < nstages - 1:
+            x1[:] = t1 + dt*a[stage]*t2
+            x2[:] = t1 + dt*b[stage]*t2
+        else:
+            x1[:] = t1 + dt*b[stage]*t2
+
+    return be.kernel_cls(run, rtnames=('dt',))
 
 
 def _evalsrcmacros(be, tplargs, dims, extrns={}, ploc=None, u=None, **kw):
@@ -658,6 +724,7 @@ _pointwise_impls = {
     'pyfr.solvers.navstokes.kernels.intcflux': _cflux_ns(False),
     'pyfr.solvers.navstokes.kernels.mpicflux': _cflux_ns(True),
     'pyfr.plugins.kernels.fieldeval': _fieldeval,
+    'pyfr.integrators.explicit.kernels.rkvdh2': _rkvdh2,
     'pyfr.solvers.navstokes.kernels.bcconu': _bcconu,
     'pyfr.solvers.navstokes.kernels.bccflux': _bccflux(True),
     'pyfr.solvers.euler.kernels.bccflux': _bccflux(False),

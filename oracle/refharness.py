@@ -49,6 +49,15 @@ class StubComm:
     def recv_init(self, xm, pid, tag):
         return self.local.recv_init(xm, pid, tag)
 
+    # Scalar collectives of the integrators (pyfr/mpiutil.py:99-103); the
+    # harness only ever reduces over a single rank
+    def Allreduce(self, sendbuf, recvbuf, op=None):
+        if self.size != 1:
+            raise NotImplementedError('multi-rank reference integrator')
+
+    def exscan(self, v):
+        return None                     # rank 0's result is undefined in MPI
+
     # Per-boundary communicators (pyfr/solvers/base/system.py:275-278);
     # only their existence matters on this path
     handle = 0

@@ -2,6 +2,8 @@
 backend and print the integrate-plugin diagnostics.
 
     python -m pyfr_b200 tgv --n 32 --order 4 --dt 1e-3 --steps 200 --every 50
+    python -m pyfr_b200 vortex --scheme rk45 --atol 1e-6 --rtol 1e-6 \\
+        --dt 1e-2 --steps 100 --every 25      # adaptive: PI controller
 
 (Inside a PyFR checkout the backend is used through ``pyfr run -b b200``
 instead; this driver exists because PyFR itself is not
@@ -31,14 +33,19 @@ def main(argv=None):
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--every', type=int, default=10, help='print the '
                     'integrals every so many steps')
+    ap.add_argument('--scheme', default='rk4', choices=['rk4', 'rk45'],
+                    help='rk45 runs under the PI step-size controller: '
+                    '--dt is the initial step and --steps*--dt the end time')
+    ap.add_argument('--atol', type=float, default=1e-6)
+    ap.add_argument('--rtol', type=float, default=1e-6)
     ap.add_argument('--opt', action='append', default=[],
                     help='[backend-b200] option key=value')
     args = ap.parse_args(argv)
 
     from pyfr_b200 import cases
     from pyfr_b200.backend import B200Backend
-    from pyfr_b200.host.integrator import (FieldIntegrator, RK4Stepper,
-                                           TGV_EXPRS)
+    from pyfr_b200.host.integrator import (FieldIntegrator, PIController,
+                                           RK4Stepper, RK45Stepper, TGV_EXPRS)
     from pyfr_b200.host.system import get_system
 
     rank = int(os.environ.get('RANK', 0))
@@ -63,24 +70,48 @@ def main(argv=None):
         comm = be.comm = NCCLComm(be.rt, rank, world)
 
     vparts = box.brick_partition(parts) if world > 1 else None
-    sysm = get_system(be, box.local_mesh(vparts, rank), cfg, 3, comm=comm)
+    adaptive = args.scheme == 'rk45'
+    sysm = get_system(be, box.local_mesh(vparts, rank), cfg,
+                      4 if adaptive else 3, comm=comm)
     ndof = sum(sysm.ele_ndofs)*world
 
     exprs = TGV_EXPRS if args.case == 'tgv' else [
         'rho', '0.5*rho*(u*u + v*v)'
     ]
     fi = FieldIntegrator(sysm, cfg, exprs)
-    st = RK4Stepper(sysm)
+
+    bufs = {}
+
+    def allreduce(vals, op='sum'):
+        if world == 1:
+            return vals
+        arr = np.atleast_1d(np.asarray(vals, dtype=float))
+        if len(arr) not in bufs:
+            bufs[len(arr)] = be.matrix((1, len(arr)), tags={'noblock'})
+            be.commit()
+        buf = bufs[len(arr)]
+        buf.set(arr[None])
+        comm.allreduce(buf.data, len(arr), 1, {'sum': 0, 'max': 2}[op],
+                       be.stream)
+        be.wait()
+        out = buf.get()[0]
+        return out if np.ndim(vals) else float(out[0])
+
+    if adaptive:
+        convars = ['rho', 'rhou', 'rhov', 'rhow'][:nd + 1] + ['E']
+        sect = 'solver-time-integrator'
+        for k in ('dt', 'atol', 'rtol'):
+            cfg.set(sect, k, getattr(args, k))
+        st = RK45Stepper(sysm, errest=True)
+        ctl = PIController(st, cfg, convars, allreduce=allreduce)
+    else:
+        st = RK4Stepper(sysm)
 
     def report():
-        vals = fi(st.tcurr, st.idxcurr)
-        if world > 1:
-            buf = be.matrix((1, len(vals)), vals[None], tags={'noblock'})
-            comm.allreduce(buf.data, len(vals), 1, 0, be.stream)
-            be.wait()
-            vals = buf.get()[0]
+        vals = allreduce(fi(st.tcurr, st.idxcurr))
+        nsteps = ctl.nacptsteps if adaptive else st.nsteps
         if rank == 0:
-            print(f'{st.nsteps:8d} {st.tcurr:12.6f} '
+            print(f'{nsteps:8d} {st.tcurr:12.6f} '
                   + ' '.join(f'{v:.12e}' for v in vals), flush=True)
 
     if rank == 0:
@@ -91,13 +122,21 @@ def main(argv=None):
     be.wait()
     t0 = time.perf_counter()
     for i in range(1, args.steps + 1):
-        st.step(args.dt)
+        if not adaptive:
+            st.step(args.dt)
         if i % args.every == 0 or i == args.steps:
+            if adaptive:
+                ctl.advance_to(i*args.dt)
             report()
     be.wait()
     dt = time.perf_counter() - t0
 
-    if rank == 0:
+    if rank == 0 and adaptive:
+        nrhs = 5*(ctl.nacptsteps + ctl.nrjctsteps)
+        print(f'# {ctl.nacptsteps} accepted / {ctl.nrjctsteps} rejected RK45 '
+              f'steps in {dt:.3f} s: {nrhs*ndof/dt/1e9:.3f} GDoF-RHS/s '
+              'including the register updates, error norms and diagnostics')
+    elif rank == 0:
         print(f'# {args.steps} RK4 steps in {dt:.3f} s: '
               f'{4*args.steps*ndof/dt/1e9:.3f} GDoF-RHS/s including the '
               'register updates and diagnostics')

@@ -14,9 +14,19 @@ Host-side counterparts of the callers either side of the RHS path
   per point on the device, weighted with ``w_p |J|`` and summed per
   element by the backend's ``fieldeval`` kernel; the host adds up elements.
 
+* ``RK45Stepper`` + ``PIController`` -- the integrator of BASELINE.json's
+  configs[0] (``scheme = rk45``, ``controller = pi``):
+  ``pyfr/integrators/explicit/steppers.py:111-243`` (two-register van der
+  Houwen scheme; one ``rkvdh2`` kernel per stage, two extra registers for
+  the previous solution and the embedded error estimate) and
+  ``pyfr/integrators/controllers.py:45-121`` /
+  ``pyfr/integrators/explicit/controllers.py:66-131`` (weighted error norm
+  by the backend's ``reduction`` kernel, PI step-size law, accept/reject).
+
 Everything numerical is a backend kernel; this file only sequences them.
 """
 
+import math
 import re
 
 import numpy as np
@@ -49,8 +59,8 @@ class RK4Stepper:
 
         self.backend.run_kernels(self._addk[regs])
 
-    def step(self, dt):
-        add, rhs, t = self._add, self.system.rhs, self.tcurr
+    def _step(self, t, dt):
+        add, rhs = self._add, self.system.rhs
         r0, r1, r2 = self._regidx
 
         if r0 != self.idxcurr:
@@ -73,11 +83,14 @@ class RK4Stepper:
 
         add(1.0, r1, dt/6.0, r2)
 
-        self.idxcurr = r1
+        return r1
+
+    def step(self, dt):
+        self.idxcurr = self._step(self.tcurr, dt)
         self.tcurr += dt
         self.nsteps += 1
 
-        return r1
+        return self.idxcurr
 
     def advance(self, nsteps, dt):
         for _ in range(nsteps):
@@ -86,6 +99,284 @@ class RK4Stepper:
     @property
     def soln(self):
         return self.system.ele_scal_upts(self.idxcurr)
+
+
+class RKVdH2RStepper:
+    """Low-storage RK schemes of Kennedy, Carpenter & Lewis (2000) in van
+    der Houwen form: stage ``i`` evaluates the RHS into ``r2`` and one
+    pointwise kernel forms ``r1 + dt a_i r2`` and ``r1 + dt b_i r2``."""
+
+    a, b, bhat = [], [], []
+    stepper_order = None
+
+    def __init__(self, system, tstart=0.0, errest=False):
+        self.system, self.backend = system, system.backend
+        self.errest = bool(errest and self.bhat)
+        self.nregs = 4 if self.errest else 2
+
+        if system.nrhs < self.nregs:
+            raise ValueError(f'{type(self).__name__} needs {self.nregs} '
+                             'register banks')
+
+        self.tcurr, self.idxcurr, self.nsteps = tstart, 0, 0
+        self._regidx = list(range(self.nregs))
+
+        self.backend.pointwise.register(
+            'pyfr.integrators.explicit.kernels.rkvdh2'
+        )
+
+        self.c = [0.0] + [sum(self.b[:i]) + ai for i, ai in enumerate(self.a)]
+        self.e = [b - bh for b, bh in zip(self.b, self.bhat)]
+        self.nstages = len(self.c)
+        self._kerns = {}
+
+    def _stage_kerns(self, stage, r1, r2, *rs):
+        key = (stage, r1, r2, *rs)
+
+        if key not in self._kerns:
+            tplargs = {
+                'a': self.a, 'b': self.b, 'e': self.e, 'stage': stage,
+                'nstages': self.nstages, 'nvars': self.system.nvars,
+                'errest': bool(rs)
+            }
+            names = ('r1', 'r2', 'rold', 'rerr')
+
+            self._kerns[key] = [
+                self.backend.kernel(
+                    'rkvdh2', tplargs=tplargs, dims=[shp[0], shp[2]],
+                    **{n: em[r] for n, r in zip(names, key[1:])}
+                )
+                for shp, em in zip(self.system.ele_shapes.values(),
+                                   self.system.ele_banks)
+            ]
+
+        return self._kerns[key]
+
+    def _step(self, t, dt):
+        r1 = self.idxcurr
+        r2, *rs = sorted(set(self._regidx) - {r1})
+
+        for i, ci in enumerate(self.c):
+            self.system.rhs(t + ci*dt, r2 if i > 0 else r1, r2)
+
+            kerns = self._stage_kerns(i, r1, r2, *rs)
+            for k in kerns:
+                k.bind(dt=dt)
+            self.backend.run_kernels(kerns)
+
+            r1, r2 = r2, r1
+
+        return (r2, *rs) if rs else r2
+
+    def advance(self, nsteps, dt):
+        """Fixed step size (``controller = none``)."""
+        for _ in range(nsteps):
+            ret = self._step(self.tcurr, dt)
+            self.idxcurr = ret[0] if self.errest else ret
+            self.tcurr += dt
+            self.nsteps += 1
+
+    @property
+    def soln(self):
+        return self.system.ele_scal_upts(self.idxcurr)
+
+
+class RK45Stepper(RKVdH2RStepper):
+    # RK4(3)5[2R+]C of Kennedy, Carpenter & Lewis, Appl. Numer. Math. 35
+    # (2000), table 8 -- the rationals PyFR's rk45 uses (steppers.py:218)
+    stepper_order = 4
+
+    a = [970286171893/4311952581923, 6584761158862/12103376702013,
+         2251764453980/15575788980749, 26877169314380/34165994151039]
+
+    b = [1153189308089/22510343858157, 1772645290293/4653164025191,
+         -1672844663538/4480602732383, 2114624349019/3568978502595,
+         5198255086312/14908931495163]
+
+    bhat = [1016888040809/7410784769900, 11231460423587/58533540763752,
+            -1563879915014/6823010717585, 606302364029/971179775848,
+            1097981568119/3980877426909]
+
+
+class NoneController:
+    """Fixed nominal step size (``controller = none``,
+    ``pyfr/integrators/explicit/controllers.py:46-63``); like the reference
+    the last ``dt-lookahead`` steps before a target time are equalised."""
+
+    sect = 'solver-time-integrator'
+
+    def __init__(self, stepper, cfg):
+        self.stepper, self.system = stepper, stepper.system
+        self.backend = stepper.backend
+
+        self.dt = cfg.getfloat(self.sect, 'dt')
+        self.dtmin = cfg.getfloat(self.sect, 'dt-min', 1e-12)
+        self._dt_lookahead = cfg.getint(self.sect, 'dt-lookahead', 10)
+
+        self.nacptsteps = self.nrjctsteps = 0
+        self.stepinfo = []
+        self._tcomp = 0.0
+
+    @property
+    def tcurr(self):
+        return self.stepper.tcurr
+
+    def _advance_time(self, dt):
+        # Compensated summation, as pyfr/integrators/base.py:282-287
+        st = self.stepper
+        y = dt - self._tcomp
+        t = st.tcurr + y
+        self._tcomp = (t - st.tcurr) - y
+        st.tcurr = t
+
+    def _clamp_dt(self, dt_want, t):
+        remaining = t - self.tcurr
+        nsteps = -(-remaining // dt_want)
+
+        if nsteps > self._dt_lookahead:
+            return dt_want
+        else:
+            return max(remaining / nsteps, self.dtmin)
+
+    def _accept(self, dt, idxcurr, err=None):
+        self._advance_time(dt)
+        self.stepper.idxcurr = idxcurr
+        self.stepper.nsteps += 1
+        self.nacptsteps += 1
+        self.stepinfo.append((dt, 'accept', err))
+
+    def advance_to(self, t):
+        if t < self.tcurr:
+            raise ValueError('Advance time is in the past')
+
+        st = self.stepper
+
+        while self.tcurr < t:
+            dt = self._clamp_dt(self.dt, t)
+            ret = st._step(st.tcurr, dt)
+            self._accept(dt, ret[0] if isinstance(ret, tuple) else ret)
+
+
+class PIController(NoneController):
+    """Adaptive step size for a stepper with an embedded error estimate.
+
+    ``cfg`` supplies ``[solver-time-integrator]`` ``atol``, ``rtol``
+    (or ``atol-<var>``), ``errest-norm``, ``safety-fact``, ``max-fact``,
+    ``min-fact``, ``pi-alpha``, ``pi-beta``, ``dt``, ``dt-max``, ``dt-min``,
+    ``dt-lookahead`` with the reference's defaults.  ``allreduce(x, op)``
+    (op 'sum' or 'max') combines the ranks' error norms and DoF counts; the
+    default is a single rank."""
+
+    def __init__(self, stepper, cfg, convars, allreduce=None):
+        if not stepper.errest:
+            raise TypeError('Incompatible stepper/controller combination')
+
+        super().__init__(stepper, cfg)
+        be = self.backend
+        self._allreduce = allreduce or (lambda x, op: x)
+
+        f = lambda k, d=None: cfg.getfloat(self.sect, k, d)
+        eps = float(np.finfo(be.fpdtype).eps)
+
+        self.dtmax = f('dt-max', 1e2)
+
+        self._rtol = f('rtol')
+        if self._rtol < 10*eps:
+            raise ValueError('Relative tolerance too small')
+
+        has = [cfg.hasopt(self.sect, f'atol-{v}') for v in convars]
+        if any(has) and not all(has):
+            raise ValueError('Missing atol for some variables')
+
+        if all(has):
+            self._atols = tuple(f(f'atol-{v}') for v in convars)
+        else:
+            self._atols = (f('atol'),)*len(convars)
+
+        if any(a < 10*eps for a in self._atols):
+            raise ValueError('Absolute tolerance too small')
+
+        self._norm = cfg.get(self.sect, 'errest-norm', 'l2')
+        if self._norm not in {'l2', 'uniform'}:
+            raise ValueError('Invalid error norm')
+
+        self._saffac = f('safety-fact', 0.8)
+        self._maxfac = f('max-fact', 1.1)
+        self._minfac = f('min-fact', 0.9)
+        if not self._minfac < 1 <= self._maxfac:
+            raise ValueError('Invalid max-fact, min-fact')
+
+        self._alpha, self._beta = f('pi-alpha', 0.58), f('pi-beta', 0.42)
+        self._errprev = 1.0
+
+        self.gndofs = self._allreduce(
+            sum(int(np.prod(s)) for s in self.system.ele_shapes.values()),
+            'sum'
+        )
+
+        self._ekerns = {}
+
+    def _errest(self, rcurr, rerr):
+        if (rcurr, rerr) not in self._ekerns:
+            expr = 'err / (atol + rtol*fabs(curr))'
+            if self._norm == 'uniform':
+                expr, rop = f'fabs({expr})', 'max'
+            else:
+                expr, rop = f'({expr})*({expr})', 'sum'
+
+            kerns = [
+                self.backend.kernel('reduction', rop, [expr],
+                                    {'curr': em[rcurr], 'err': em[rerr]},
+                                    svars=['rtol'],
+                                    pvars={'atol': self._atols})
+                for em in self.system.ele_banks
+            ]
+            self.backend.commit()
+            for k in kerns:
+                k.bind(self._rtol)
+
+            self._ekerns[rcurr, rerr] = kerns
+
+        kerns = self._ekerns[rcurr, rerr]
+        self.backend.run_kernels(kerns, wait=True)
+
+        if self._norm == 'l2':
+            err = self._allreduce(sum(float(k.retval[0]) for k in kerns),
+                                  'sum')
+            err = math.sqrt(err / self.gndofs)
+        else:
+            err = self._allreduce(max(float(k.retval[0]) for k in kerns),
+                                  'max')
+
+        return err if not math.isnan(err) else 100
+
+    def advance_to(self, t):
+        if t < self.tcurr:
+            raise ValueError('Advance time is in the past')
+
+        st = self.stepper
+        expa, expb = self._alpha/st.stepper_order, self._beta/st.stepper_order
+
+        while self.tcurr < t:
+            dt = self._clamp_dt(min(self.dt, self.dtmax), t)
+
+            icurr, iprev, ierr = st._step(st.tcurr, dt)
+            err = self._errest(icurr, ierr)
+
+            fac = err**-expa * self._errprev**expb
+            fac = min(self._maxfac, max(self._minfac, self._saffac*fac))
+            self.dt = fac*dt
+
+            if err < 1.0:
+                self._errprev = err
+                self._accept(dt, icurr, err)
+            else:
+                if dt <= self.dtmin:
+                    raise RuntimeError('Minimum sized time step rejected')
+
+                st.idxcurr = iprev
+                self.nrjctsteps += 1
+                self.stepinfo.append((dt, 'reject', err))
 
 
 def compile_expr(expr, privars, ndims):

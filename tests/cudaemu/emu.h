@@ -23,7 +23,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 #define __constant__ static const
-#define __shared__
+#define __shared__ static      // one CTA runs at a time
 
 struct emu_dim3 { unsigned x, y, z; };
 struct int4 { int x, y, z, w; };
@@ -43,6 +43,35 @@ using std::fmin;
 using std::fmax;
 
 template <class T> static inline T __ldg(const T *p) { return *p; }
+
+// ---- atomics / bit casts -------------------------------------------------------
+static std::mutex emu_atomic_mutex;
+
+template <class T> static inline T atomicAdd(T *p, T v)
+{
+    std::lock_guard<std::mutex> lk(emu_atomic_mutex);
+    T old = *p;
+    *p = old + v;
+    return old;
+}
+
+template <class T> static inline T atomicCAS(T *p, T cmp, T val)
+{
+    std::lock_guard<std::mutex> lk(emu_atomic_mutex);
+    T old = *p;
+    if (old == cmp)
+        *p = val;
+    return old;
+}
+
+static inline double __longlong_as_double(long long v)
+{ double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d)
+{ long long v; std::memcpy(&v, &d, 8); return v; }
+static inline float __uint_as_float(unsigned v)
+{ float f; std::memcpy(&f, &v, 4); return f; }
+static inline unsigned __float_as_uint(float f)
+{ unsigned v; std::memcpy(&v, &f, 4); return v; }
 
 // ---- CTA-wide barrier ---------------------------------------------------------
 struct EmuBarrier

@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import refharness as rh                       # noqa: E402
-from oracle.npbackend import LocalComm                    # noqa: E402
+from oracle.npbackend import LocalComm, make_backend      # noqa: E402
 from pyfr_b200 import cases                               # noqa: E402
 
 # name -> (case, mesh, case kwargs, partition bricks, oracle-backend options)
@@ -386,8 +386,92 @@ def ref_connectivity_case(name):
     return out
 
 
+# Time integration: the reference's own integrator classes (stepper +
+# controller composed by pyfr.integrators.get_integrator) on the oracle
+# backend.  name -> (case, n, kw, [solver-time-integrator] options, target
+# times handed to advance_to one after the other)
+INTG_CASES = {
+    'vortex_p3_rk45_pi_l2': (
+        'vortex', (4, 4), dict(order=3),
+        dict(scheme='rk45', controller='pi', dt=0.05, atol=1e-6, rtol=1e-6),
+        [0.2, 0.33]),
+    'tgv_p2_rk45_pi_uniform': (
+        'tgv', (2, 2, 2), dict(order=2),
+        {'scheme': 'rk45', 'controller': 'pi', 'dt': 0.02,
+         'errest-norm': 'uniform', 'rtol': 1e-5, 'atol-rho': 1e-5,
+         'atol-rhou': 2e-5, 'atol-rhov': 2e-5, 'atol-rhow': 2e-5,
+         'atol-E': 1e-4, 'pi-alpha': 0.7, 'pi-beta': 0.4,
+         'safety-fact': 0.9, 'max-fact': 1.5, 'min-fact': 0.5,
+         'dt-lookahead': 3},
+        [0.15]),
+    'vortex_p3_rk45_none': (
+        'vortex', (4, 4), dict(order=3),
+        dict(scheme='rk45', controller='none', dt=0.01), [0.05]),
+    'vortex_p3_rk4_none': (
+        'vortex', (4, 4), dict(order=3),
+        dict(scheme='rk4', controller='none', dt=0.01), [0.05]),
+}
+
+
+def intg_cfg_text(name):
+    case, n, kw, opts, tlist = INTG_CASES[name]
+    sect = '\n'.join(f'{k} = {v}' for k, v in opts.items())
+    return (cfg_text(case, kw, {}) + '\n[solver-time-integrator]\n'
+            f'formulation = explicit\ntstart = 0\ntend = {tlist[-1]!r}\n'
+            f'{sect}\n')
+
+
+def ref_intg_case(name):
+    case, n, kw, opts, tlist = INTG_CASES[name]
+    _, box = cases.make(case, n, **kw)
+
+    rh.install_stubs()
+    rh.set_rank(LocalComm(0, 1).peer(0))
+
+    import pyfr.backends.base as rbase
+    from pyfr.inifile import Inifile
+    from pyfr.integrators import get_integrator
+    from pyfr.solvers.euler import EulerSystem
+    from pyfr.solvers.navstokes import NavierStokesSystem
+
+    cfg = Inifile(intg_cfg_text(name))
+    be = make_backend(rbase, name='oracle-ref')(cfg)
+    cls = {'euler': EulerSystem,
+           'navier-stokes': NavierStokesSystem}[cfg.get('solver', 'system')]
+    intg = get_integrator(be, cls, rh.ref_mesh(box.local_mesh()), None, cfg)
+
+    # Record every accept / reject decision
+    hist = []
+    for what in ('accept', 'reject'):
+        def wrap(dt, idx, wtime, err=None, _w=what,
+                 _o=getattr(intg, f'_{what}_step')):
+            hist.append((dt, _w == 'accept', -1.0 if err is None else err))
+            _o(dt, idx, wtime, err=err)
+        setattr(intg, f'_{what}_step', wrap)
+
+    out = {'u0': intg.soln[0].copy()}
+    for i, t in enumerate(tlist):
+        intg.advance_to(t)
+        out[f'u_t{i}'] = intg.soln[0].copy()
+        out[f'tcurr_t{i}'] = np.array(intg.tcurr)
+
+    out['hist'] = np.array(hist, dtype=float)
+    out['counts'] = np.array([intg.nacptsteps, intg.nrjctsteps,
+                              intg.nrhsevals, intg.gndofs])
+    out['dt_final'] = np.array(intg.dt)
+    return out
+
+
 def main():
     rh.install_stubs()
+
+    for name in INTG_CASES:
+        np.savez_compressed(os.path.join(HERE, f'intg_{name}.npz'),
+                            **ref_intg_case(name))
+        print(f'intg_{name}.npz written')
+
+    if sys.argv[1:] == ['--intg']:
+        return
 
     for name in CONN_CASES:
         np.savez_compressed(os.path.join(HERE, f'{name}.npz'),

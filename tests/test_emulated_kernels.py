@@ -298,3 +298,97 @@ def test_sutherland_viscosity_through_generated_kernels(emulated):
 
     assert_parity(out, ref[0], ext[0], 1e-12)
     assert rel_err(ref[0], const[0]) > 1e-7
+
+
+def _pi_run(sysm, cfg, tend, norm='l2'):
+    from pyfr_b200.host.integrator import PIController, RK45Stepper
+
+    cfg.set('solver-time-integrator', 'dt', 0.05)
+    cfg.set('solver-time-integrator', 'atol', 1e-6)
+    cfg.set('solver-time-integrator', 'rtol', 1e-6)
+    cfg.set('solver-time-integrator', 'errest-norm', norm)
+
+    st = RK45Stepper(sysm, errest=True)
+    pi = PIController(st, cfg, ['rho', 'rhou', 'rhov', 'E'])
+    pi.advance_to(tend)
+
+    return pi, st
+
+
+@pytest.mark.parametrize('norm', ['l2', 'uniform'])
+def test_rk45_pi_controller_through_generated_kernels(emulated, norm):
+    """BASELINE configs[0]: Euler vortex, rk45 + PI controller.  The
+    rkvdh2 and reduction kernels and the accept/reject history must agree
+    with the oracle backend driven by the same host code."""
+    res = []
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make('vortex', (4, 4), order=3)
+        sysm = (_b200(cfg, box, nregs=4) if which == 'b200' else
+                get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4))
+        pi, st = _pi_run(sysm, cfg, 0.2, norm)
+        res.append((pi.stepinfo, st.soln[0], pi))
+
+    (io, so, po), (ib, sb, pb) = res
+    assert [a[1] for a in io] == [a[1] for a in ib]
+    assert po.nacptsteps >= 3 and po.nrjctsteps >= 1
+    assert pb.tcurr == po.tcurr == 0.2
+    np.testing.assert_allclose([a[0] for a in ib], [a[0] for a in io],
+                               rtol=1e-9)
+    np.testing.assert_allclose([a[2] for a in ib], [a[2] for a in io],
+                               rtol=1e-8)
+    assert rel_err(sb, so) < 1e-12
+
+
+def test_reduction_kernel_ignores_padding(emulated):
+    """Elements beyond neles in the last block hold whatever the kernels
+    left there; the reduction must not see them."""
+    cfg, box = cases.make('vortex', (3, 3), order=2)
+    sysm = _b200(cfg, box, nregs=2)
+    be = sysm.backend
+    a, b = sysm.ele_banks[0]
+
+    rng = np.random.default_rng(3)
+    va, vb = (rng.standard_normal(a.ioshape) for _ in range(2))
+    a.set(va)
+    b.set(vb)
+
+    # poison the padding through the raw storage image
+    raw = np.empty(a.nbytes // a.itemsize)
+    be.rt.memcpy(raw.ctypes.data, a.data, a.nbytes)
+    be.rt.device_sync()
+    neles = a.ioshape[-1]
+    assert neles % be.csubsz, 'case must have a ragged last block'
+    marker = raw.copy()
+    a.set(np.full(a.ioshape, 7.0))
+    be.rt.memcpy(marker.ctypes.data, a.data, a.nbytes)
+    be.rt.device_sync()
+    raw[marker != 7.0] = 1e30
+    be.rt.memcpy(a.data, raw.ctypes.data, a.nbytes)
+    be.rt.device_sync()
+
+    pv = (0.5, 1.0, 2.0, 4.0)
+    for rop, red in (('sum', np.sum), ('max', np.max)):
+        k = be.kernel('reduction', rop, ['s*x*y + w', 'fabs(x)'],
+                      {'x': a, 'y': b}, svars=['s'], pvars={'w': pv})
+        be.commit()
+        k.bind(1.5)
+        be.run_kernels([k], wait=True)
+
+        w = np.array(pv)[None, :, None]
+        want = [red(1.5*va*vb + w), red(np.abs(va))]
+        np.testing.assert_allclose(k.retval, want, rtol=1e-13)
+
+
+def test_standalone_driver_adaptive(emulated, capsys):
+    """python -m pyfr_b200 vortex --scheme rk45: PI-controlled run."""
+    from pyfr_b200.__main__ import main
+
+    main(['vortex', '--n', '3', '--order', '2', '--scheme', 'rk45', '--dt',
+          '0.05', '--steps', '4', '--every', '2', '--opt', 'graphs=false'])
+    out = capsys.readouterr().out.splitlines()
+    rows = [l.split() for l in out if l and not l.startswith('#')]
+
+    assert len(rows) == 3 and float(rows[-1][1]) == pytest.approx(0.2)
+    # mass is conserved by the scheme to round-off
+    assert abs(float(rows[-1][2])/float(rows[0][2]) - 1) < 1e-13
+    assert 'accepted' in out[-1]
