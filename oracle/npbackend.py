@@ -449,6 +449,34 @@ def _negdivconf(be, tplargs, dims, extrns={}, tdivtconf=None, rcpdjac=None,
     return be.kernel_cls(run, rtnames=('t',))
 
 
+def _wavespeed(be, tplargs, dims, extrns={}, u=None, wspd=None, smats=None,
+               rcpdjac=None, verts=None, upts=None, **kw):
+    """pyfr/solvers/euler/kernels/wavespeed.mako: per element the maximum
+    over its points of sum_i |(S_i/|J|).v| + c |S_i/|J||."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    gamma = tplargs['c']['gamma']
+    geom = _geometry(be, tplargs, dims[0], smats, rcpdjac, verts, upts, True)
+
+    def run(t=0.0):
+        sm, rj = geom()
+        us = _stacked(u, nv)
+        rho = us[0]
+        v = [us[i + 1]/rho for i in range(nd)]
+        p = (gamma - 1)*(us[nv - 1] - 0.5*rho*sum(vi*vi for vi in v))
+        csnd = np.sqrt(gamma*p/rho)
+
+        lam = 0
+        for i in range(nd):
+            sij = [sm[i][j]*rj for j in range(nd)]
+            lam = lam + (np.abs(sum(a*b for a, b in zip(sij, v)))
+                         + csnd*np.sqrt(sum(a*a for a in sij)))
+
+        # (nblocks, npts, nchunks, k) -> max over the points
+        _plain(wspd)[:] = lam.max(axis=1, keepdims=True)
+
+    return be.kernel_cls(run)
+
+
 def _rkvdh2(be, tplargs, dims, extrns={}, r1=None, r2=None, rold=None,
             rerr=None, **kw):
     """pyfr/integrators/explicit/kernels/rkvdh2.mako: one stage of a
@@ -725,6 +753,7 @@ _pointwise_impls = {
     'pyfr.solvers.navstokes.kernels.mpicflux': _cflux_ns(True),
     'pyfr.plugins.kernels.fieldeval': _fieldeval,
     'pyfr.integrators.explicit.kernels.rkvdh2': _rkvdh2,
+    'pyfr.solvers.euler.kernels.wavespeed': _wavespeed,
     'pyfr.solvers.navstokes.kernels.bcconu': _bcconu,
     'pyfr.solvers.navstokes.kernels.bccflux': _bccflux(True),
     'pyfr.solvers.euler.kernels.bccflux': _bccflux(False),

@@ -36,6 +36,9 @@ def main(argv=None):
     ap.add_argument('--scheme', default='rk4', choices=['rk4', 'rk45'],
                     help='rk45 runs under the PI step-size controller: '
                     '--dt is the initial step and --steps*--dt the end time')
+    ap.add_argument('--cfl', type=float, default=None, help='choose the '
+                    'step size from the largest wave speed (CFL '
+                    'controller); --steps*--dt is the end time')
     ap.add_argument('--atol', type=float, default=1e-6)
     ap.add_argument('--rtol', type=float, default=1e-6)
     ap.add_argument('--opt', action='append', default=[],
@@ -44,8 +47,9 @@ def main(argv=None):
 
     from pyfr_b200 import cases
     from pyfr_b200.backend import B200Backend
-    from pyfr_b200.host.integrator import (FieldIntegrator, PIController,
-                                           RK4Stepper, RK45Stepper, TGV_EXPRS)
+    from pyfr_b200.host.integrator import (CFLController, FieldIntegrator,
+                                           PIController, RK4Stepper,
+                                           RK45Stepper, TGV_EXPRS)
     from pyfr_b200.host.system import get_system
 
     rank = int(os.environ.get('RANK', 0))
@@ -70,9 +74,10 @@ def main(argv=None):
         comm = be.comm = NCCLComm(be.rt, rank, world)
 
     vparts = box.brick_partition(parts) if world > 1 else None
-    adaptive = args.scheme == 'rk45'
+    adaptive = args.scheme == 'rk45' or args.cfl is not None
     sysm = get_system(be, box.local_mesh(vparts, rank), cfg,
-                      4 if adaptive else 3, comm=comm)
+                      4 if args.scheme == 'rk45' else 3, comm=comm,
+                      needs_cfl=args.cfl is not None)
     ndof = sum(sysm.ele_ndofs)*world
 
     exprs = TGV_EXPRS if args.case == 'tgv' else [
@@ -97,11 +102,17 @@ def main(argv=None):
         out = buf.get()[0]
         return out if np.ndim(vals) else float(out[0])
 
-    if adaptive:
+    sect = 'solver-time-integrator'
+    for k in ('dt', 'atol', 'rtol'):
+        cfg.set(sect, k, getattr(args, k))
+
+    if args.cfl is not None:
+        cfg.set(sect, 'cfl', args.cfl)
+        st = (RK45Stepper(sysm) if args.scheme == 'rk45' else
+              RK4Stepper(sysm))
+        ctl = CFLController(st, cfg, allreduce=allreduce)
+    elif adaptive:
         convars = ['rho', 'rhou', 'rhov', 'rhow'][:nd + 1] + ['E']
-        sect = 'solver-time-integrator'
-        for k in ('dt', 'atol', 'rtol'):
-            cfg.set(sect, k, getattr(args, k))
         st = RK45Stepper(sysm, errest=True)
         ctl = PIController(st, cfg, convars, allreduce=allreduce)
     else:
@@ -132,8 +143,10 @@ def main(argv=None):
     dt = time.perf_counter() - t0
 
     if rank == 0 and adaptive:
-        nrhs = 5*(ctl.nacptsteps + ctl.nrjctsteps)
-        print(f'# {ctl.nacptsteps} accepted / {ctl.nrjctsteps} rejected RK45 '
+        nrhs = (5 if args.scheme == 'rk45' else 4)*(ctl.nacptsteps
+                                                    + ctl.nrjctsteps)
+        print(f'# {ctl.nacptsteps} accepted / {ctl.nrjctsteps} rejected '
+              f'{args.scheme} '
               f'steps in {dt:.3f} s: {nrhs*ndof/dt/1e9:.3f} GDoF-RHS/s '
               'including the register updates, error norms and diagnostics')
     elif rank == 0:

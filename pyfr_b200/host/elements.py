@@ -416,6 +416,42 @@ class AdvectionElements(BaseElements):
             rcpdjac=self.rcpdjac_at('upts'), ploc=None, u=None
         )
 
+    def init_wavespeed(self):
+        """Per-element maximum wave speed for the CFL controller
+        (pyfr/solvers/euler/elements.py:24-69).  Unlike the reference the
+        output is sliced per region, so that on a mesh with curved *and*
+        linear elements each kernel writes its own columns."""
+        be = self._be
+        be.pointwise.register('pyfr.solvers.euler.kernels.wavespeed')
+
+        self._wspd = be.matrix((1, self.neles), tags={'align'})
+        tplargs = self._flux_tplargs()
+        r, s = self.mesh_regions, self._slice_mat
+
+        def kern(uin):
+            ks = []
+            if 'curved' in r:
+                ks.append(be.kernel(
+                    'wavespeed', tplargs=tplargs | {'ktype': 'curved'},
+                    dims=[self.nupts, r['curved']],
+                    u=s(self.scal_upts[uin], 'curved'),
+                    wspd=s(self._wspd, 'curved'),
+                    smats=self.curved_smat_at('upts'),
+                    rcpdjac=self.rcpdjac_at('upts', 'curved')
+                ))
+            if 'linear' in r:
+                ks.append(be.kernel(
+                    'wavespeed', tplargs=tplargs | {'ktype': 'linear'},
+                    dims=[self.nupts, r['linear']],
+                    u=s(self.scal_upts[uin], 'linear'),
+                    wspd=s(self._wspd, 'linear'),
+                    verts=self.ploc_at('linspts', 'linear'), upts=self.upts
+                ))
+            return self._sliced_kernel(ks)
+
+        self.kernels['wavespeed'] = lambda uin: kern(uin)
+        return self._wspd
+
     def _flux_tplargs(self):
         return {
             'ndims': self.ndims, 'nvars': self.nvars,

@@ -257,6 +257,42 @@ class NoneController:
             self._accept(dt, ret[0] if isinstance(ret, tuple) else ret)
 
 
+class CFLController(NoneController):
+    """``controller = cfl`` (pyfr/integrators/controllers.py:7-42): every
+    ``cfl-nsteps`` accepted steps the step size is reset to
+    ``cfl / (lambda_max (2p + 1))`` from the largest wave speed of the
+    current solution.  The system must have been built with
+    ``needs_cfl=True``."""
+
+    def __init__(self, stepper, cfg, allreduce=None):
+        super().__init__(stepper, cfg)
+        self._allreduce = allreduce or (lambda x, op: x)
+
+        self._order = cfg.getint('solver', 'order')
+        self._cfl = cfg.getfloat(self.sect, 'cfl')
+        self.dtmax = cfg.getfloat(self.sect, 'dt-max', 1e2)
+        self._cfl_nsteps = cfg.getint(self.sect, 'cfl-nsteps', 1)
+
+    def _compute_dt_cfl(self, uinbank):
+        local_max = self.system.compute_max_wavespeed(uinbank)
+        global_max = self._allreduce(local_max, 'max')
+        return self._cfl / (global_max*(2*self._order + 1))
+
+    def advance_to(self, t):
+        if t < self.tcurr:
+            raise ValueError('Advance time is in the past')
+
+        st = self.stepper
+
+        while self.tcurr < t:
+            if self.nacptsteps % self._cfl_nsteps == 0:
+                self.dt = self._compute_dt_cfl(st.idxcurr)
+
+            dt = self._clamp_dt(min(self.dt, self.dtmax), t)
+            ret = st._step(st.tcurr, dt)
+            self._accept(dt, ret[0] if isinstance(ret, tuple) else ret)
+
+
 class PIController(NoneController):
     """Adaptive step size for a stepper with an embedded error estimate.
 

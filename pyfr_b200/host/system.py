@@ -34,8 +34,10 @@ class BaseSystem:
     bcmap = {}
     _nonces = it.count()
 
-    def __init__(self, backend, mesh, initsoln, nregs, cfg, comm=None):
+    def __init__(self, backend, mesh, initsoln, nregs, cfg, comm=None,
+                 needs_cfl=False):
         self.backend = be = backend
+        self._needs_cfl = needs_cfl
         self.mesh, self.cfg = mesh, cfg
         self.comm = comm = comm or SerialComm()
         self.ndims = mesh.ndims
@@ -58,6 +60,11 @@ class BaseSystem:
             curved = mesh.spts_curved[et]
             linoff = np.max(np.nonzero(curved)[0], initial=-1) + 1
             e.set_backend(be, nonce, linoff)
+
+        # pyfr/solvers/baseadvec/system.py:16-18
+        if needs_cfl:
+            for e in eles:
+                e.init_wavespeed()
 
         be.commit()
 
@@ -120,6 +127,15 @@ class BaseSystem:
         self.backend.commit()
 
         self._gen_kernels()
+
+        # Reduction kernels for the largest wave speed of each element type
+        # (pyfr/solvers/baseadvec/system.py:48-54)
+        if self._needs_cfl:
+            self._wspd_red_kerns = [
+                self.backend.kernel('reduction', 'max', ['x'], {'x': e._wspd})
+                for e in self.ele_map.values()
+            ]
+
         self.backend.commit()
 
         # What the post-step field integrator needs of the elements
@@ -212,6 +228,13 @@ class BaseSystem:
 
         for g in graphs:
             self.backend.run_graph(g)
+
+    def compute_max_wavespeed(self, uinbank):
+        """pyfr/solvers/baseadvec/system.py:157-161"""
+        k = self._get_kernels(uinbank, None)
+        kerns = k['eles/wavespeed'] + self._wspd_red_kerns
+        self.backend.run_kernels(kerns, wait=True)
+        return max(float(k.retval[0]) for k in self._wspd_red_kerns)
 
     def ele_scal_upts(self, idx):
         return [eb[idx].get() for eb in self.ele_banks]
@@ -435,8 +458,9 @@ class NavierStokesSystem(BaseSystem):
 system_map = {'euler': EulerSystem, 'navier-stokes': NavierStokesSystem}
 
 
-def get_system(backend, mesh, cfg, nregs, comm=None, initsoln=None):
+def get_system(backend, mesh, cfg, nregs, comm=None, initsoln=None,
+               needs_cfl=False):
     cls = system_map[cfg.get('solver', 'system')]
-    sys = cls(backend, mesh, initsoln, nregs, cfg, comm)
+    sys = cls(backend, mesh, initsoln, nregs, cfg, comm, needs_cfl=needs_cfl)
     sys.commit()
     return sys

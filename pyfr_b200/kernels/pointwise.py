@@ -322,3 +322,73 @@ fieldeval({', '.join(args)})
 }}
 '''
     return src, 'fieldeval', [a.split()[-1].lstrip('*') for a in args]
+
+
+def wavespeed_source(be, tplargs, npts, pts):
+    """``wavespeed`` (``pyfr/solvers/euler/kernels/wavespeed.mako``): per
+    element, the largest over its solution points of
+    ``sum_i |(S_i/|J|).v| + c |S_i/|J||`` -- the quantity the CFL
+    controller divides by.  One thread owns one element and walks its
+    points (the ``reduce(max)`` of the reference's kernel spec), so the
+    per-element result needs no atomics."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', npts),
+            ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1)]
+    defs += ph.physics_defines(tplargs['c'])
+
+    gsrc, gargs, gbody = _geom(tplargs, pts)
+
+    args = (['int neles', 'const fpdtype_t* __restrict__ u',
+             'long long u_bsz', 'fpdtype_t* __restrict__ wspd',
+             'long long wspd_bsz'] + gargs)
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+#define LD (NVARS*C_SUB)
+{ph.flux_src}
+{ph.geom_src}
+{gsrc}
+
+extern "C" __global__ void __launch_bounds__(128)
+wavespeed({', '.join(args)})
+{{
+    const long long gid = (long long) blockIdx.x*blockDim.x + threadIdx.x;
+    const int e = (int) (gid % C_SUB);
+    const long long blk = gid / C_SUB;
+
+    if (blk*C_SUB + e >= neles)
+        return;
+
+    fpdtype_t wmax = FP(0.0);
+
+    for (int p = 0; p < NPTS; p++)
+    {{
+{gbody}
+        fpdtype_t us[NVARS], ft[NDIMS][NVARS], pr, vel[NDIMS];
+        UNROLL for (int v = 0; v < NVARS; v++)
+            us[v] = u[blk*u_bsz + (long long) p*LD + COFF(e, v, NVARS)];
+
+        inviscid_flux(us, ft, pr, vel);
+        const fpdtype_t csnd = sqrt(C_GAMMA*pr/us[0]);
+
+        fpdtype_t lam = FP(0.0);
+        UNROLL for (int i = 0; i < NDIMS; i++)
+        {{
+            fpdtype_t sv = FP(0.0), ss = FP(0.0);
+            UNROLL for (int j = 0; j < NDIMS; j++)
+            {{
+                const fpdtype_t sij = s[i][j]*rcpdjac_v;
+                sv += sij*vel[j];
+                ss += sij*sij;
+            }}
+            lam += fabs(sv) + csnd*sqrt(ss);
+        }}
+
+        wmax = fmax(wmax, lam);
+    }}
+
+    wspd[blk*wspd_bsz + e] = wmax;
+}}
+'''
+    return src, 'wavespeed', [a.split()[-1].lstrip('*') for a in args]

@@ -410,6 +410,14 @@ INTG_CASES = {
     'vortex_p3_rk4_none': (
         'vortex', (4, 4), dict(order=3),
         dict(scheme='rk4', controller='none', dt=0.01), [0.05]),
+    'vortex_p3_rk4_cfl': (
+        'vortex', (4, 4), dict(order=3),
+        {'scheme': 'rk4', 'controller': 'cfl', 'dt': 0.01, 'cfl': 0.4,
+         'cfl-nsteps': 2}, [0.12]),
+    'tgv_p2_rk45_cfl_curved': (
+        'tgv', (2, 2, 2), dict(order=2, warp=0.1),
+        {'scheme': 'rk45', 'controller': 'cfl', 'dt': 0.01, 'cfl': 0.3,
+         'dt-max': 0.02}, [0.1]),
 }
 
 

@@ -392,3 +392,52 @@ def test_standalone_driver_adaptive(emulated, capsys):
     # mass is conserved by the scheme to round-off
     assert abs(float(rows[-1][2])/float(rows[0][2]) - 1) < 1e-13
     assert 'accepted' in out[-1]
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('vortex', (4, 3), dict(order=3)),
+    ('tgv', (2, 2, 3), dict(order=2, warp=0.1)),
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, curved=0.5)),
+], ids=['linear', 'curved', 'mixed'])
+def test_wavespeed_and_cfl_controller(emulated, case, n, kw):
+    """wavespeed kernel, max reduction and the CFL step-size rule against
+    the oracle backend under the same host code."""
+    from pyfr_b200.host.integrator import CFLController, RK45Stepper
+
+    res, tend = [], None
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make(case, n, **kw)
+        if which == 'b200':
+            cfg.set('backend-b200', 'graphs', 'false')
+            from pyfr_b200.backend import B200Backend
+            be = B200Backend(cfg)
+        else:
+            be = OracleBackend(cfg)
+        sysm = get_system(be, box.local_mesh(), cfg, 2, needs_cfl=True)
+
+        for k, v in (('dt', 0.01), ('cfl', 0.5), ('cfl-nsteps', 2)):
+            cfg.set('solver-time-integrator', k, v)
+        lam = sysm.compute_max_wavespeed(0)
+        ctl = CFLController(RK45Stepper(sysm), cfg)
+        tend = tend or 3.5*ctl._compute_dt_cfl(0)
+        ctl.advance_to(tend)
+        res.append((lam, [d for d, *_ in ctl.stepinfo],
+                    ctl.stepper.soln[0]))
+
+    (lo, do, so), (lb, db, sb) = res
+    assert lb == pytest.approx(lo, rel=1e-13)
+    assert len(do) >= 3
+    np.testing.assert_allclose(db, do, rtol=1e-12)
+    assert rel_err(sb, so) < 1e-12
+
+
+def test_standalone_driver_cfl(emulated, capsys):
+    from pyfr_b200.__main__ import main
+
+    main(['tgv', '--n', '2', '--order', '2', '--cfl', '0.4', '--dt', '0.01',
+          '--steps', '4', '--every', '4', '--opt', 'graphs=false'])
+    out = capsys.readouterr().out.splitlines()
+    rows = [l.split() for l in out if l and not l.startswith('#')]
+
+    assert float(rows[-1][1]) == pytest.approx(0.04)
+    assert int(rows[-1][0]) >= 2 and 'accepted' in out[-1]

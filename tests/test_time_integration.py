@@ -140,11 +140,19 @@ INTG = {
     'vortex_p3_rk4_none': (
         'vortex', (4, 4), dict(order=3),
         dict(scheme='rk4', controller='none', dt=0.01), [0.05]),
+    'vortex_p3_rk4_cfl': (
+        'vortex', (4, 4), dict(order=3),
+        {'scheme': 'rk4', 'controller': 'cfl', 'dt': 0.01, 'cfl': 0.4,
+         'cfl-nsteps': 2}, [0.12]),
+    'tgv_p2_rk45_cfl_curved': (
+        'tgv', (2, 2, 2), dict(order=2, warp=0.1),
+        {'scheme': 'rk45', 'controller': 'cfl', 'dt': 0.01, 'cfl': 0.3,
+         'dt-max': 0.02}, [0.1]),
 }
 
 
 def make_integrator(sysm, cfg, opts):
-    from pyfr_b200.host.integrator import NoneController
+    from pyfr_b200.host.integrator import CFLController, NoneController
 
     for k, v in opts.items():
         cfg.set('solver-time-integrator', k, v)
@@ -157,6 +165,8 @@ def make_integrator(sysm, cfg, opts):
         nd = sysm.ndims
         convars = ['rho', 'rhou', 'rhov', 'rhow'][:nd + 1] + ['E']
         return PIController(st, cfg, convars), st
+    elif opts['controller'] == 'cfl':
+        return CFLController(st, cfg), st
     else:
         return NoneController(st, cfg), st
 
@@ -172,7 +182,8 @@ def test_host_integrators_reproduce_the_reference(name):
 
     case, n, kw, opts, tlist = INTG[name]
     cfg, box = cases.make(case, n, **kw)
-    sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4)
+    sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4,
+                      needs_cfl=opts['controller'] == 'cfl')
     ctl, st = make_integrator(sysm, cfg, opts)
 
     assert rel_err(st.soln[0], g['u0']) < 1e-14
