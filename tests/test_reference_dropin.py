@@ -162,3 +162,82 @@ def test_reference_host_executes_on_b200_backend(built):
     assert [r[1] for r in rows] == ['tgv', 'vortex']
     assert all(float(r[2]) < 1e-12 for r in rows)
     assert [int(r[3]) for r in rows] == [5, 3]
+
+
+_intg_script = r'''
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm, make_backend
+rh.install_stubs()
+rh.set_rank(LocalComm(0, 1).peer(0))
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+import pyfr.backends.base as rbase
+from pyfr.inifile import Inifile
+from pyfr.integrators import get_integrator
+from pyfr.solvers.euler import EulerSystem
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+INTG = {
+    'pi': ('vortex', (4, 4), dict(order=3), 'scheme = rk45\ncontroller = pi\n'
+           'dt = 0.05\natol = 1e-6\nrtol = 1e-6\n', 0.12),
+    'cfl': ('tgv', (2, 2, 2), dict(order=2, warp=0.1), 'scheme = rk4\n'
+            'controller = cfl\ndt = 0.01\ncfl = 0.4\n', 0.03),
+}
+
+for name, (case, n, kw, sect, tend) in INTG.items():
+    kw2 = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
+    txt += ('\n[backend-b200]\ngraphs = false\n[solver-time-integrator]\n'
+            f'formulation = explicit\ntstart = 0\ntend = {tend}\n{sect}')
+    _, box = cases.make(case, n, **kw)
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+
+    res = []
+    for which in ('oracle', 'b200'):
+        cfg = Inifile(txt)
+        be = (B200Backend(cfg) if which == 'b200' else
+              make_backend(rbase, name='oracle-ref')(cfg))
+        intg = get_integrator(be, cls, rh.ref_mesh(box.local_mesh()), None,
+                              cfg)
+        intg.advance_to(tend)
+        res.append((intg.soln[0].copy(), intg.nacptsteps, intg.nrjctsteps,
+                    intg.dt))
+
+    (so, ao, ro, dto), (sb, ab, rb, dtb) = res
+    print('RESULT', name, np.abs(sb - so).max()/np.abs(so).max(), ao, ab, ro,
+          rb, abs(dtb/dto - 1))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_reference_integrators_execute_on_b200_backend(built):
+    """The reference's composed integrator classes (RK45 + PI controller,
+    RK4 + CFL controller) drive B200Backend through their own call sites:
+    ``kernel('rkvdh2', ...)``, ``kernel('reduction', rop, exprs, vvars,
+    svars=, pvars=)`` with positional ``bind`` and ``retval``,
+    ``kernel('wavespeed', ...)``, ``axnpby``.  Same decisions and solution
+    as on the oracle backend."""
+    res = subprocess.run([sys.executable, '-c',
+                          _intg_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+    rows = {l.split()[1]: l.split()[2:] for l in res.stdout.splitlines()
+            if l.startswith('RESULT')}
+    assert set(rows) == {'pi', 'cfl'}
+
+    for name, (err, ao, ab, ro, rb, ddt) in rows.items():
+        assert float(err) < 1e-12 and float(ddt) < 1e-9
+        assert (ao, ro) == (ab, rb) and int(ao) >= 2
+
+    assert int(rows['pi'][3]) >= 1                # a rejected step happened
