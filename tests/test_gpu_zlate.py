@@ -1,0 +1,192 @@
+"""GPU parity of the features finished after this round's GPU budget was
+spent ("device status"): flux anti-aliasing,
+Sutherland's law, the total-pressure inflow boundary, the rkvdh2 /
+reduction / wavespeed kernels under the PI and CFL controllers.  Each case
+mirrors one that runs on the CPU execution model in
+tests/test_emulated_kernels.py; the file sorts last so that the
+established parity suite reports first."""
+
+import numpy as np
+import pytest
+
+from pyfr_b200 import cases
+from pyfr_b200.host.system import get_system
+
+from util import OracleBackend, assert_parity, oracle_rhs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+
+
+def _b200(cfg, box, nregs=2, **kw):
+    from pyfr_b200.backend import B200Backend
+
+    return get_system(B200Backend(cfg), box.local_mesh(), cfg, nregs, **kw)
+
+
+def _kinds(sysm):
+    return [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
+            for w, k in g.plan if w == 'kernel']
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (4, 3, 3), dict(order=3, warp=0.1, antialias='flux')),
+    ('tgv', (3, 3, 3), dict(order=2, antialias='flux', rsolver='hllc',
+                            beta=0.0)),
+    ('vortex', 9, dict(order=3, antialias='flux', rsolver='hllc')),
+], ids=str)
+def test_flux_antialiasing_matches_oracle(built, case, n, kw):
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+
+    assert_parity(out, ref[0], ext[0], TOL64)
+    assert 'tflux' in _kinds(sysm) and 'gradflux' not in _kinds(sysm)
+
+
+def test_sutherland_viscosity_matches_oracle(built):
+    n, kw = (4, 3, 3), dict(order=3, warp=0.1, visc_corr='sutherland')
+    cfg, box = cases.make('tgv', n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs('tgv', n, **kw)
+    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+    _, const = oracle_rhs('tgv', n, **{**kw, 'visc_corr': 'none'})
+
+    assert 'gradflux' in _kinds(sysm)
+    assert_parity(out, ref[0], ext[0], TOL64)
+    assert rel_err(ref[0], const[0]) > 1e-7
+
+
+def test_total_pressure_inflow_matches_oracle(built):
+    system, n, bcs, kw = ('navier-stokes', (4, 3, 3),
+                          {'xlo': 'sub-in-ftpttang', 'xhi': 'sup-out-fn'},
+                          dict(order=2, warp=0.1))
+    outs = []
+    for which in ('oracle', 'oracle-ext', 'b200'):
+        cfg, box, _ = cases.box_case(system, n, bcs, **kw)
+        if which == 'b200':
+            sysm = _b200(cfg, box)
+        else:
+            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
+            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.5, 0, 1)
+        if which == 'b200':
+            sysm.backend.wait()
+        outs.append(sysm.ele_scal_upts(1)[0])
+
+    assert_parity(outs[2], outs[0], outs[1], TOL64)
+
+
+def test_reduction_kernel(built):
+    """sum / max of expressions with a scalar and per-variable constants;
+    the padding columns of the ragged last block must not contribute."""
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box = cases.make('vortex', (7, 5), order=2)
+    be = B200Backend(cfg)
+    sysm = get_system(be, box.local_mesh(), cfg, 2)
+    a, b = sysm.ele_banks[0]
+    assert a.ioshape[-1] % be.csubsz
+
+    rng = np.random.default_rng(3)
+    va, vb = (rng.standard_normal(a.ioshape) for _ in range(2))
+    b.set(vb)
+
+    # Poison the padding columns through the raw storage image: find them
+    # with a marker pattern, then overwrite them behind the data
+    a.set(np.full(a.ioshape, 7.0))
+    marker = np.empty(a.nbytes // a.itemsize)
+    be.rt.memcpy(marker.ctypes.data, a.data, a.nbytes)
+    be.rt.device_sync()
+    a.set(va)
+    raw = np.empty_like(marker)
+    be.rt.memcpy(raw.ctypes.data, a.data, a.nbytes)
+    be.rt.device_sync()
+    assert (marker != 7.0).any()
+    raw[marker != 7.0] = 1e30
+    be.rt.memcpy(a.data, raw.ctypes.data, a.nbytes)
+    be.rt.device_sync()
+    assert np.array_equal(a.get(), va)
+
+    pv = (0.5, 1.0, 2.0, 4.0)
+    w = np.array(pv)[None, :, None]
+    for rop, red in (('sum', np.sum), ('max', np.max)):
+        k = be.kernel('reduction', rop, ['s*x*y + w', 'fabs(x)'],
+                      {'x': a, 'y': b}, svars=['s'], pvars={'w': pv})
+        be.commit()
+        for s in (1.5, -0.25):                   # rebinding and re-running
+            k.bind(s)
+            be.run_kernels([k], wait=True)
+            want = [red(s*va*vb + w), red(np.abs(va))]
+            np.testing.assert_allclose(k.retval, want, rtol=1e-12)
+
+
+@pytest.mark.parametrize('norm', ['l2', 'uniform'])
+def test_rk45_pi_controller_matches_oracle(built, norm):
+    """BASELINE configs[0]'s integrator: rkvdh2 stages, error norm by the
+    reduction kernel, accept / reject history."""
+    from pyfr_b200.host.integrator import PIController, RK45Stepper
+
+    res = []
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make('vortex', (6, 6), order=3)
+        sysm = (_b200(cfg, box, nregs=4) if which == 'b200' else
+                get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4))
+
+        for k, v in (('dt', 0.08), ('atol', 1e-6), ('rtol', 1e-6),
+                     ('errest-norm', norm)):
+            cfg.set('solver-time-integrator', k, v)
+        st = RK45Stepper(sysm, errest=True)
+        pi = PIController(st, cfg, ['rho', 'rhou', 'rhov', 'E'])
+        pi.advance_to(0.3)
+        res.append((pi.stepinfo, st.soln[0], pi))
+
+    (io, so, po), (ib, sb, pb) = res
+    assert [a[1] for a in io] == [a[1] for a in ib]
+    assert po.nacptsteps >= 3 and po.nrjctsteps >= 1
+    assert pb.tcurr == po.tcurr == 0.3
+    np.testing.assert_allclose([a[0] for a in ib], [a[0] for a in io],
+                               rtol=1e-9)
+    np.testing.assert_allclose([a[2] for a in ib], [a[2] for a in io],
+                               rtol=1e-7)
+    assert rel_err(sb, so) < 1e-11
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('vortex', (6, 5), dict(order=3)),
+    ('tgv', (3, 3, 4), dict(order=2, warp=0.1, curved=0.5)),
+], ids=['linear', 'mixed'])
+def test_wavespeed_and_cfl_controller_match_oracle(built, case, n, kw):
+    from pyfr_b200.host.integrator import CFLController, RK45Stepper
+
+    res, tend = [], None
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make(case, n, **kw)
+        sysm = (_b200(cfg, box, needs_cfl=True) if which == 'b200' else
+                get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2,
+                           needs_cfl=True))
+
+        for k, v in (('dt', 0.01), ('cfl', 0.5), ('cfl-nsteps', 2)):
+            cfg.set('solver-time-integrator', k, v)
+        lam = sysm.compute_max_wavespeed(0)
+        ctl = CFLController(RK45Stepper(sysm), cfg)
+        tend = tend or 3.5*ctl._compute_dt_cfl(0)
+        ctl.advance_to(tend)
+        res.append((lam, [d for d, *_ in ctl.stepinfo],
+                    ctl.stepper.soln[0]))
+
+    (lo, do, so), (lb, db, sb) = res
+    assert lb == pytest.approx(lo, rel=1e-13)
+    assert len(do) >= 3
+    np.testing.assert_allclose(db, do, rtol=1e-12)
+    assert rel_err(sb, so) < 1e-11
