@@ -30,12 +30,27 @@ def _kinds(sysm):
             for w, k in g.plan if w == 'kernel']
 
 
-@pytest.mark.parametrize('case,n,kw', [
+AA_CASES = [
     ('tgv', (4, 3, 3), dict(order=3, warp=0.1, antialias='flux')),
     ('tgv', (3, 3, 3), dict(order=2, antialias='flux', rsolver='hllc',
                             beta=0.0)),
     ('vortex', 9, dict(order=3, antialias='flux', rsolver='hllc')),
-], ids=str)
+]
+
+SUTHERLAND_CASE = ('tgv', (4, 3, 3),
+                   dict(order=3, warp=0.1, visc_corr='sutherland'))
+
+FTPTTANG_CASE = ('navier-stokes', (4, 3, 3),
+                 {'xlo': 'sub-in-ftpttang', 'xhi': 'sup-out-fn'},
+                 dict(order=2, warp=0.1))
+
+CFL_CASES = [
+    ('vortex', (6, 5), dict(order=3)),
+    ('tgv', (3, 3, 4), dict(order=2, warp=0.1, curved=0.5)),
+]
+
+
+@pytest.mark.parametrize('case,n,kw', AA_CASES, ids=str)
 def test_flux_antialiasing_matches_oracle(built, case, n, kw):
     cfg, box = cases.make(case, n, **kw)
     sysm = _b200(cfg, box)
@@ -51,7 +66,7 @@ def test_flux_antialiasing_matches_oracle(built, case, n, kw):
 
 
 def test_sutherland_viscosity_matches_oracle(built):
-    n, kw = (4, 3, 3), dict(order=3, warp=0.1, visc_corr='sutherland')
+    _, n, kw = SUTHERLAND_CASE
     cfg, box = cases.make('tgv', n, **kw)
     sysm = _b200(cfg, box)
     sysm.rhs(0.0, 0, 1)
@@ -68,9 +83,7 @@ def test_sutherland_viscosity_matches_oracle(built):
 
 
 def test_total_pressure_inflow_matches_oracle(built):
-    system, n, bcs, kw = ('navier-stokes', (4, 3, 3),
-                          {'xlo': 'sub-in-ftpttang', 'xhi': 'sup-out-fn'},
-                          dict(order=2, warp=0.1))
+    system, n, bcs, kw = FTPTTANG_CASE
     outs = []
     for which in ('oracle', 'oracle-ext', 'b200'):
         cfg, box, _ = cases.box_case(system, n, bcs, **kw)
@@ -162,10 +175,7 @@ def test_rk45_pi_controller_matches_oracle(built, norm):
     assert rel_err(sb, so) < 1e-11
 
 
-@pytest.mark.parametrize('case,n,kw', [
-    ('vortex', (6, 5), dict(order=3)),
-    ('tgv', (3, 3, 4), dict(order=2, warp=0.1, curved=0.5)),
-], ids=['linear', 'mixed'])
+@pytest.mark.parametrize('case,n,kw', CFL_CASES, ids=['linear', 'mixed'])
 def test_wavespeed_and_cfl_controller_match_oracle(built, case, n, kw):
     from pyfr_b200.host.integrator import CFLController, RK45Stepper
 
