@@ -29,3 +29,4 @@ def test_two_process_halo_exchange(nranks):
 
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-2000:])
     assert res.stdout.count('bit-identical=True') == 3*nranks
+    assert res.stdout.count('adaptive: decisions=True dt=True') == nranks
