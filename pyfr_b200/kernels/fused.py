@@ -340,6 +340,22 @@ class PhaseEmitter:
         NC = self.ncol if LD % self.ncol == 0 else 1
         W, WB = LD // NC, (LD // NC)*isz
 
+        if inplace:
+            # A work item overwrites its own inputs after reading them
+            # all; that is only an in-place *transform* if no other item
+            # reads those rows (block-diagonal operator, one group per
+            # block).  Dense blocks that were split into several groups
+            # (more than smax inputs) do not qualify.
+            owner = {r: (ci, mi) for ci, c in enumerate(classes)
+                     for mi, (rows, ins) in enumerate(c.members)
+                     for r in rows}
+            for ci, c in enumerate(classes):
+                for mi, (rows, ins) in enumerate(c.members):
+                    if any(owner.get(k, (ci, mi)) != (ci, mi)
+                           for k in ins[0]):
+                        raise NotFusable('in-place transform over '
+                                         'overlapping groups')
+
         for ci, c in enumerate(classes):
             nidx = (0 if inplace else c.nout) + sum(c.nins)
             npad = -(-nidx // 4)*4
