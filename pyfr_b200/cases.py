@@ -9,7 +9,7 @@ quads (configs[0]).  Settings follow SURVEY.md section 8(d).
 import numpy as np
 
 from pyfr_b200.host.config import Config
-from pyfr_b200.host.mesh import BoxMesh
+from pyfr_b200.host.mesh import BoxMesh, MixedBoxMesh
 
 
 def tgv_cfg(order=4, precision='double', rsolver='rusanov', beta=0.5,
@@ -153,6 +153,72 @@ def box_case(system, n, bcs, order=3, rsolver='rusanov', beta=0.5,
         txt += f'\n[soln-bcs-{name}]\n{sect}'
 
     return Config(txt), box, txt
+
+
+# Point sets of BASELINE.json configs[3]
+MIXED_POINTS = '''
+[solver-interfaces-line]
+flux-pts = gauss-legendre
+[solver-interfaces-quad]
+flux-pts = gauss-legendre
+[solver-interfaces-tri]
+flux-pts = williams-shunn
+[solver-elements-quad]
+soln-pts = gauss-legendre
+[solver-elements-tri]
+soln-pts = williams-shunn
+[solver-elements-hex]
+soln-pts = gauss-legendre
+[solver-elements-tet]
+soln-pts = shunn-ham
+[solver-elements-pri]
+soln-pts = williams-shunn~gauss-legendre
+[solver-elements-pyr]
+soln-pts = gauss-legendre
+'''
+
+MIXED_PATTERNS = {
+    'quad+tri': ['quad', 'tri'],
+    'hex+pri': ['hex', 'pri'],
+    'hex+pri+pyr+tet': ['hex', 'pri', 'pyr', 'pyt'],
+}
+
+
+def mixed_case(pattern, n, order=3, warp=0.05, h=1.0, **kw):
+    """A periodic box mixing element types (``pattern``: a key of
+    ``MIXED_PATTERNS``; ``n = (nx, ny[, nz])`` unit cells): Euler in 2-D,
+    Navier-Stokes in 3-D, smooth box-periodic initial condition.  Returns
+    ``(Config, MixedBoxMesh, config text)``."""
+    import re
+
+    kinds = MixedBoxMesh.columns(*(tuple(n) + (None,))[:3],
+                                 MIXED_PATTERNS[pattern])
+    nd = kinds.ndim
+
+    if nd == 2:
+        txt = vortex_cfg(order=order, **kw)
+        ics = ('rho = 1 + 0.1*sin(kx*x)*cos(ky*y)\n'
+               'u = 0.3 + 0.1*cos(kx*x + ky*y)\nv = 0.15 + 0.1*sin(ky*y)\n'
+               'p = 4.5*(1 + 0.02*cos(kx*x))\n')
+    else:
+        txt = tgv_cfg(order=order, **kw)
+        ics = ('rho = 1 + 0.1*sin(kx*x)*cos(ky*y)\n'
+               'u = 0.3 + 0.1*cos(kx*x + ky*y)\n'
+               'v = 0.15 + 0.1*sin(ky*y)*cos(kz*z)\n'
+               'w = 0.1 + 0.05*sin(kz*z + kx*x)\n'
+               'p = 71*(1 + 0.02*cos(kx*x)*sin(kz*z))\n')
+
+    ks = ''.join(f'k{"xyz"[a]} = {2*np.pi/(kinds.shape[a]*h)!r}\n'
+                 for a in range(nd))
+    head = txt.partition('[soln-ics]')[0]
+    head = head.replace('[constants]\n', '[constants]\n' + ks)
+
+    extra = MIXED_POINTS
+    for sect in re.findall(r'^\[([^\]]+)\]', head, flags=re.M):
+        extra = re.sub(r'\[' + re.escape(sect) + r'\]\n[^\[]*', '', extra)
+
+    txt = head + '[soln-ics]\n' + ics + extra
+    return Config(txt), MixedBoxMesh(kinds, h=h, warp=warp), txt
 
 
 def make(case, n, **kw):

@@ -243,3 +243,194 @@ class BoxMesh:
                                                   self.cidxmap)
 
         return mesh
+
+
+# -- mixed element boxes (BASELINE.json configs[3]) ---------------------------
+# Vertex lists in std-element order (pyfr/shapes.py std_ele(1)) as corner
+# offsets of the unit cell; 'P' is the cell centre.  Every element has a
+# positive Jacobian.
+_TRI_PAIR = [[(0, 0), (1, 0), (0, 1)], [(1, 1), (0, 1), (1, 0)]]
+
+# Quadrilateral bases of the six pyramids of a cell, wound so that the
+# normal of (V1 - V0) x (V2 - V0) points at the cell centre
+_PYR_BASES = [
+    [(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0)],       # z lo
+    [(0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 1)],       # z hi
+    [(0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1)],       # x lo
+    [(1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1)],       # x hi
+    [(0, 0, 0), (0, 0, 1), (1, 0, 0), (1, 0, 1)],       # y lo
+    [(0, 1, 0), (1, 1, 0), (0, 1, 1), (1, 1, 1)],       # y hi
+]
+
+
+def _cell_elements(kind):
+    if kind == 'quad':
+        return {'quad': [[(0, 0), (1, 0), (0, 1), (1, 1)]]}
+    if kind == 'tri':
+        return {'tri': _TRI_PAIR}
+    if kind == 'hex':
+        return {'hex': [[(i, j, k) for k in (0, 1) for j in (0, 1)
+                         for i in (0, 1)]]}
+    if kind == 'pri':
+        return {'pri': [[v + (k,) for k in (0, 1) for v in t]
+                        for t in _TRI_PAIR]}
+    if kind == 'pyr':
+        return {'pyr': [b + ['P'] for b in _PYR_BASES]}
+    if kind == 'pyt':
+        # top and bottom pyramids split into two tetrahedra on the V0-V3
+        # diagonal of their bases (the same physical diagonal on both)
+        tets = []
+        for v0, v1, v2, v3 in _PYR_BASES[:2]:
+            tets += [[v0, v1, v3, 'P'], [v0, v3, v2, 'P']]
+        return {'pyr': [b + ['P'] for b in _PYR_BASES[2:]], 'tet': tets}
+    raise ValueError(f'Unknown cell kind {kind!r}')
+
+
+class MixedBoxMesh:
+    """Fully periodic conforming box of several element types.
+
+    ``kinds[i, j(, k)]`` is the kind of each unit cell: ``quad`` | ``tri``
+    (cell cut on its anti-diagonal) in 2-D; ``hex`` | ``pri`` (that triangle
+    pair extruded) | ``pyr`` (six pyramids about the cell centre) | ``pyt``
+    (ditto, top and bottom pyramid cut into two tetrahedra each) in 3-D.
+    Cells stacked in z must share their kind (``columns`` builds such
+    arrays) so that neighbouring columns meet in whole quadrilaterals.
+    Single partition only."""
+
+    def __init__(self, kinds, h=1.0, warp=0.0):
+        self.kinds = kinds = np.asarray(kinds, dtype=object)
+        self.ndims = nd = kinds.ndim
+        self.n, self.h, self.warp = kinds.shape, h, warp
+        self.L = np.array(self.n, dtype=float)*h
+
+        verts = {}
+        for idx in np.ndindex(*self.n):
+            org = np.array(idx, dtype=float)
+            for et, lists in _cell_elements(kinds[idx]).items():
+                for vl in lists:
+                    verts.setdefault(et, []).append(
+                        [(org + 0.5 if isinstance(v, str) else
+                          org + np.array(v))*h for v in vl]
+                    )
+
+        self.etypes = etypes = sorted(verts)
+        # (nverts, neles, ndims), unwarped: face pairing works on these
+        self._x0 = {et: np.array(verts[et]).swapaxes(0, 1) for et in etypes}
+
+        fv = {et: _face_verts(et) for et in etypes}
+        self.codec = [f'eles/{et}' for et in etypes]
+        for et in etypes:
+            self.codec += [f'eles/{et}/face/{f}' for f in range(len(fv[et]))]
+        self.cidxmap = {self.codec.index(f'eles/{et}/face/{f}'): (et, f)
+                        for et in etypes for f in range(len(fv[et]))}
+
+        # Pair faces through their centroids (vertex means), folded into
+        # the period and scaled so that every centroid is an integer
+        table = {}
+        per = 12*np.array(self.n)
+        for et in etypes:
+            for f, ids in enumerate(fv[et]):
+                cen = self._x0[et][ids].mean(axis=0)
+                keys = np.rint(cen*12/h).astype(np.int64) % per
+                for e, k in enumerate(map(tuple, keys)):
+                    table.setdefault(k, []).append((et, e, f))
+
+        if any(len(v) != 2 for v in table.values()):
+            raise ValueError('Cell kinds do not form a conforming mesh')
+
+        self.faces = {et: np.zeros((self._x0[et].shape[1], len(fv[et]), 2),
+                                   dtype=np.int64) for et in etypes}
+        for a, b in table.values():
+            for (et, e, f), (net, ne, nf) in ((a, b), (b, a)):
+                self.faces[et][e, f] = (
+                    self.codec.index(f'eles/{net}/face/{nf}'), ne
+                )
+
+    @staticmethod
+    def columns(nx, ny, nz, pattern):
+        """Kinds for an ``nx x ny (x nz)`` box: column (i, j) gets
+        ``pattern[(i + 2 j) % len(pattern)]``."""
+        k2 = np.array([[pattern[(i + 2*j) % len(pattern)] for j in range(ny)]
+                       for i in range(nx)], dtype=object)
+        return k2 if nz is None else np.repeat(k2[:, :, None], nz, axis=2)
+
+    def vertices(self, et):
+        x = self._x0[et]
+
+        if self.warp:
+            nd = self.ndims
+            ph = 2*np.pi*x/self.L
+            x = x + self.warp*self.h*np.stack(
+                [np.sin(ph[..., (a + 1) % nd] + 0.5 + 0.4*a)
+                 for a in range(nd)], axis=-1
+            )
+
+        return np.ascontiguousarray(x)
+
+    def local_mesh(self, vparts=None, rank=0):
+        if vparts is not None and np.any(np.asarray(vparts) != 0):
+            raise NotImplementedError('partitioned mixed meshes')
+
+        mesh = Mesh(ndims=self.ndims, codec=self.codec,
+                    etypes=list(self.etypes), cidxmap=self.cidxmap,
+                    uuid='mixed')
+
+        # Flatten: type by type, face by face, element by element
+        # (pyfr/readers/native.py:430-443)
+        parts = []
+        for et in self.etypes:
+            ne = self._x0[et].shape[1]
+            mesh.eidxs[et] = np.arange(ne)
+            mesh.spts[et] = self.vertices(et)
+            mesh.spts_curved[et] = np.zeros(ne, dtype=bool)
+
+            for f in range(self.faces[et].shape[1]):
+                lc = self.codec.index(f'eles/{et}/face/{f}')
+                parts.append((np.full(ne, lc), np.arange(ne),
+                              self.faces[et][:, f, 0],
+                              self.faces[et][:, f, 1]))
+
+        lcidx, leidx, rcidx, reidx = map(np.concatenate, zip(*parts))
+
+        # Interior faces once, smaller (cidx, element) key on the left
+        stride = max(leidx.max(), reidx.max()) + 1
+        keep = np.flatnonzero(lcidx*stride + leidx < rcidx*stride + reidx)
+
+        mesh.con = (Connectivity(lcidx[keep], leidx[keep], self.cidxmap),
+                    Connectivity(rcidx[keep], reidx[keep], self.cidxmap))
+
+        return mesh
+
+
+def _face_verts(etype):
+    """Vertex numbers (std-element order) on each face of a linear
+    element."""
+    shape = shape_map[etype]
+
+    if hasattr(shape, 'faces') and shape.faces is not None:
+        corners = {'line': [(-1,), (1,)],
+                   'quad': [(-1, -1), (1, -1), (-1, 1), (1, 1)]}
+        lin = np.asarray(shape.std_ele(1), dtype=float)
+        return [[int(np.argmin(np.abs(lin - np.array(proj(*c),
+                                                     dtype=float)).sum(1)))
+                 for c in corners[kind]]
+                for kind, proj, _ in shape.faces]
+    else:
+        return shape(_nverts[etype], _LinCfg(etype)).faceverts
+
+
+_nverts = {'tri': 3, 'tet': 4, 'pri': 6, 'pyr': 5}
+
+
+class _LinCfg:
+    """Just enough configuration to look a tabulated shape up."""
+
+    def __init__(self, etype):
+        from pyfr_b200.host.shapes import TabulatedShape
+        self._rule = TabulatedShape._rules[etype]
+
+    def getint(self, sect, opt, default=None):
+        return 1
+
+    def get(self, sect, opt, default=None):
+        return self._rule if opt == 'soln-pts' else default

@@ -11,6 +11,7 @@ so no (p+1)^3-sized Vandermonde matrix is ever inverted.
 
 from functools import cached_property
 import itertools as it
+import os
 import re
 
 import numpy as np
@@ -462,4 +463,121 @@ class HexShape(TensorShape):
     jac_exprs = _lin_jac_exprs(3)
 
 
-shape_map = {'quad': QuadShape, 'hex': HexShape}
+class TabulatedShape:
+    """Simplex, prism and pyramid elements from tabulated data.
+
+    Their orthonormal bases and point sets (Williams-Shunn, Shunn-Ham, ...)
+    are not constructed here: ``data/tabshapes.npz`` holds, for the point
+    sets of BASELINE.json configs[3] and orders 1-3, the operator matrices,
+    point sets, weights, normals and nodal-basis evaluations produced by
+    the reference's ``pyfr/shapes.py`` (generator:
+    ``tests/golden/make_golden.py --shapes``).  Linear (straight-sided)
+    elements only; no anti-aliasing."""
+
+    name = ndims = None
+    _data = None
+    _rules = {
+        'tri': 'williams-shunn', 'tet': 'shunn-ham',
+        'pri': 'williams-shunn~gauss-legendre', 'pyr': 'gauss-legendre',
+    }
+
+    def __init__(self, nspts, cfg):
+        if TabulatedShape._data is None:
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                'data', 'tabshapes.npz')
+            TabulatedShape._data = dict(np.load(path))
+
+        self.nspts, self.cfg = nspts, cfg
+        self.order = cfg.getint('solver', 'order')
+        self.antialias = set()
+
+        aa = cfg.get('solver', 'anti-alias', 'none')
+        rule = cfg.get(f'solver-elements-{self.name}', 'soln-pts')
+        self._pre = pre = f'{self.name}_p{self.order}_'
+
+        if aa != 'none' or rule != self._rules[self.name] or \
+           pre + 'upts' not in self._data:
+            raise NotImplementedError(
+                f'{self.name} elements are tabulated for orders 1-3, the '
+                f'{self._rules[self.name]} points and no anti-aliasing'
+            )
+        if nspts != len(self.linspts):
+            raise NotImplementedError('curved simplex/prism/pyramid elements')
+
+        self.nsptsord = 1
+
+    def _get(self, key):
+        return self._data[self._pre + key]
+
+    upts = property(lambda self: self._get('upts'))
+    upts_wts = property(lambda self: self._get('upts_wts'))
+    fpts = property(lambda self: self._get('fpts'))
+    mpts = property(lambda self: self._get('mpts'))
+    linspts = property(lambda self: self._get('linspts'))
+    spts = property(lambda self: self._get('linspts'))
+    norm_fpts = property(lambda self: self._get('norm_fpts'))
+    nupts = property(lambda self: len(self._get('upts')))
+    nfpts = property(lambda self: len(self._get('fpts')))
+    nmpts = property(lambda self: len(self._get('mpts')))
+    nqpts = qpts = None
+    fpts_in_upts = False
+
+    @cached_property
+    def nfacefpts(self):
+        return self._get('nfacefpts').tolist()
+
+    @cached_property
+    def facefpts(self):
+        flat = self._get('facefpts').tolist()
+        off = np.cumsum([0] + self.nfacefpts)
+        return [flat[a:b] for a, b in zip(off, off[1:])]
+
+    @cached_property
+    def faceverts(self):
+        flat = self._get('faceverts').tolist()
+        off = np.cumsum([0] + self._get('nfaceverts').tolist())
+        return [flat[a:b] for a, b in zip(off, off[1:])]
+
+    @cached_property
+    def jac_exprs(self):
+        return [[str(e) for e in row] for row in self._get('jac_exprs')]
+
+    def _named(self, pts):
+        pts = np.atleast_2d(np.asarray(pts, dtype=float))
+        for n in ('upts', 'fpts', 'mpts', 'linspts'):
+            ref = self._get(n)
+            if ref.shape == pts.shape and np.array_equal(ref, pts):
+                return n
+        raise NotImplementedError('basis evaluation away from the tabulated '
+                                  'point sets')
+
+    def sbasis_at(self, pts):
+        return self._get(f'sbasis@{self._named(pts)}')
+
+    def mbasis_at(self, pts):
+        return self._get(f'mbasis@{self._named(pts)}')
+
+    def mbasis_deriv_at(self, pts, d):
+        if self._named(pts) != 'mpts':
+            raise NotImplementedError('metric basis derivative away from the '
+                                      'metric points')
+        return self._get('mbasis_deriv@mpts')[d]
+
+    def opmat(self, expr):
+        expr = expr.lower().replace('*', '@')
+
+        if not re.match(r'[m0-9\-+@() ]+$', expr):
+            raise ValueError('Invalid operator matrix expression')
+
+        mats = {m: self._get(m) for m in re.findall(r'm\d+', expr)}
+        return clean(eval(expr, {'__builtins__': None}, mats))
+
+
+def _tabulated(name_, ndims_):
+    return type(f'{name_.title()}Shape', (TabulatedShape,),
+                dict(name=name_, ndims=ndims_))
+
+
+shape_map = {'quad': QuadShape, 'hex': HexShape,
+             'tri': _tabulated('tri', 2), 'tet': _tabulated('tet', 3),
+             'pri': _tabulated('pri', 3), 'pyr': _tabulated('pyr', 3)}

@@ -95,6 +95,21 @@ BC_CASES = {
                      dict(order=3)),
 }
 
+# Mixed element types (BASELINE.json configs[3]): name -> mixed_case arguments
+MIXED_CASES = {
+    'mixed_quad_tri_p3': ('quad+tri', (4, 3), dict(order=3, rsolver='hllc')),
+    'mixed_hex_pri_p2': ('hex+pri', (3, 2, 2), dict(order=2, beta=0.0)),
+    'mixed_all_p3': ('hex+pri+pyr+tet', (4, 2, 2), dict(order=3)),
+}
+
+
+def cat_fields(arrs):
+    """One array per case: the field itself for a single element type,
+    the element types' fields flattened one after the other otherwise."""
+    return arrs[0] if len(arrs) == 1 else np.concatenate(
+        [a.ravel() for a in arrs])
+
+
 OPMAT_SHAPES = [('quad', 3, 'gauss-legendre'), ('hex', 2, 'gauss-legendre'),
                 ('hex', 3, 'gauss-legendre'), ('hex', 4, 'gauss-legendre'),
                 ('hex', 4, 'gauss-legendre-lobatto'),
@@ -200,6 +215,10 @@ def ref_host_case(name):
         system, n, bcs, kw = BC_CASES[name]
         _, box, txt = cases.box_case(system, n, bcs, **kw)
         parts = (1,)*box.ndims
+    elif name in MIXED_CASES:
+        pattern, n, kw = MIXED_CASES[name]
+        _, box, txt = cases.mixed_case(pattern, n, **kw)
+        parts = (1,)*box.ndims
     else:
         case, n, kw, parts, beopts = HOST_CASES[name]
         txt = cfg_text(case, kw, beopts)
@@ -252,8 +271,8 @@ def ref_host_case(name):
             out[f'r{r}_view{i}'] = a
         for i, a in enumerate(consts[r]):
             out[f'r{r}_const{i}'] = a
-        out[f'r{r}_ics'] = s.ele_scal_upts(0)[0]
-        out[f'r{r}_rhs'] = s.ele_scal_upts(1)[0]
+        out[f'r{r}_ics'] = cat_fields(s.ele_scal_upts(0))
+        out[f'r{r}_rhs'] = cat_fields(s.ele_scal_upts(1))
 
     return out
 
@@ -470,15 +489,107 @@ def ref_intg_case(name):
     return out
 
 
+# Element types whose bases and point sets the host mirror does not
+# construct itself: everything pyfr_b200/host needs of a shape, tabulated
+# from the reference's shapes.py / polys.py / quadrules at the point sets of
+# BASELINE.json configs[3].  Lives inside the
+# package because the GPU box has no /root/reference.
+TAB_SHAPES = [(et, p) for et in ('tri', 'tet', 'pri', 'pyr')
+              for p in (1, 2, 3)]
+
+TAB_POINTS = {
+    'tri': 'williams-shunn', 'tet': 'shunn-ham',
+    'pri': 'williams-shunn~gauss-legendre', 'pyr': 'gauss-legendre',
+    'line': 'gauss-legendre', 'quad': 'gauss-legendre',
+}
+
+
+def ref_tabulated_shapes():
+    from pyfr.inifile import Inifile
+    from pyfr.quadrules import get_quadrule
+    from pyfr.shapes import BaseShape
+    from pyfr.util import subclass_where
+
+    out = {}
+    for et, order in TAB_SHAPES:
+        cfg = Inifile(
+            f'[solver]\norder = {order}\n' +
+            ''.join(f'[solver-elements-{k}]\nsoln-pts = {v}\n'
+                    f'[solver-interfaces-{k}]\nflux-pts = {v}\n'
+                    for k, v in TAB_POINTS.items())
+        )
+        scls = subclass_where(BaseShape, name=et)
+        nverts = len(scls.std_ele(1))
+        sh = scls(nverts, cfg)
+        pre = f'{et}_p{order}_'
+
+        named = {'upts': sh.upts, 'fpts': sh.fpts, 'mpts': sh.mpts,
+                 'linspts': sh.linspts}
+        for n, pts in named.items():
+            pts = np.asarray(pts, dtype=float)
+            out[pre + n] = pts
+            out[pre + f'sbasis@{n}'] = sh.sbasis.nodal_basis_at(pts)
+            out[pre + f'mbasis@{n}'] = sh.mbasis.nodal_basis_at(pts)
+        J = sh.mbasis.jac_nodal_basis_at(sh.mpts)       # (nd, nbasis, npts)
+        out[pre + 'mbasis_deriv@mpts'] = np.array([Jd.T for Jd in J])
+
+        rname = cfg.get(f'solver-elements-{et}', 'soln-pts')
+        out[pre + 'upts_wts'] = get_quadrule(et, rname, sh.nupts).wts
+        out[pre + 'norm_fpts'] = sh.norm_fpts
+        out[pre + 'nfacefpts'] = np.array(sh.nfacefpts)
+        out[pre + 'facefpts'] = np.concatenate(
+            [np.asarray(f) for f in sh.facefpts])
+        out[pre + 'jac_exprs'] = np.array(sh.jac_exprs)
+        for m in ('m0', 'm1', 'm2', 'm3', 'm4', 'm6'):
+            out[pre + m] = getattr(sh, m)
+
+        # Vertices on each face (face pairing of linear meshes)
+        fverts, counts = [], []
+        fc = {'line': [(-1,), (1,)], 'quad': [(-1, -1), (1, -1), (-1, 1),
+                                              (1, 1)],
+              'tri': [(-1, -1), (1, -1), (-1, 1)]}
+        lin = np.asarray(sh.linspts, dtype=float)
+        for ftype, proj, _ in scls.faces:
+            ids = [int(np.argmin(np.abs(lin - np.array(proj(*c),
+                                                       dtype=float)).sum(1)))
+                   for c in fc[ftype]]
+            assert all(np.allclose(lin[i], proj(*c))
+                       for i, c in zip(ids, fc[ftype]))
+            fverts += ids
+            counts.append(len(ids))
+        out[pre + 'faceverts'] = np.array(fverts)
+        out[pre + 'nfaceverts'] = np.array(counts)
+
+    return out
+
+
 def main():
     rh.install_stubs()
 
-    for name in INTG_CASES:
-        np.savez_compressed(os.path.join(HERE, f'intg_{name}.npz'),
-                            **ref_intg_case(name))
-        print(f'intg_{name}.npz written')
+    if sys.argv[1:] in ([], ['--shapes']):
+        path = os.path.join(ROOT, 'pyfr_b200', 'host', 'data',
+                            'tabshapes.npz')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez_compressed(path, **ref_tabulated_shapes())
+        print('pyfr_b200/host/data/tabshapes.npz written')
 
-    if sys.argv[1:] == ['--intg']:
+        if sys.argv[1:]:
+            return
+
+    if sys.argv[1:] in ([], ['--intg']):
+        for name in INTG_CASES:
+            np.savez_compressed(os.path.join(HERE, f'intg_{name}.npz'),
+                                **ref_intg_case(name))
+            print(f'intg_{name}.npz written')
+
+        if sys.argv[1:]:
+            return
+
+    if sys.argv[1:] == ['--mixed']:
+        for name in MIXED_CASES:
+            np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
+                                **ref_host_case(name))
+            print(f'host_{name}.npz written')
         return
 
     for name in CONN_CASES:
@@ -489,7 +600,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'opmats.npz'), **ref_opmats())
     print('opmats.npz written')
 
-    for name in list(HOST_CASES) + list(BC_CASES):
+    for name in list(HOST_CASES) + list(BC_CASES) + list(MIXED_CASES):
         np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
                             **ref_host_case(name))
         print(f'host_{name}.npz written')

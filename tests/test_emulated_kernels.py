@@ -441,3 +441,39 @@ def test_standalone_driver_cfl(emulated, capsys):
 
     assert float(rows[-1][1]) == pytest.approx(0.04)
     assert int(rows[-1][0]) >= 2 and 'accepted' in out[-1]
+
+
+def _mixed_outs(pattern, n, kw, b200):
+    outs = []
+    for which in ('oracle', 'oracle-ext', 'b200'):
+        cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+        if which == 'b200':
+            sysm = b200(cfg, box)
+        else:
+            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
+            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.0, 0, 1)
+        if which == 'b200':
+            sysm.backend.wait()
+        outs.append(sysm.ele_scal_upts(1))
+
+    return outs, sysm
+
+
+@pytest.mark.parametrize('pattern,n,kw,nfused', [
+    ('quad+tri', (4, 3), dict(order=3, rsolver='hllc'), 2),
+    ('hex+pri', (3, 2, 2), dict(order=2, beta=0.0), 2),
+    ('hex+pri+pyr+tet', (4, 2, 2), dict(order=3), 2),
+], ids=str)
+def test_mixed_element_types(emulated, pattern, n, kw, nfused):
+    """BASELINE configs[3] through the host mirror: several element types
+    in one mesh, mixed-face interface views, dense operators (tabulated
+    shapes, pyfr_b200/host/data)."""
+    (ref, ext, out), sysm = _mixed_outs(pattern, n, kw, _b200)
+
+    assert len(out) == len(pattern.split('+'))
+    for o, r, e in zip(out, ref, ext):
+        assert_parity(o, r, e, 1e-12)
+
+    kinds = _kinds(sysm)
+    assert kinds.count('fluxdiv') + kinds.count('gradflux') == nfused

@@ -200,3 +200,33 @@ def test_wavespeed_and_cfl_controller_match_oracle(built, case, n, kw):
     assert len(do) >= 3
     np.testing.assert_allclose(db, do, rtol=1e-12)
     assert rel_err(sb, so) < 1e-11
+
+
+MIXED_CASES = [
+    ('quad+tri', (12, 9), dict(order=3, rsolver='hllc')),
+    ('hex+pri', (4, 4, 3), dict(order=2, beta=0.0)),
+    ('hex+pri+pyr+tet', (4, 4, 3), dict(order=3)),
+]
+
+
+@pytest.mark.parametrize('pattern,n,kw', MIXED_CASES, ids=str)
+def test_mixed_element_types_match_oracle(built, pattern, n, kw):
+    """BASELINE configs[3]: several element types in one mesh -- dense
+    simplex / pyramid operators, mixed-face interface views."""
+    outs = []
+    for which in ('oracle', 'oracle-ext', 'b200'):
+        cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+        if which == 'b200':
+            sysm = _b200(cfg, box)
+        else:
+            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
+            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.0, 0, 1)
+        if which == 'b200':
+            sysm.backend.wait()
+        outs.append(sysm.ele_scal_upts(1))
+
+    ref, ext, out = outs
+    assert len(out) == len(pattern.split('+'))
+    for o, r, e in zip(out, ref, ext):
+        assert_parity(o, r, e, TOL64)

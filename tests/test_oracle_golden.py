@@ -84,6 +84,10 @@ def _host_case(name, extended=False):
         system, n, bcs, kw = mg.BC_CASES[name]
         parts, beopts = (1,), {}
         mk = lambda: cases.box_case(system, n, bcs, **kw)[:2]
+    elif name in mg.MIXED_CASES:
+        pattern, n, kw = mg.MIXED_CASES[name]
+        parts, beopts = (1,), {}
+        mk = lambda: cases.mixed_case(pattern, n, **kw)[:2]
     else:
         case, n, kw, parts, beopts = mg.HOST_CASES[name]
         mk = lambda: cases.make(case, n, **kw)
@@ -116,13 +120,14 @@ def _host_case(name, extended=False):
         keys, arrs = mg.trace_digest(tr)
         out[f'r{r}_viewkeys'] = np.array(keys)
         out[f'r{r}_consts'] = consts[r]
-        out[f'r{r}_ics'] = s.ele_scal_upts(0)[0]
-        out[f'r{r}_rhs'] = s.ele_scal_upts(1)[0]
+        out[f'r{r}_ics'] = mg.cat_fields(s.ele_scal_upts(0))
+        out[f'r{r}_rhs'] = mg.cat_fields(s.ele_scal_upts(1))
 
     return out, nparts
 
 
-@pytest.mark.parametrize('name', list(mg.HOST_CASES) + list(mg.BC_CASES))
+@pytest.mark.parametrize('name', list(mg.HOST_CASES) + list(mg.BC_CASES)
+                         + list(mg.MIXED_CASES))
 def test_host_mirror_matches_reference_host(name):
     gold = np.load(os.path.join(GOLDEN, f'host_{name}.npz'))
     out, nparts = _host_case(name)
@@ -161,7 +166,7 @@ def test_host_mirror_matches_reference_host(name):
 @pytest.mark.skipif(not mg.rh.available(), reason='needs /root/reference')
 @pytest.mark.parametrize('name', ['tgv_p2_beta0_2parts',
                                   'vortex_p3_hllc_2parts',
-                                  'bc_ns_wall_farfield'])
+                                  'bc_ns_wall_farfield', 'mixed_all_p3'])
 def test_fixtures_are_current(name):
     """Where the reference is present, regenerate a fixture from it and
     check the committed copy is what the reference produces today."""
