@@ -42,6 +42,11 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--n', type=int, default=64, help='hexes per direction '
                     'per GPU')
+    ap.add_argument('--case', default='tgv',
+                    choices=['tgv', 'hex+pri', 'hex+pri+pyr+tet'],
+                    help='tgv: the headline workload; the others time '
+                    'BASELINE configs[3]-style mixed meshes of --n^3 cells on '
+                    'one GPU (device-resident figure only)')
     ap.add_argument('--order', type=int, default=4)
     ap.add_argument('--precision', default='double')
     ap.add_argument('--rsolver', default='rusanov')
@@ -209,6 +214,17 @@ def reference_arm(args):
 
 
 def workload_config(args):
+    if args.case != 'tgv':
+        return {
+            'workload': f'compressible Navier-Stokes, {args.n}^3 periodic '
+                        f'cells of mixed type ({args.case}), p={args.order}, '
+                        f'{"fp64" if args.precision == "double" else "fp32"}'
+                        f', {args.rsolver}, one RHS evaluation per step',
+            'mesh': f'{args.n}^3 cells, one partition',
+            'l2': 'inputs larger than L2 for n >= 32',
+            'parallelism': 'single GPU'
+        }
+
     return {
         'workload': f'TGV compressible Navier-Stokes, {args.n}^3 periodic '
                     f'hexes per GPU, p={args.order}, '
@@ -246,9 +262,18 @@ def main():
 
     # Mesh: `world` bricks of n^3 hexes
     parts = bricks(world)
-    cfg, box = cases.make('tgv', tuple(args.n*p for p in parts),
-                          order=args.order, precision=args.precision,
-                          rsolver=args.rsolver)
+    if args.case == 'tgv':
+        cfg, box = cases.make('tgv', tuple(args.n*p for p in parts),
+                              order=args.order, precision=args.precision,
+                              rsolver=args.rsolver)
+    else:
+        if world > 1:
+            raise SystemExit('mixed-element cases run on one GPU')
+        args.no_e2e = args.no_cpu = True
+        cfg, box, _ = cases.mixed_case(args.case, (args.n,)*3,
+                                       order=args.order,
+                                       precision=args.precision,
+                                       rsolver=args.rsolver)
     cfg.set('backend-b200', 'device-id', lrank)
     if args.no_graphs:
         cfg.set('backend-b200', 'graphs', 'false')
@@ -384,7 +409,8 @@ def main():
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
             tj = json.load(f)
-        if tj['workload'] == (f'tgv n={args.n} order={args.order} '
+        if args.case == 'tgv' and \
+           tj['workload'] == (f'tgv n={args.n} order={args.order} '
                               f'{args.precision} {args.rsolver}'):
             traffic = {k: v['dram_bytes'] for k, v in tj['kernels'].items()}
     except (OSError, KeyError, ValueError):
@@ -412,7 +438,7 @@ def main():
         'achieved_gbs_3pass': value*balg,
         'frac_of_hbm_3pass': value*balg/peak_gbs,
         'peak_source': peak_src
-    }
+    } if args.case == 'tgv' else None
 
     # ---- end to end: host buffers in, host buffers out ---------------------
     # Every step uploads its solution from pinned host memory, evaluates

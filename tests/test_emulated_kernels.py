@@ -477,3 +477,23 @@ def test_mixed_element_types(emulated, pattern, n, kw, nfused):
 
     kinds = _kinds(sysm)
     assert kinds.count('fluxdiv') + kinds.count('gradflux') == nfused
+
+
+def test_bench_script_mixed_case(emulated, monkeypatch, capsys):
+    """bench.py --case hex+pri: the configs[3]-style diagnostic mode."""
+    import json
+    import runpy
+
+    monkeypatch.setattr(emu.EmuRuntime, 'elapsed_ms', lambda s, a, b: 1.0)
+    monkeypatch.setattr(sys, 'argv', [
+        'bench.py', '--case', 'hex+pri', '--n', '2', '--order', '2',
+        '--steps', '2', '--warmup', '1', '--no-clocks', '--no-graphs'
+    ])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, 'bench.py'), run_name='__main__')
+
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert 'hex+pri' in line['config']['workload']
+    assert line['value'] > 0 and line['rhs_model'] is None
+    # 4 hexes (27 points) and 8 prisms (18 points), 5 variables
+    assert line['dof'] == (4*27 + 8*18)*5
