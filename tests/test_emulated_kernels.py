@@ -497,3 +497,23 @@ def test_bench_script_mixed_case(emulated, monkeypatch, capsys):
     assert line['value'] > 0 and line['rhs_model'] is None
     # 4 hexes (27 points) and 8 prisms (18 points), 5 variables
     assert line['dof'] == (4*27 + 8*18)*5
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, beta=0.0, rsolver='hllc')),
+    ('vortex', 5, dict(order=3)),
+], ids=str)
+def test_int64_index_model(emulated, case, n, kw):
+    """``[backend] memory-model = large``: 64-bit view / packing indices
+    (pyfr/backends/base/backend.py:60-68)."""
+    cfg, box = cases.make(case, n, **kw)
+    cfg.set('backend', 'memory-model', 'large')
+    sysm = _b200(cfg, box)
+    assert sysm.backend.ixdtype == np.int64
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+    assert_parity(out, ref[0], ext[0], 1e-12)
