@@ -55,6 +55,10 @@ class StubComm:
         if self.size != 1:
             raise NotImplementedError('multi-rank reference integrator')
 
+    def Reduce(self, sendbuf, recvbuf, op=None, root=0):
+        if self.size != 1:
+            raise NotImplementedError('multi-rank reference plugins')
+
     def exscan(self, v):
         return None                     # rank 0's result is undefined in MPI
 

@@ -241,3 +241,79 @@ def test_reference_integrators_execute_on_b200_backend(built):
         assert (ao, ro) == (ab, rb) and int(ao) >= 2
 
     assert int(rows['pi'][3]) >= 1                # a rejected step happened
+
+
+_plugin_script = r'''
+import os, sys, tempfile
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm, make_backend
+rh.install_stubs()
+rh.set_rank(LocalComm(0, 1).peer(0))
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+import pyfr.backends.base as rbase
+from pyfr.inifile import Inifile
+from pyfr.integrators import get_integrator
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+from pyfr_b200.host.integrator import TGV_EXPRS
+
+_, box = cases.make('tgv', (3, 2, 2), order=2, warp=0.1)
+tmp = tempfile.mkdtemp()
+rows = {}
+for which in ('oracle', 'b200'):
+    csv = os.path.join(tmp, which + '.csv')
+    txt = cases.tgv_cfg(order=2) + f"""
+[backend-b200]
+graphs = false
+[solver-time-integrator]
+formulation = explicit
+scheme = rk4
+controller = none
+tstart = 0
+tend = 0.006
+dt = 0.002
+[soln-plugin-integrate]
+nsteps = 1
+file = {csv}
+header = true
+int-ke = {TGV_EXPRS[0]}
+int-ens = {TGV_EXPRS[1]}
+"""
+    cfg = Inifile(txt)
+    be = (B200Backend(cfg) if which == 'b200' else
+          make_backend(rbase, name='oracle-ref')(cfg))
+    intg = get_integrator(be, NavierStokesSystem,
+                          rh.ref_mesh(box.local_mesh()), None, cfg)
+    intg.advance_to(0.006)
+    rows[which] = np.loadtxt(csv, delimiter=',', skiprows=1)
+
+print('RESULT', rows['oracle'].shape[0],
+      np.abs(rows['b200']/rows['oracle'] - 1)[:, 1:].max(),
+      rows['oracle'][0, 1]/(2*np.pi)**3)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_reference_integrate_plugin_on_b200_backend(built):
+    """The reference's ``[soln-plugin-integrate]`` (``BackendFieldReducer``,
+    ``compute_grads`` graph, ``fieldeval`` kernel) inside the reference's
+    RK4 integrator, on B200Backend: the CSV of Taylor-Green kinetic energy
+    and enstrophy equals the oracle backend's to round-off."""
+    res = subprocess.run([sys.executable, '-c',
+                          _plugin_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+    _, nrows, err, ke0 = [l for l in res.stdout.splitlines()
+                          if l.startswith('RESULT')][0].split()
+    assert int(nrows) == 4 and float(err) < 1e-13
+    assert abs(float(ke0) - 0.125) < 5e-3
