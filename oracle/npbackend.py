@@ -519,18 +519,21 @@ def _evalsrcmacros(be, tplargs, dims, extrns={}, ploc=None, u=None, **kw):
 
 def _fieldeval(be, tplargs, dims, extrns={}, u=None, gradu=None, ploc=None,
                wts=None, out=None, **kw):
-    """pyfr/plugins/kernels/fieldeval.mako (sum reduction) with
+    """pyfr/plugins/kernels/fieldeval.mako (sum / min / max over the
+    points of an element, optional weights or mask, coordinates) with
     con_to_pri / grad_con_to_pri of pyfr/solvers/euler/kernels/eos.mako."""
     nd, nv = tplargs['ndims'], tplargs['nvars']
     gm1 = tplargs['c']['gamma'] - 1
-    exprs = tplargs['exprs']
+    exprs, rop = tplargs['exprs'], tplargs['reduceop']
+    has_wts = bool(tplargs.get('has_wts', wts is not None))
 
-    if tplargs['reduceop'] != 'sum' or ploc is not None:
-        raise NotImplementedError('oracle fieldeval: weighted sums only')
+    if tplargs.get('use_views') or rop not in ('sum', 'min', 'max'):
+        raise NotImplementedError('oracle fieldeval over views')
 
     fns = {'sqrt': np.sqrt, 'exp': np.exp, 'log': np.log, 'sin': np.sin,
            'cos': np.cos, 'tan': np.tan, 'tanh': np.tanh, 'pow': np.power,
-           'fabs': np.abs, 'fmin': np.minimum, 'fmax': np.maximum}
+           'fabs': np.abs, 'abs': np.abs, 'fmin': np.minimum,
+           'fmax': np.maximum}
 
     def run(t=0.0):
         cons = list(_stacked(u, nv))
@@ -557,9 +560,23 @@ def _fieldeval(be, tplargs, dims, extrns={}, u=None, gradu=None, ploc=None,
                 gp[nv - 1][d] = gm1*(gc[d][nv - 1] - 0.5*term)
             env['grad_pri'] = gp
 
-        w, o = _plain(wts), _plain(out)
+        if ploc is not None:
+            env['ploc'] = list(_stacked(ploc, nd))
+
+        o = _plain(out)
+        w = _plain(wts) if has_wts else None
+        fmax = np.finfo(o.dtype).max
+
         for j, e in enumerate(exprs):
-            o[:, j] = (w*eval(e, {'__builtins__': {}}, env)).sum(axis=1)
+            val = eval(e, {'__builtins__': {}}, env) + 0*cons[0]
+            if rop == 'sum':
+                o[:, j] = (w*val).sum(axis=1)
+            elif rop == 'max':
+                val = np.where(w > 0, val, -fmax) if has_wts else val
+                o[:, j] = val.max(axis=1)
+            else:
+                val = np.where(w > 0, val, fmax) if has_wts else val
+                o[:, j] = val.min(axis=1)
 
     return be.kernel_cls(run, rtnames=('t',))
 

@@ -430,39 +430,61 @@ def compile_expr(expr, privars, ndims):
 class FieldIntegrator:
     """Volume integrals of expressions, summed on the device per element."""
 
-    def __init__(self, system, cfg, exprs):
+    def __init__(self, system, cfg, exprs, reduceop='sum'):
         self.system, self.backend = system, system.backend
         be = self.backend
 
         _, _, privars, ndims, nvars, _, _ = system.ele_quad[0]
-        self.nexprs = len(exprs)
+        self.nexprs, self.reduceop = len(exprs), reduceop
         self.has_grads = bool(re.search(r'\bgrad_', ' '.join(exprs)))
-
-        if re.search(r'\b[xyz]\b', ' '.join(exprs)):
-            raise NotImplementedError('coordinate-dependent integrands')
+        self.has_ploc = bool(re.search(r'\b[xyz]\b', ' '.join(exprs)))
 
         be.pointwise.register('pyfr.plugins.kernels.fieldeval')
 
         self._tplargs = {
             'ndims': ndims, 'nvars': nvars, 'nexprs': self.nexprs,
             'exprs': [compile_expr(e, privars, ndims) for e in exprs],
-            'reduceop': 'sum', 'c': cfg.items_as('constants', float),
+            'reduceop': reduceop, 'c': cfg.items_as('constants', float),
             'has_grads': self.has_grads, 'use_views': False,
-            'has_wts': True,
+            'has_wts': reduceop == 'sum',
             'eos_mod': 'pyfr.solvers.euler.kernels.eos'
         }
 
         self._edata = []
-        for wts, rcpdjac, _, _, _, nupts, neles in system.ele_quad:
-            w = be.const_matrix(wts[:, None]/rcpdjac, tags={'align'})
+        for i, (wts, rcpdjac, _, _, _, nupts, neles) in \
+                enumerate(system.ele_quad):
+            w = (be.const_matrix(wts[:, None]/rcpdjac, tags={'align'})
+                 if reduceop == 'sum' else None)
+            ploc = (be.const_matrix(system.ele_ploc_upts[i](),
+                                    tags={'align'})
+                    if self.has_ploc else None)
             out = be.matrix((self.nexprs, neles), tags={'align'})
-            self._edata.append((w, out, nupts, neles))
+            self._edata.append((w, out, nupts, neles, ploc))
 
         be.commit()
         self._kerns = {}
 
     def total_volume(self):
-        return sum(float(w.get().sum()) for w, *_ in self._edata)
+        return sum(float((wts[:, None]/rcpdjac).sum())
+                   for wts, rcpdjac, *_ in self.system.ele_quad)
+
+    def kernels(self, uidx):
+        be, sysm = self.backend, self.system
+
+        if uidx not in self._kerns:
+            self._kerns[uidx] = [
+                be.pointwise.fieldeval(
+                    tplargs=self._tplargs, dims=[nupts, neles],
+                    u=sysm.ele_banks[i][uidx], out=out,
+                    **({'gradu': sysm.eles_vect_upts[i]}
+                       if self.has_grads else {}),
+                    **({'wts': w} if w is not None else {}),
+                    **({'ploc': ploc} if ploc is not None else {})
+                )
+                for i, (w, out, nupts, neles, ploc) in enumerate(self._edata)
+            ]
+
+        return self._kerns[uidx]
 
     def __call__(self, t, uidx):
         be, sysm = self.backend, self.system
@@ -470,25 +492,21 @@ class FieldIntegrator:
         if self.has_grads:
             sysm.compute_grads(t, uidx)
 
-        if uidx not in self._kerns:
-            self._kerns[uidx] = [
-                be.pointwise.fieldeval(
-                    tplargs=self._tplargs, dims=[nupts, neles],
-                    u=sysm.ele_banks[i][uidx], out=out, wts=w,
-                    **({'gradu': sysm.eles_vect_upts[i]}
-                       if self.has_grads else {})
-                )
-                for i, (w, out, nupts, neles) in enumerate(self._edata)
-            ]
-
-        for k in self._kerns[uidx]:
+        for k in self.kernels(uidx):
             if hasattr(k, 'bind'):
                 k.bind(t=t)
-        be.run_kernels(self._kerns[uidx])
+        be.run_kernels(self.kernels(uidx))
 
-        res = np.zeros(self.nexprs)
+        ident = {'sum': 0.0, 'min': np.inf, 'max': -np.inf}[self.reduceop]
+        res = np.full(self.nexprs, ident)
         for w, out, *_ in self._edata:
-            res += out.get().sum(axis=1)
+            o = out.get()
+            if self.reduceop == 'sum':
+                res += o.sum(axis=1)
+            elif self.reduceop == 'max':
+                res = np.maximum(res, o.max(axis=1))
+            else:
+                res = np.minimum(res, o.min(axis=1))
 
         return res
 

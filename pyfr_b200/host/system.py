@@ -146,6 +146,17 @@ class BaseSystem:
                           e.privars, e.ndims, e.nvars, e.nupts, e.neles)
                          for e in self.ele_map.values()]
 
+        # Physical solution-point locations on demand (coordinate-dependent
+        # integrands); only the vertices and the small interpolation
+        # operator outlive the element objects
+        def ploc_getter(e):
+            op, x = e.basis.sbasis_at(e.basis.upts), e.eles
+            shp = (len(op), e.neles, e.ndims)
+            return lambda: (op @ x.reshape(len(x), -1)).reshape(
+                shp).swapaxes(1, 2)
+
+        self.ele_ploc_upts = [ploc_getter(e) for e in self.ele_map.values()]
+
         del self.ele_map, self._int_inters, self._mpi_inters
         del self._bc_inters
         self._graphs = {}

@@ -14,6 +14,8 @@ Grids are sized in whole blocks; one launch covers every element of the
 region.
 """
 
+import re
+
 from pyfr_b200.kernels import physics as ph
 
 # Thread <-> (block, point, element-in-block) decomposition shared by the
@@ -219,11 +221,13 @@ negdivconf({', '.join(args)})
 
 
 def fieldeval_source(be, tplargs, npts):
-    """``fieldeval`` (``pyfr/plugins/kernels/fieldeval.mako``, sum
-    reduction): per element, the weighted sum over its points of each
-    expression in the primitive variables (``pri[i]``), their physical
-    gradients (``grad_pri[i][d]``, ``con_to_pri``/``grad_con_to_pri`` of
-    ``pyfr/solvers/euler/kernels/eos.mako:17-45``) and the time ``t``.
+    """``fieldeval`` (``pyfr/plugins/kernels/fieldeval.mako``): per
+    element, the weighted sum -- or the minimum / maximum, optionally under
+    a mask -- over its points of each expression in the primitive
+    variables (``pri[i]``), their physical gradients (``grad_pri[i][d]``,
+    ``con_to_pri``/``grad_con_to_pri`` of
+    ``pyfr/solvers/euler/kernels/eos.mako:17-45``), the coordinates
+    (``ploc[d]``) and the time ``t``.
 
     The expressions arrive as C text (the reference compiles them the same
     way, ``pyfr/plugins/fieldeval.py:12-22``) and are pasted into the
@@ -232,9 +236,23 @@ def fieldeval_source(be, tplargs, npts):
     nd, nv = tplargs['ndims'], tplargs['nvars']
     exprs, grads = tplargs['exprs'], tplargs['has_grads']
 
-    if tplargs['reduceop'] != 'sum' or tplargs.get('use_views'):
-        raise NotImplementedError('fieldeval: only the sum reduction over '
-                                  'element matrices is on the b200 path')
+    # The integrate plugin wraps L-p integrands in abs(): make sure the
+    # floating-point function is the one that is called
+    exprs = [re.sub(r'\babs\(', 'fabs(', e) for e in exprs]
+
+    rop, has_wts = tplargs['reduceop'], tplargs.get('has_wts', True)
+    has_ploc = tplargs.get('has_ploc', False)
+
+    if tplargs.get('use_views') or rop not in ('sum', 'min', 'max'):
+        raise NotImplementedError('fieldeval over interface views is not on '
+                                  'the b200 path')
+    if rop == 'sum' and not has_wts:
+        raise ValueError('fieldeval: a sum needs weights')
+
+    fpmax = ('1.7976931348623157e308' if be.fpdtype.__name__ == 'float64'
+             else '3.4028234e38f')
+    init = {'sum': 'FP(0.0)', 'max': f'-FP({fpmax})',
+            'min': f'FP({fpmax})'}[rop]
 
     defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', npts),
             ('NEXPRS', len(exprs)),
@@ -243,9 +261,13 @@ def fieldeval_source(be, tplargs, npts):
     args = ['int neles', 'const fpdtype_t* __restrict__ u', 'long long u_bsz']
     if grads:
         args += ['const fpdtype_t* __restrict__ gradu', 'long long gradu_bsz']
-    args += ['const fpdtype_t* __restrict__ wts', 'long long wts_bsz',
-             'int wts_ld', 'fpdtype_t* __restrict__ out',
-             'long long out_bsz', 'int out_ld', 'fpdtype_t t']
+    if has_ploc:
+        args += ['const fpdtype_t* __restrict__ plocm', 'long long ploc_bsz']
+    if has_wts:
+        args += ['const fpdtype_t* __restrict__ wts', 'long long wts_bsz',
+                 'int wts_ld']
+    args += ['fpdtype_t* __restrict__ out', 'long long out_bsz', 'int out_ld',
+             'fpdtype_t t']
 
     gsrc = r'''
         fpdtype_t grad_pri[NVARS][NDIMS];
@@ -278,8 +300,27 @@ def fieldeval_source(be, tplargs, npts):
         }
 ''' if grads else ''
 
-    esrc = '\n'.join(f'        acc[{j}] += w*({e});'
-                     for j, e in enumerate(exprs))
+    if rop == 'sum':
+        esrc = '\n'.join(f'        acc[{j}] += w*({e});'
+                         for j, e in enumerate(exprs))
+    else:
+        # the weights of a min / max are a mask: points with w <= 0 drop out
+        fn = 'fmax' if rop == 'max' else 'fmin'
+        esrc = '\n'.join(
+            f'        acc[{j}] = {fn}(acc[{j}], '
+            + (f'(w > 0) ? ({e}) : {init}' if has_wts else f'({e})') + ');'
+            for j, e in enumerate(exprs)
+        )
+
+    psrc = '''
+        fpdtype_t ploc[NDIMS];
+        UNROLL for (int d = 0; d < NDIMS; d++)
+            ploc[d] = __ldg(plocm + blk*ploc_bsz
+                            + (long long) p*(NDIMS*C_SUB) + COFF(e, d, NDIMS));
+''' if has_ploc else ''
+
+    wsrc = ('const fpdtype_t w = __ldg(wts + blk*wts_bsz + '
+            '(long long) p*wts_ld + e);' if has_wts else '')
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz, defs)}
@@ -295,7 +336,9 @@ fieldeval({', '.join(args)})
     if (blk*C_SUB + e >= neles)
         return;
 
-    fpdtype_t acc[NEXPRS] = {{}};
+    fpdtype_t acc[NEXPRS];
+    UNROLL for (int j = 0; j < NEXPRS; j++)
+        acc[j] = {init};
 
     for (int p = 0; p < NPTS; p++)
     {{
@@ -312,8 +355,8 @@ fieldeval({', '.join(args)})
             ke += cons[i + 1]*cons[i + 1];
         }}
         pri[NVARS - 1] = C_GM1*(cons[NVARS - 1] - FP(0.5)*invrho*ke);
-{gsrc}
-        const fpdtype_t w = __ldg(wts + blk*wts_bsz + (long long) p*wts_ld + e);
+{gsrc}{psrc}
+        {wsrc}
 {esrc}
     }}
 

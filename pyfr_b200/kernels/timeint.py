@@ -67,6 +67,7 @@ def reduction_source(be, rop, exprs, vnames, svars, pvars, nvars):
         raise ValueError('Invalid reduction operator')
 
     nex = len(exprs)
+    exprs = [re.sub(r'\babs\(', 'fabs(', x) for x in exprs]
     vre = '|'.join(map(re.escape, vnames))
     exprs = [re.sub(rf'\b({vre})\b', r'\1[i]', x) for x in exprs]
     if pvars:

@@ -286,6 +286,13 @@ file = {csv}
 header = true
 int-ke = {TGV_EXPRS[0]}
 int-ens = {TGV_EXPRS[1]}
+[soln-plugin-integrate-linf]
+nsteps = 1
+file = {csv[:-4]}_linf.csv
+header = true
+norm = inf
+int-q = rho*x*y - p*cos(z)
+int-g = grad_u_y + 0.1*t
 """
     cfg = Inifile(txt)
     be = (B200Backend(cfg) if which == 'b200' else
@@ -293,7 +300,10 @@ int-ens = {TGV_EXPRS[1]}
     intg = get_integrator(be, NavierStokesSystem,
                           rh.ref_mesh(box.local_mesh()), None, cfg)
     intg.advance_to(0.006)
-    rows[which] = np.loadtxt(csv, delimiter=',', skiprows=1)
+    rows[which] = np.hstack([
+        np.loadtxt(csv, delimiter=',', skiprows=1),
+        np.loadtxt(csv[:-4] + '_linf.csv', delimiter=',', skiprows=1)[:, 1:]
+    ])
 
 print('RESULT', rows['oracle'].shape[0],
       np.abs(rows['b200']/rows['oracle'] - 1)[:, 1:].max(),
@@ -315,5 +325,7 @@ def test_reference_integrate_plugin_on_b200_backend(built):
 
     _, nrows, err, ke0 = [l for l in res.stdout.splitlines()
                           if l.startswith('RESULT')][0].split()
+    # columns: t, two volume integrals, two L-inf norms (max reduction,
+    # coordinate- and time-dependent expressions)
     assert int(nrows) == 4 and float(err) < 1e-13
     assert abs(float(ke0) - 0.125) < 5e-3
