@@ -48,4 +48,25 @@ for case, n, kw in runs:
     s.rhs(0.0, 0, 1)
     s.rhs(0.0, 0, 1)
 
+if '--drop-barrier' not in sys.argv:
+    # Mixed element types: fused kernels over triangle / prism operators
+    for pattern, n, kw in [('quad+tri', (4, 3), dict(order=3)),
+                           ('hex+pri', (3, 2, 2), dict(order=2))]:
+        cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+        cfg.set('backend-b200', 'graphs', 'false')
+        s = get_system(B200Backend(cfg), box.local_mesh(), cfg, 2)
+        s.rhs(0.0, 0, 1)
+
+    # Shared-memory tree reduction + atomics (error norm), rkvdh2 stages
+    from pyfr_b200.host.integrator import PIController, RK45Stepper
+
+    cfg, box = cases.make('vortex', (4, 4), order=3)
+    cfg.set('backend-b200', 'graphs', 'false')
+    for k, v in (('dt', 0.05), ('atol', 1e-6), ('rtol', 1e-6)):
+        cfg.set('solver-time-integrator', k, v)
+    s = get_system(B200Backend(cfg), box.local_mesh(), cfg, 4)
+    pi = PIController(RK45Stepper(s, errest=True), cfg,
+                      ['rho', 'rhou', 'rhov', 'E'])
+    pi.advance_to(0.06)
+
 print('PROBE DONE')
