@@ -72,6 +72,9 @@ class B200Backend(base.BaseBackend):
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
         self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
         self.euler_fusion = cfg.getbool(sect, 'euler-fusion', True)
+        # Runge-Kutta stage update in the epilogue of the last RHS kernel
+        # (only when the caller groups an rkvdh2 kernel with the RHS)
+        self.rk_fusion = cfg.getbool(sect, 'rk-fusion', True)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

@@ -256,10 +256,51 @@ def fuse_gradflux(be, kerns, subs):
     return out
 
 
+def _rk_tail(be, kerns, fout):
+    """Splits an optional trailing ``rkvdh2`` kernel off a group: returns
+    (remaining kernels, rk template arguments or None, extra kernel
+    arguments, extra matrices, rk traffic in bank passes).  The stage
+    update must consume the RHS bank ``fout`` as its ``r2``."""
+    if not kerns or getattr(kerns[-1], 'kind', None) != 'rkvdh2':
+        return kerns, None, [], [], 0
+    if not be.rk_fusion:
+        raise kfused.NotFusable('rk fusion disabled')
+
+    i = kerns[-1].info
+    tpl, r1 = i['tplargs'], i['r1']
+    if not _same(i['r2'], fout) or r1.traits != fout.traits:
+        raise kfused.NotFusable('rkvdh2 does not follow this RHS')
+
+    regs = [r1] + ([i['rold'], i['rerr']] if tpl['errest'] else [])
+    args = [a for m in regs for a in (('p', m.data), ('l', m.blocksz))]
+    args.append(('d' if be.fpdtype == np.float64 else 'f', 0.0))
+
+    last = tpl['stage'] == tpl['nstages'] - 1
+    passes = 2 + (2 if tpl['errest'] else 0) - (1 if last else 0)
+    return kerns[:-1], tpl, args, regs, passes
+
+
+def _bind_dt(k, nargs):
+    """Gives a fused kernel the ``bind(dt=)`` of the rkvdh2 it absorbed."""
+    idt = nargs - 1
+
+    def bind(dt=0.0):
+        if k._vals[idt].value != dt:
+            k.set_arg(idt, dt)
+
+    k.rtnames, k.bind = ('dt',), bind
+
+
 def fuse_tdivtconf_negdivconf(be, kerns, subs):
     """tdivtconf (out += M3 @ scal_fpts) followed by negdivconf."""
     from pyfr_b200.providers import B200Kernel
 
+    if len(kerns) not in (2, 3) or getattr(kerns[0], 'kind', None) != 'mul':
+        return None
+
+    allk = kerns
+    kerns, rk, rkargs, rkmats, rkpasses = _rk_tail(be, kerns,
+                                                   kerns[0].info['out'])
     if len(kerns) != 2:
         return None
 
@@ -282,26 +323,29 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
 
     src, name, meta = kmul.mul_source(
         be, im['A'], LD, im['alpha'], im['beta'], smem_budget=be.smem_budget,
-        rowgroups=be.mul_rowgroups, negdiv_nvars=nv
+        rowgroups=be.mul_rowgroups, negdiv_nvars=nv, rk=rk
     )
     fn = be.pointwise._function(src, name)
     fn.set_smem(meta['smem'])
 
     isz = b.itemsize
-    traffic = ((b.nrow + out.nrow*(2 if im['beta'] else 1))*LD +
-               out.nrow*be.csubsz)*nblocks*isz
+    traffic = ((b.nrow + out.nrow*(2 if im['beta'] else 1) +
+                out.nrow*rkpasses)*LD + out.nrow*be.csubsz)*nblocks*isz
 
+    args = [('i', nblocks), ('p', b.data), ('l', b.blocksz), ('p', out.data),
+            ('l', out.blocksz), ('p', r.data), ('l', r.blocksz)] + rkargs
     k = B200Kernel(
         be, fn, (min(nblocks, be.sm_count), 1, 1), (meta['nthreads'], 1, 1),
-        meta['smem'],
-        [('i', nblocks), ('p', b.data), ('l', b.blocksz), ('p', out.data),
-         ('l', out.blocksz), ('p', r.data), ('l', r.blocksz)],
-        mats=[b, out, r], misc=[meta], traffic=traffic, kind='mul+negdivconf',
-        info=dict(replaces=kerns)
+        meta['smem'], args, mats=[b, out, r] + rkmats, misc=[meta],
+        traffic=traffic,
+        kind='mul+negdivconf+rkvdh2' if rk else 'mul+negdivconf',
+        info=dict(replaces=allk)
     )
 
     # negdivconf carries the (unused here) run-time argument t
     k.rtnames = ()
+    if rk:
+        _bind_dt(k, len(args))
     return [k]
 
 
@@ -310,7 +354,14 @@ def fuse_fluxdiv(be, kerns, subs):
     advection (Euler) system -> ``fluxdiv``."""
     from pyfr_b200.providers import B200Kernel
 
-    if len(kerns) != 4 or not be.euler_fusion:
+    if len(kerns) not in (4, 5) or not be.euler_fusion or \
+       getattr(kerns[1], 'kind', None) != 'mul':
+        return None
+
+    allk = kerns
+    kerns, rk, rkargs, rkmats, rkpasses = _rk_tail(be, kerns,
+                                                   kerns[1].info['out'])
+    if len(kerns) != 4:
         return None
 
     k0, k1, k2, k3 = kerns
@@ -355,7 +406,7 @@ def fuse_fluxdiv(be, kerns, subs):
         pts = ti['upts'].get() if ti['upts'] is not None else None
 
         src, name, meta = keuler.fluxdiv_source(be, ops, ti['tplargs'], pts,
-                                                LD)
+                                                LD, rk=rk)
         fn = be.pointwise._function(src, name)
         fn.set_smem(meta['smem'])
 
@@ -375,13 +426,22 @@ def fuse_fluxdiv(be, kerns, subs):
                      ('p', r.data + b0*r.blocksz*isz), ('l', r.blocksz)]
             geo = [s, r]
 
-        out.append(B200Kernel(
+        if rk:
+            # the stage registers of this region's blocks
+            args += [(c, v + b0*rkmats[i // 2].blocksz*isz) if c == 'p' else
+                     (c, v) for i, (c, v) in enumerate(rkargs)]
+
+        kern = B200Kernel(
             be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
             (meta['nthreads'], 1, 1), meta['smem'], args,
-            mats=[U, C, FOUT, F] + geo, misc=[meta],
-            traffic=meta['words_per_block']*nblocks*isz, kind='fluxdiv',
-            info=dict(replaces=kerns)
-        ))
+            mats=[U, C, FOUT, F] + geo + rkmats, misc=[meta],
+            traffic=(meta['words_per_block'] + rkpasses*nu*LD)*nblocks*isz,
+            kind='fluxdiv+rkvdh2' if rk else 'fluxdiv',
+            info=dict(replaces=allk)
+        )
+        if rk:
+            _bind_dt(kern, len(args))
+        out.append(kern)
 
     return out
 

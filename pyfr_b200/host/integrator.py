@@ -109,8 +109,14 @@ class RKVdH2RStepper:
     a, b, bhat = [], [], []
     stepper_order = None
 
-    def __init__(self, system, tstart=0.0, errest=False):
+    def __init__(self, system, tstart=0.0, errest=False, fused=False):
+        """``fused``: hand each stage's update kernel to the system as a
+        post-RHS kernel, grouped with the last RHS kernel, so that the
+        backend may apply it in that kernel's epilogue (SURVEY.md section
+        8f, rank 1) -- the RHS value then never makes the round trip
+        through memory.  Same arithmetic either way."""
         self.system, self.backend = system, system.backend
+        self.fused = fused
         self.errest = bool(errest and self.bhat)
         self.nregs = 4 if self.errest else 2
 
@@ -157,12 +163,17 @@ class RKVdH2RStepper:
         r2, *rs = sorted(set(self._regidx) - {r1})
 
         for i, ci in enumerate(self.c):
-            self.system.rhs(t + ci*dt, r2 if i > 0 else r1, r2)
-
             kerns = self._stage_kerns(i, r1, r2, *rs)
-            for k in kerns:
-                k.bind(dt=dt)
-            self.backend.run_kernels(kerns)
+            uin = r2 if i > 0 else r1
+
+            if self.fused:
+                self.system.rhs(t + ci*dt, uin, r2,
+                                post=((i, r1, r2, *rs), kerns), dt=dt)
+            else:
+                self.system.rhs(t + ci*dt, uin, r2)
+                for k in kerns:
+                    k.bind(dt=dt)
+                self.backend.run_kernels(kerns)
 
             r1, r2 = r2, r1
 

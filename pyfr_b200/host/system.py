@@ -217,25 +217,51 @@ class BaseSystem:
         subs = [[(k, n) for k, n in sub if k] for sub in subs]
         g.group(kerns, [sub for sub in subs if len(sub) > 1])
 
-    def _rhs_graphs(self, uin, fout):
+    def _rhs_graphs(self, uin, fout, post=()):
         raise NotImplementedError
 
-    def rhs_graphs(self, uin, fout):
-        if (uin, fout) not in self._graphs:
-            self._graphs[uin, fout] = self._rhs_graphs(uin, fout)
+    def _add_post(self, g, k, post):
+        """Appends per-element-type kernels that consume the finished RHS
+        (a Runge-Kutta stage update) to its last graph, grouped with the
+        kernels they follow so that the backend may fuse them."""
+        for l in post:
+            g.add(l, deps=k['eles/negdivconf'])
 
-        return self._graphs[uin, fout]
+    def rhs_graphs(self, uin, fout, post=None):
+        """``post = (key, kernels)``: see ``_add_post``; graphs are
+        memoised per ``(uin, fout, key)``."""
+        key = (uin, fout) if post is None else (uin, fout, post[0])
 
-    def rhs(self, t, uinbank, foutbank):
+        if key not in self._graphs:
+            self._graphs[key] = (
+                self._rhs_graphs(uin, fout) if post is None else
+                self._rhs_graphs(uin, fout, tuple(post[1]))
+            )
+
+        return self._graphs[key]
+
+    def rhs(self, t, uinbank, foutbank, post=None, **rtargs):
+        """``rtargs``: run-time scalars of the ``post`` kernels (``dt``)."""
         if uinbank >= self.nrhs or foutbank >= self.nrhs:
             raise ValueError('Invalid register numbers')
 
-        graphs = self.rhs_graphs(uinbank, foutbank)
+        graphs = self.rhs_graphs(uinbank, foutbank, post)
 
         for ks in self._get_kernels(uinbank, foutbank).values():
             for k in ks:
                 if k.rtnames:
                     k.bind(t=t)
+
+        if post is not None:
+            # After fusion the scalars belong to whatever kernel absorbed
+            # the post kernels: look them up in the committed plans
+            for g in graphs:
+                plan = getattr(g, 'plan', None)
+                ks = ([k for w, k in plan if w == 'kernel']
+                      if plan is not None else post[1])
+                for k in ks:
+                    if set(getattr(k, 'rtnames', ()) or ()) & set(rtargs):
+                        k.bind(**rtargs)
 
         for g in graphs:
             self.backend.run_graph(g)
@@ -258,7 +284,7 @@ class EulerSystem(BaseSystem):
     mpiinterscls = EulerMPIInters
     bcmap = euler_bc_map
 
-    def _rhs_graphs(self, uin, fout):
+    def _rhs_graphs(self, uin, fout, post=()):
         m, k = self._mpireqs, self._get_kernels(uin, fout)
         deps = lambda dk, *names: self._kdeps(k, dk, *names)
         be = self.backend
@@ -289,8 +315,10 @@ class EulerSystem(BaseSystem):
         for l in k['eles/negdivconf']:
             g2.add(l, deps=deps(l, 'eles/tdivtconf'))
 
+        self._add_post(g2, k, post)
+
         kgroup = [k['eles/qptsu'], k['eles/tdisf'], k['eles/tdivtpcorf'],
-                  k['eles/tdivtconf'], k['eles/negdivconf']]
+                  k['eles/tdivtconf'], k['eles/negdivconf'], list(post)]
         for ks in it.zip_longest(*kgroup):
             self._group(g2, ks, subs=[[(ks[0], 'out'), (ks[1], 'u')],
                                       [(ks[1], 'f'), (ks[2], 'b')]])
@@ -319,7 +347,7 @@ class NavierStokesSystem(BaseSystem):
         # solution exchange, so it takes the lower tag on every interface
         super().commit()
 
-    def _rhs_graphs(self, uin, fout):
+    def _rhs_graphs(self, uin, fout, post=()):
         m, k = self._mpireqs, self._get_kernels(uin, fout)
         deps = lambda dk, *names: self._kdeps(k, dk, *names)
         be = self.backend
@@ -415,9 +443,10 @@ class NavierStokesSystem(BaseSystem):
         g3.add_all(k['eles/tdivtconf'], deps=k['mpiint/comm_flux'])
         for l in k['eles/negdivconf']:
             g3.add(l, deps=deps(l, 'eles/tdivtconf'))
-        for k1, k2 in it.zip_longest(k['eles/tdivtconf'],
-                                     k['eles/negdivconf']):
-            self._group(g3, [k1, k2])
+        self._add_post(g3, k, post)
+        for ks in it.zip_longest(k['eles/tdivtconf'], k['eles/negdivconf'],
+                                 list(post)):
+            self._group(g3, list(ks))
         g3.commit()
 
         return g1, g2, g3

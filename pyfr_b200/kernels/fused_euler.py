@@ -29,11 +29,13 @@ from pyfr_b200.kernels.fused import (ConstPool, NotFusable, PhaseEmitter,
 from pyfr_b200.kernels.mul import _pipeline_src
 
 
-def fluxdiv_source(be, ops, tplargs, pts, LD):
+def fluxdiv_source(be, ops, tplargs, pts, LD, rk=None):
     """``ops``: ``A5`` (nupts x ndims*nupts) and ``M3`` (nupts x nfpts);
     ``tplargs``: the Euler ``tflux`` template arguments (``ktype`` 'linear'
-    or 'curved').  Raises ``NotFusable`` when the operators lack line
-    structure or the block does not fit shared memory."""
+    or 'curved').  ``rk``: template arguments of an ``rkvdh2`` stage to
+    apply to the result on its way out (see ``mul_source``).  Raises
+    ``NotFusable`` when the operators lack line structure or the block does
+    not fit shared memory."""
     nd, nv = tplargs['ndims'], tplargs['nvars']
     A5, M3 = (np.asarray(ops[k], dtype=float) for k in ('A5', 'M3'))
     nu, nf = M3.shape
@@ -121,6 +123,31 @@ def fluxdiv_source(be, ops, tplargs, pts, LD):
     if smem > 227*1024:
         raise NotFusable(f'needs {smem} bytes of shared memory')
 
+    if rk:
+        st, last = rk['stage'], rk['stage'] == rk['nstages'] - 1
+        c = lambda x: ph.fpconst(x[st])
+        rix = lambda n: f'{n}[blk*{n}_bsz + item]'
+        L = [f'const fpdtype_t kk = -RJ[p*C_SUB + e]*({psum}), '
+             f't1 = {rix("r1")};']
+        if rk['errest'] and st == 0:
+            L += [f'{rix("rerr")} = dt*{c(rk["e"])}*kk;',
+                  f'{rix("rold")} = t1;']
+        elif rk['errest']:
+            L += [f'{rix("rerr")} = {rix("rerr")} + dt*{c(rk["e"])}*kk;']
+        if last:
+            L += [f'{rix("r1")} = t1 + dt*{c(rk["b"])}*kk;']
+        else:
+            L += [f'{rix("r1")} = t1 + dt*{c(rk["a"])}*kk;',
+                  f'fout[fob + item] = t1 + dt*{c(rk["b"])}*kk;']
+        out_stmt = '\n            '.join(L)
+        regs = ['r1'] + (['rold', 'rerr'] if rk['errest'] else [])
+        rkargs = ''.join(f',\n        fpdtype_t* __restrict__ {n}, '
+                         f'long long {n}_bsz' for n in regs)
+        rkargs += ',\n        fpdtype_t dt'
+    else:
+        out_stmt = f'fout[fob + item] = -RJ[p*C_SUB + e]*({psum});'
+        rkargs = ''
+
     tail = f'RJ + {npoints} + {geo_words}'
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
@@ -141,7 +168,7 @@ fluxdiv(int nblocks, int neles,
         const fpdtype_t* __restrict__ u, long long u_bsz,
         const fpdtype_t* __restrict__ fcomm, long long fcomm_bsz,
         fpdtype_t* __restrict__ fout, long long fout_bsz,
-        {gargs})
+        {gargs}{rkargs})
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
@@ -245,7 +272,7 @@ fluxdiv(int nblocks, int neles,
         {{
             const int p = item / LD, col = item - p*LD;
             const int e = (col / (K_SOA*NVARS))*K_SOA + col % K_SOA;
-            fout[fob + item] = -RJ[p*C_SUB + e]*({psum});
+            {out_stmt}
         }}
         __syncthreads();
     }}

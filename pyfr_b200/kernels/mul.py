@@ -97,13 +97,20 @@ def plan_chunks(K, LD, itemsize, smem_budget, hint=None):
 
 
 def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
-               chunk_hint=None, negdiv_nvars=None):
+               chunk_hint=None, negdiv_nvars=None, rk=None):
     """CUDA source for ``out = alpha*A@b + beta*out``.
 
     With ``negdiv_nvars`` the ``negdivconf`` step that follows the last
     operator of the RHS (``out = -rcpdjac*out``, pyfr/solvers/baseadvec/
     kernels/negdivconf.mako) is applied in the epilogue, saving one full
     read-modify-write pass over the result.
+
+    With ``rk`` (the ``rkvdh2`` template arguments, only together with
+    ``negdiv_nvars``) the Runge-Kutta stage update that consumes the RHS
+    (pyfr/integrators/explicit/kernels/rkvdh2.mako) is applied as well:
+    the RHS value ``k`` never reaches memory, the kernel reads ``r1`` and
+    writes ``r1 + dt a k`` and (into ``out``, the RHS bank ``r2``)
+    ``r1 + dt b k``, plus the error-estimate registers when asked.
 
     Returns (source, name, launch meta dict)."""
     A = alpha*np.asarray(A, dtype=float)
@@ -139,13 +146,34 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
 
         return expr
 
+    if rk and not negdiv_nvars:
+        raise ValueError('rk epilogue needs the negdivconf epilogue')
+
     def store(m, val):
         ix = f'ob + {m*LD} + col'
         if negdiv_nvars:
             old = f'out[{ix}] + ' if beta == 1 else (
                 f'{ph.fpconst(beta)}*out[{ix}] + ' if beta else '')
-            return (f'out[{ix}] = -__ldg(rcpdjac + rjb + {m}*C_SUB)*'
-                    f'({old}{val});')
+            rhs = f'-__ldg(rcpdjac + rjb + {m}*C_SUB)*({old}{val})'
+
+            if not rk:
+                return f'out[{ix}] = {rhs};'
+
+            st, last = rk['stage'], rk['stage'] == rk['nstages'] - 1
+            c = lambda x: ph.fpconst(x[st])
+            rix = lambda n: f'{n}[blk*{n}_bsz + {m*LD} + col]'
+            L = [f'{{ const fpdtype_t kk = {rhs}, t1 = {rix("r1")};']
+            if rk['errest'] and st == 0:
+                L += [f'{rix("rerr")} = dt*{c(rk["e"])}*kk;',
+                      f'{rix("rold")} = t1;']
+            elif rk['errest']:
+                L += [f'{rix("rerr")} = {rix("rerr")} + dt*{c(rk["e"])}*kk;']
+            if last:
+                L += [f'{rix("r1")} = t1 + dt*{c(rk["b"])}*kk; }}']
+            else:
+                L += [f'{rix("r1")} = t1 + dt*{c(rk["a"])}*kk;',
+                      f'out[{ix}] = t1 + dt*{c(rk["b"])}*kk; }}']
+            return ' '.join(L)
         if beta == 0:
             return f'out[{ix}] = {val};'
         elif beta == 1:
@@ -187,6 +215,11 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
                       'long long rcpdjac_bsz')
         extra_pre = (f'        const long long rjb = blk*rcpdjac_bsz + '
                      f'(col/(K_SOA*{negdiv_nvars}))*K_SOA + col % K_SOA;')
+    if rk:
+        regs = ['r1'] + (['rold', 'rerr'] if rk['errest'] else [])
+        extra_args += ''.join(f', fpdtype_t* __restrict__ {n}, '
+                              f'long long {n}_bsz' for n in regs)
+        extra_args += ', fpdtype_t dt'
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz)}

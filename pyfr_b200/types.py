@@ -152,6 +152,11 @@ class B200Graph(base.Graph):
 
         for kerns, subs in getattr(self, '_fgroups', []):
             new = fusion.fuse_group(be, kerns, subs)
+            if not new and kerns and \
+               getattr(kerns[-1], 'kind', None) == 'rkvdh2':
+                # the RHS chain fuses without the stage update
+                kerns = kerns[:-1]
+                new = fusion.fuse_group(be, kerns, subs)
             if not new:
                 continue
 

@@ -300,7 +300,7 @@ def test_sutherland_viscosity_through_generated_kernels(emulated):
     assert rel_err(ref[0], const[0]) > 1e-7
 
 
-def _pi_run(sysm, cfg, tend, norm='l2'):
+def _pi_run(sysm, cfg, tend, norm='l2', fused=False):
     from pyfr_b200.host.integrator import PIController, RK45Stepper
 
     cfg.set('solver-time-integrator', 'dt', 0.05)
@@ -308,7 +308,7 @@ def _pi_run(sysm, cfg, tend, norm='l2'):
     cfg.set('solver-time-integrator', 'rtol', 1e-6)
     cfg.set('solver-time-integrator', 'errest-norm', norm)
 
-    st = RK45Stepper(sysm, errest=True)
+    st = RK45Stepper(sysm, errest=True, fused=fused)
     pi = PIController(st, cfg, ['rho', 'rhou', 'rhov', 'E'])
     pi.advance_to(tend)
 
@@ -325,7 +325,10 @@ def test_rk45_pi_controller_through_generated_kernels(emulated, norm):
         cfg, box = cases.make('vortex', (4, 4), order=3)
         sysm = (_b200(cfg, box, nregs=4) if which == 'b200' else
                 get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4))
-        pi, st = _pi_run(sysm, cfg, 0.2, norm)
+        # the l2 case also takes the fused stage update (dt rebound at
+        # every step, rejected steps included)
+        pi, st = _pi_run(sysm, cfg, 0.2, norm,
+                         fused=which == 'b200' and norm == 'l2')
         res.append((pi.stepinfo, st.soln[0], pi))
 
     (io, so, po), (ib, sb, pb) = res
@@ -547,3 +550,50 @@ def test_field_reductions_with_coordinates(emulated):
     want = (rho*x[:, 0]**2 + p*np.cos(x[:, 1])).max()
     assert res['oracle', 'max'][0] == pytest.approx(want, rel=1e-13)
     assert res['oracle', 'min'][0] < res['oracle', 'max'][0]
+
+
+@pytest.mark.parametrize('case,n,kw,kind', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1), 'mul+negdivconf+rkvdh2'),
+    ('vortex', (4, 4), dict(order=3), 'fluxdiv+rkvdh2'),
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, curved=0.5),
+     'mul+negdivconf+rkvdh2'),
+], ids=str)
+@pytest.mark.parametrize('errest', [False, True])
+def test_rk_stage_update_fused_into_last_rhs_kernel(emulated, case, n, kw,
+                                                    kind, errest):
+    """the rkvdh2 stage update applied in the epilogue of
+    the last RHS kernel.  Same result as the separate kernels and as the
+    oracle; one launch fewer per stage."""
+    from pyfr_b200.host.integrator import RK45Stepper
+
+    sols, launches = {}, {}
+    for which in ('oracle', 'b200', 'b200-fused'):
+        cfg, box = cases.make(case, n, **kw)
+        sysm = (get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4)
+                if which == 'oracle' else _b200(cfg, box, nregs=4))
+        st = RK45Stepper(sysm, errest=errest, fused=which != 'b200')
+        st.advance(1, 2e-3)                      # builds the kernels
+        rt = getattr(sysm.backend, 'rt', None)
+        n0 = getattr(rt, 'nlaunch', 0)
+        st.advance(2, 2e-3)
+        launches[which] = getattr(rt, 'nlaunch', 0) - n0
+        sols[which] = [sysm.ele_scal_upts(i)[0] for i in range(4)]
+
+        if which == 'b200-fused':
+            kinds = [getattr(k, 'kind', None) for g in sysm._graphs.values()
+                     for gg in g for w, k in gg.plan if w == 'kernel']
+            assert kind in kinds and 'rkvdh2' not in kinds
+
+    # every register bank that carries state (solution, previous solution,
+    # error estimate) agrees; the bank left holding a raw RHS is not state
+    # (the error estimate is a cancelling sum of O(dt k) terms: measure it
+    # against the scale of the solution it estimates the error of)
+    live = [st.idxcurr] + (sorted(set(range(4)) - {0, 1}) if errest else [])
+    scale = np.abs(sols['oracle'][st.idxcurr]).max()
+    for i in live:
+        for other, tol in (('oracle', 1e-12), ('b200', 1e-13)):
+            d = np.abs(sols['b200-fused'][i] - sols[other][i]).max()
+            assert d < tol*scale, (i, other, d)
+
+    # 5 stages x 2 steps, one launch saved per stage and element region
+    assert launches['b200'] - launches['b200-fused'] >= 10
