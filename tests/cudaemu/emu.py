@@ -108,6 +108,35 @@ class EmuRuntime:
         self._bufs = {}
         self._mods = []
         self.nlaunch = 0
+        self._cap = None            # operations of the graph being captured
+        self.ncaptures = 0
+
+    # -- stream capture -------------------------------------------------------
+    # Modelled on CUDA graphs: while a capture is open nothing executes;
+    # kernel parameters are copied *by value* into the captured node, so a
+    # replay does not see later changes to the caller's argument storage
+    # (the backend has to re-capture, which is what its dirty flags are for)
+    def capture_begin(self, stream):
+        if self._cap is not None:
+            raise RuntimeError('nested stream capture')
+        self._cap = []
+
+    def end_capture(self, stream):
+        ops, self._cap = self._cap, None
+        self.ncaptures += 1
+        return ops
+
+    def graph_launch(self, graph, stream):
+        if self._cap is not None:
+            raise RuntimeError('graph launch during capture')
+        for op in graph:
+            op()
+
+    def _do(self, op):
+        if self._cap is not None:
+            self._cap.append(op)
+        else:
+            op()
 
     # -- handles ------------------------------------------------------------
     def new_ptr(self, fn, *args):
@@ -147,17 +176,21 @@ class EmuRuntime:
 
     # -- data movement ------------------------------------------------------
     def memset(self, ptr, value, nbytes, stream):
-        ct.memset(ptr, value, nbytes)
+        self._do(lambda: ct.memset(ptr, value, nbytes))
 
     def memcpy(self, dst, src, nbytes):
+        if self._cap is not None:
+            raise RuntimeError('synchronous copy during stream capture')
         ct.memmove(dst, src, nbytes)
 
     def memcpy_async(self, dst, src, nbytes, stream):
-        ct.memmove(dst, src, nbytes)
+        self._do(lambda: ct.memmove(dst, src, nbytes))
 
     def memcpy2d_async(self, dst, dpitch, src, spitch, width, height, stream):
-        for r in range(height):
-            ct.memmove(dst + r*dpitch, src + r*spitch, width)
+        def op():
+            for r in range(height):
+                ct.memmove(dst + r*dpitch, src + r*spitch, width)
+        self._do(op)
 
     # -- kernels --------------------------------------------------------------
     def module_load(self, image):
@@ -174,9 +207,26 @@ class EmuRuntime:
     def launch(self, func, gx, gy, gz, bx, by, bz, smem, stream, argv):
         if smem > 256*1024:
             raise RuntimeError('emulated shared memory exceeded')
-        func.entry(ct.cast(argv, ct.c_void_p), *map(int, (gx, gy, gz, bx, by,
-                                                          bz)))
-        self.nlaunch += 1
+
+        dims = tuple(map(int, (gx, gy, gz, bx, by, bz)))
+
+        if self._cap is None:
+            func.entry(ct.cast(argv, ct.c_void_p), *dims)
+            self.nlaunch += 1
+            return
+
+        # Snapshot the parameters (every one is at most 8 bytes wide)
+        n = len(argv)
+        vals = (ct.c_uint64*n)()
+        for i in range(n):
+            ct.memmove(ct.addressof(vals) + 8*i, argv[i], 8)
+        ptrs = (ct.c_void_p*n)(*[ct.addressof(vals) + 8*i for i in range(n)])
+
+        def op(keep=(vals, ptrs)):
+            func.entry(ct.cast(ptrs, ct.c_void_p), *dims)
+            self.nlaunch += 1
+
+        self._cap.append(op)
 
     def device_info(self):
         return dict(sm_count=148, cc=(10, 0), total_mem=0, free_mem=0,
@@ -189,7 +239,7 @@ class EmuRuntime:
 
 
 def install(monkeypatch):
-    """Route B200Backend through the emulator (graphs off)."""
+    """Route B200Backend through the emulator."""
     import pyfr_b200.backend as bk
     import pyfr_b200.compiler as comp
 

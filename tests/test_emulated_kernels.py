@@ -31,12 +31,14 @@ def emulated(monkeypatch):
 def _b200(cfg, box, vparts=None, rank=0, comm=None, nregs=2, opts={}):
     from pyfr_b200.backend import B200Backend
 
-    cfg.set('backend-b200', 'graphs', 'false')
+    cfg.set('backend-b200', 'graphs', os.environ.get('EMU_GRAPHS', 'false'))
     for k, v in opts.items():
         cfg.set('backend-b200', k, v)
 
     be = B200Backend(cfg, comm=comm)
     assert getattr(be.rt, 'emulated', False)
+    if comm is not None:
+        comm.rt = be.rt
     return get_system(be, box.local_mesh(vparts, rank), cfg, nregs,
                       comm=comm)
 
@@ -151,13 +153,19 @@ class EmuWorld:
             size = w.size
 
             def exchange(self, reqs, stream):
-                for r in reqs:
-                    m = r.mat
-                    nb = m.nrow*m.ncol*m.itemsize
-                    if r.kind == 'send':
-                        w.box[rank, r.peer, r.tag] = ct.string_at(m.data, nb)
-                    else:
-                        w.pending.append(((r.peer, rank, r.tag), m.data, nb))
+                # (an operation on the stream: deferred while a graph is
+                # being captured, like the NCCL calls it stands in for)
+                def op():
+                    for r in reqs:
+                        m = r.mat
+                        nb = m.nrow*m.ncol*m.itemsize
+                        if r.kind == 'send':
+                            w.box[rank, r.peer, r.tag] = ct.string_at(m.data,
+                                                                      nb)
+                        else:
+                            w.pending.append(((r.peer, rank, r.tag), m.data,
+                                              nb))
+                self.rt._do(op)
 
         c = Comm()
         c.rank = rank
@@ -169,10 +177,11 @@ class EmuWorld:
         self.pending.clear()
 
 
+@pytest.mark.parametrize('graphs', ['false', 'true'])
 @pytest.mark.parametrize('kw', [dict(order=2, warp=0.1),
                                 dict(order=2, beta=0.0, rsolver='hllc')],
                          ids=str)
-def test_partitioned_run_through_generated_kernels(emulated, kw):
+def test_partitioned_run_through_generated_kernels(emulated, kw, graphs):
     """Two partitions, halo exchange through the backend's exchange
     descriptors (pack kernels, mpiconu / mpicflux, receive-only graphs):
     against the partitioned oracle."""
@@ -184,7 +193,8 @@ def test_partitioned_run_through_generated_kernels(emulated, kw):
     systems = []
     for r in range(2):
         cfg, box = cases.make('tgv', n, **kw)
-        systems.append(_b200(cfg, box, vparts, r, comm=world.peer(r)))
+        systems.append(_b200(cfg, box, vparts, r, comm=world.peer(r),
+                             opts={'graphs': graphs}))
 
     for stage in zip(*[s.rhs_graphs(0, 1) for s in systems]):
         for g in stage:
@@ -597,3 +607,75 @@ def test_rk_stage_update_fused_into_last_rhs_kernel(emulated, case, n, kw,
 
     # 5 stages x 2 steps, one launch saved per stage and element region
     assert launches['b200'] - launches['b200-fused'] >= 10
+
+
+def _b200_graphs(cfg, box, nregs=2, **kw):
+    from pyfr_b200.backend import B200Backend
+
+    cfg.set('backend-b200', 'graphs', 'true')
+    be = B200Backend(cfg)
+    assert be.use_graphs and getattr(be.rt, 'emulated', False)
+    return get_system(be, box.local_mesh(), cfg, nregs, **kw)
+
+
+def test_graph_replay_and_recapture(emulated):
+    """``graphs = true``: each RHS graph is captured once and replayed; the
+    emulated runtime copies kernel parameters by value at capture time, as
+    CUDA graphs do, so a run-time scalar that changes (here the time ``t``
+    a boundary condition depends on) is only seen if the backend notices
+    and re-captures."""
+    bcs = {'xlo': 'sub-in-frv', 'xhi': 'sub-out-fp'}
+    tdep = '\n[soln-bcs-xlo]\nu = 0.2 + 0.1*sin(3*t)\n'
+
+    def systems():
+        out = []
+        for which in ('oracle', 'b200'):
+            cfg, box, txt = cases.box_case('navier-stokes', (3, 2, 2), bcs,
+                                           order=2, warp=0.1)
+            cfg.set('soln-bcs-xlo', 'u', '0.2 + 0.1*sin(3*t)')
+            out.append(_b200_graphs(cfg, box) if which == 'b200' else
+                       get_system(OracleBackend(cfg), box.local_mesh(), cfg,
+                                  2))
+        return out
+
+    so, sb = systems()
+    rt = sb.backend.rt
+
+    outs = []
+    for t in (0.0, 0.0, 0.4, 0.4, 0.9):
+        for s in (so, sb):
+            s.rhs(t, 0, 1)
+        sb.backend.wait()
+        outs.append((t, so.ele_scal_upts(1)[0], sb.ele_scal_upts(1)[0],
+                     rt.ncaptures))
+
+    for t, ro, rb, _ in outs:
+        assert rel_err(rb, ro) < 1e-12, t
+
+    # the boundary value really depends on t ...
+    assert rel_err(outs[2][1], outs[0][1]) > 1e-6
+    # ... and only the graphs holding a t-dependent kernel were re-captured,
+    # only when t changed
+    ncap = [c for *_, c in outs]
+    ngraphs = len(sb.rhs_graphs(0, 1))
+    assert ncap[0] == ngraphs and ncap[1] == ncap[0]
+    assert ncap[0] < ncap[2] <= ncap[0] + ngraphs and ncap[3] == ncap[2]
+    assert ncap[4] > ncap[3]
+
+
+def test_fused_stage_update_under_graphs(emulated):
+    """PI-controlled RK45 with the fused stage update and graphs on: dt is a
+    captured kernel parameter that changes every step."""
+    res = []
+    for which in ('oracle', 'b200'):
+        cfg, box = cases.make('vortex', (4, 4), order=3)
+        sysm = (_b200_graphs(cfg, box, nregs=4) if which == 'b200' else
+                get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4))
+        pi, st = _pi_run(sysm, cfg, 0.2, fused=which == 'b200')
+        res.append((pi.stepinfo, st.soln[0]))
+
+    (io, so), (ib, sb) = res
+    assert [a[1] for a in io] == [a[1] for a in ib]
+    np.testing.assert_allclose([a[0] for a in ib], [a[0] for a in io],
+                               rtol=1e-9)
+    assert rel_err(sb, so) < 1e-12

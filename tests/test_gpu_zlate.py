@@ -230,3 +230,43 @@ def test_mixed_element_types_match_oracle(built, pattern, n, kw):
     assert len(out) == len(pattern.split('+'))
     for o, r, e in zip(out, ref, ext):
         assert_parity(o, r, e, TOL64)
+
+
+@pytest.mark.parametrize('case,n,kw,kind', [
+    ('tgv', (4, 3, 3), dict(order=3, warp=0.1), 'mul+negdivconf+rkvdh2'),
+    ('vortex', (8, 8), dict(order=3), 'fluxdiv+rkvdh2'),
+], ids=['ns', 'euler'])
+def test_fused_rk_stage_update_matches_oracle(built, case, n, kw, kind):
+    """rkvdh2 applied in the epilogue of the last RHS
+    kernel, fixed step size (graphs captured once) and under the PI
+    controller (dt re-bound every step: graphs re-captured)."""
+    from pyfr_b200.host.integrator import PIController, RK45Stepper
+
+    convars = ['rho', 'rhou', 'rhov', 'rhow'][:len(n) + 1] + ['E']
+    dt0 = 2e-3 if case == 'tgv' else 0.08
+    res = {}
+    for which in ('oracle', 'b200', 'b200-fused'):
+        cfg, box = cases.make(case, n, **kw)
+        sysm = (get_system(OracleBackend(cfg), box.local_mesh(), cfg, 4)
+                if which == 'oracle' else _b200(cfg, box, nregs=4))
+        for k, v in (('dt', dt0), ('atol', 1e-6), ('rtol', 1e-6)):
+            cfg.set('solver-time-integrator', k, v)
+
+        st = RK45Stepper(sysm, errest=True, fused=which == 'b200-fused')
+        st.advance(3, dt0/4)
+        pi = PIController(st, cfg, convars)
+        pi.advance_to(st.tcurr + 3.5*dt0)
+        res[which] = (st.soln[0], pi.stepinfo)
+
+        if which == 'b200-fused':
+            kinds = [getattr(k, 'kind', None) for g in sysm._graphs.values()
+                     for gg in g for w, k in gg.plan if w == 'kernel']
+            assert kind in kinds and 'rkvdh2' not in kinds
+
+    so, io = res['oracle']
+    for which in ('b200', 'b200-fused'):
+        s, i = res[which]
+        assert [a[1] for a in i] == [a[1] for a in io]
+        np.testing.assert_allclose([a[0] for a in i], [a[0] for a in io],
+                                   rtol=1e-9)
+        assert rel_err(s, so) < 1e-11
