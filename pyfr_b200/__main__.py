@@ -39,6 +39,9 @@ def main(argv=None):
     ap.add_argument('--cfl', type=float, default=None, help='choose the '
                     'step size from the largest wave speed (CFL '
                     'controller); --steps*--dt is the end time')
+    ap.add_argument('--fused-update', action='store_true', help='rk45: '
+                    'apply each stage update in the epilogue of the last RHS '
+                    'kernel')
     ap.add_argument('--atol', type=float, default=1e-6)
     ap.add_argument('--rtol', type=float, default=1e-6)
     ap.add_argument('--opt', action='append', default=[],
@@ -108,12 +111,12 @@ def main(argv=None):
 
     if args.cfl is not None:
         cfg.set(sect, 'cfl', args.cfl)
-        st = (RK45Stepper(sysm) if args.scheme == 'rk45' else
-              RK4Stepper(sysm))
+        st = (RK45Stepper(sysm, fused=args.fused_update)
+              if args.scheme == 'rk45' else RK4Stepper(sysm))
         ctl = CFLController(st, cfg, allreduce=allreduce)
     elif adaptive:
         convars = ['rho', 'rhou', 'rhov', 'rhow'][:nd + 1] + ['E']
-        st = RK45Stepper(sysm, errest=True)
+        st = RK45Stepper(sysm, errest=True, fused=args.fused_update)
         ctl = PIController(st, cfg, convars, allreduce=allreduce)
     else:
         st = RK4Stepper(sysm)

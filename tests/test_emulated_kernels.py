@@ -397,7 +397,7 @@ def test_standalone_driver_adaptive(emulated, capsys):
     from pyfr_b200.__main__ import main
 
     main(['vortex', '--n', '3', '--order', '2', '--scheme', 'rk45', '--dt',
-          '0.05', '--steps', '4', '--every', '2', '--opt', 'graphs=false'])
+          '0.05', '--steps', '4', '--every', '2', '--fused-update'])
     out = capsys.readouterr().out.splitlines()
     rows = [l.split() for l in out if l and not l.startswith('#')]
 
