@@ -329,3 +329,97 @@ def test_reference_integrate_plugin_on_b200_backend(built):
     # coordinate- and time-dependent expressions)
     assert int(nrows) == 4 and float(err) < 1e-13
     assert abs(float(ke0) - 0.125) < 5e-3
+
+
+_mpi_script = r'''
+import ctypes as ct, os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+from types import SimpleNamespace
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+rh.install_stubs()
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+from pyfr.inifile import Inifile
+from pyfr.solvers.euler import EulerSystem
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+from test_emulated_kernels import EmuWorld
+
+for case, n, parts, kw in [('tgv', (4, 2, 2), (2, 1, 1), dict(order=2, warp=0.1)),
+                           ('tgv', (4, 2, 2), (2, 1, 1),
+                            dict(order=2, beta=0.0, rsolver='hllc')),
+                           ('vortex', (6, 4), (3, 1), dict(order=3))]:
+    kw2 = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
+    _, box = cases.make(case, n, **kw)
+    nparts = int(np.prod(parts))
+    vparts = box.brick_partition(parts)
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+
+    # The reference's host code per rank: on the oracle backend ...
+    lworld = LocalComm(0, nparts)
+    ref = [rh.ref_system(txt, box.local_mesh(vparts, r), 2, lworld.peer(r))[0]
+           for r in range(nparts)]
+
+    # ... and on the B200 backend with an in-process communicator
+    eworld = EmuWorld(nparts)
+    b200 = []
+    for r in range(nparts):
+        rh.set_rank(lworld.peer(r))
+        cfg = Inifile(txt + '\n[backend-b200]\ngraphs = true\n')
+        comm = eworld.peer(r)
+        be = B200Backend(cfg, comm=comm)
+        comm.rt = be.rt
+        regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+        s = cls(be, rh.ref_mesh(box.local_mesh(vparts, r)), None, regs, cfg,
+                None)
+        s.commit()
+        b200.append(s)
+
+    for systems, world in ((ref, lworld), (b200, eworld)):
+        graphs = [s._rhs_graphs(0, 1) for s in systems]
+        for s in systems:
+            s._prepare_kernels(0.0, 0, 1)
+        for stage in zip(*graphs):
+            for g in stage:
+                g.run()
+            world.deliver()
+
+    err = max(np.abs(a.ele_scal_upts(1)[0] - b.ele_scal_upts(1)[0]).max()
+              / np.abs(a.ele_scal_upts(1)[0]).max()
+              for a, b in zip(ref, b200))
+    nx = sum(1 for g in b200[0]._rhs_graphs(0, 1)
+             for w, o in g.plan if w == 'xchg')
+    print('RESULT', case, nparts, err, nx)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_reference_mpi_interfaces_on_b200_backend(built):
+    """Partitioned runs under the reference's own host code: its
+    ``MPIInters`` classes create the exchange views, pack kernels and
+    ``sendreq``/``recvreq`` requests (``register_mpi_exchange``,
+    pyfr/solvers/base/system.py:185-202) and hand them to ``Graph.
+    add_mpi_req``; the backend turns them into grouped exchanges inside
+    captured graphs.  Two and three ranks, same RHS as the reference host on
+    the oracle backend."""
+    res = subprocess.run([sys.executable, '-c',
+                          _mpi_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2500:]
+
+    rows = [l.split()[1:] for l in res.stdout.splitlines()
+            if l.startswith('RESULT')]
+    assert [(r[0], int(r[1])) for r in rows] == [('tgv', 2), ('tgv', 2),
+                                                 ('vortex', 3)]
+    assert all(float(r[2]) < 1e-12 for r in rows)
+    # Navier-Stokes exchanges twice per RHS, Euler once
+    assert [int(r[3]) for r in rows] == [2, 2, 1]
