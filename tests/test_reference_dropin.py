@@ -423,3 +423,79 @@ def test_reference_mpi_interfaces_on_b200_backend(built):
     assert all(float(r[2]) < 1e-12 for r in rows)
     # Navier-Stokes exchanges twice per RHS, Euler once
     assert [int(r[3]) for r in rows] == [2, 2, 1]
+
+
+_bc_script = r'''
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+from types import SimpleNamespace
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+rh.install_stubs()
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+from pyfr.inifile import Inifile
+from pyfr.solvers.euler import EulerSystem
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+CASES = [
+    ('navier-stokes', (3, 3, 2), {'ylo': 'no-slp-adia-wall',
+                                  'yhi': 'char-riem-inv',
+                                  'xlo': 'sub-in-ftpttang',
+                                  'xhi': 'sub-out-fp'},
+     dict(order=2, warp=0.1)),
+    ('navier-stokes', (2, 2, 3), {'xlo': 'sub-in-frv', 'xhi': 'sup-out-fn',
+                                  'zlo': 'slp-adia-wall',
+                                  'zhi': 'no-slp-isot-wall',
+                                  'ylo': 'sup-in-fa', 'yhi': 'sub-out-fp'},
+     dict(order=2, rsolver='hllc', beta=0.0)),
+    ('euler', (5, 4), {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn',
+                       'ylo': 'slp-adia-wall', 'yhi': 'sup-in-fa'},
+     dict(order=3)),
+]
+
+for system, n, bcs, kw in CASES:
+    _, box, txt = cases.box_case(system, n, bcs, **kw)
+    mesh = box.local_mesh()
+    world = LocalComm(0, 1)
+    rh.set_rank(world.peer(0))
+
+    cfg = Inifile(txt + '\n[backend-b200]\ngraphs = true\n')
+    be = B200Backend(cfg)
+    regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+    cls = NavierStokesSystem if system == 'navier-stokes' else EulerSystem
+    s = cls(be, rh.ref_mesh(mesh), None, regs, cfg, None)
+    s.commit()
+
+    rs, rbe = rh.ref_system(txt, mesh, 2, world.peer(0))
+    errs = []
+    for t in (0.0, 0.7):
+        s.rhs(t, 0, 1)
+        rs.rhs(t, 0, 1)
+        out, ref = s.ele_scal_upts(1)[0], rs.ele_scal_upts(1)[0]
+        errs.append(np.abs(out - ref).max()/np.abs(ref).max())
+    print('RESULT', system, len(bcs), max(errs))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+                    reason='needs /root/reference')
+def test_reference_boundary_interfaces_on_b200_backend(built):
+    """The reference's boundary-interface classes (``pyfr/solvers/*/
+    inters.py``: template arguments, boundary-section constants and
+    expressions, ``ploc`` views) drive ``bcconu`` / ``bccflux`` for all
+    nine boundary types on the path."""
+    res = subprocess.run([sys.executable, '-c', _bc_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2500:]
+
+    rows = [l.split()[1:] for l in res.stdout.splitlines()
+            if l.startswith('RESULT')]
+    assert len(rows) == 3 and all(float(r[2]) < 1e-12 for r in rows)
