@@ -119,7 +119,13 @@ from pyfr_b200 import cases
 from pyfr_b200.backend import B200Backend
 
 for case, n, kw in [('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
-                    ('vortex', 5, dict(order=3))]:
+                    ('vortex', 5, dict(order=3)),
+                    ('tgv', (3, 2, 2), dict(order=2, warp=0.1,
+                                            antialias='flux')),
+                    ('vortex', 5, dict(order=3, antialias='flux')),
+                    ('tgv', (3, 2, 2), dict(order=3, warp=0.1,
+                                            visc_corr='sutherland',
+                                            rsolver='hllc'))]:
     kw2 = {k: v for k, v in kw.items() if k != 'warp'}
     txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
     txt += '\n[backend-b200]\ngraphs = false\n'
@@ -159,9 +165,11 @@ def test_reference_host_executes_on_b200_backend(built):
 
     rows = [l.split() for l in res.stdout.splitlines()
             if l.startswith('RESULT')]
-    assert [r[1] for r in rows] == ['tgv', 'vortex']
+    # + flux anti-aliasing (both systems) and Sutherland's law with HLLC
+    assert [r[1] for r in rows] == ['tgv', 'vortex', 'tgv', 'vortex', 'tgv']
     assert all(float(r[2]) < 1e-12 for r in rows)
-    assert [int(r[3]) for r in rows] == [5, 3]
+    assert [int(r[3]) for r in rows][:2] == [5, 3]
+    assert int(rows[4][3]) == 5
 
 
 _intg_script = r'''
