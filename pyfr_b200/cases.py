@@ -13,7 +13,8 @@ from pyfr_b200.host.mesh import BoxMesh, MixedBoxMesh
 
 
 def tgv_cfg(order=4, precision='double', rsolver='rusanov', beta=0.5,
-            extra='', antialias='none', visc_corr='none'):
+            extra='', antialias='none', visc_corr='none',
+            pts='gauss-legendre'):
     return f'''
 [backend]
 precision = {precision}
@@ -39,10 +40,10 @@ ldg-beta = {beta}
 ldg-tau = 0.1
 
 [solver-interfaces-quad]
-flux-pts = gauss-legendre
+flux-pts = {pts}
 
 [solver-elements-hex]
-soln-pts = gauss-legendre
+soln-pts = {pts}
 
 [soln-ics]
 rho = 1
@@ -55,7 +56,7 @@ p = 1/(gamma*M*M) + (cos(2*x) + cos(2*y))*(cos(2*z) + 2)/16
 
 
 def vortex_cfg(order=3, precision='double', rsolver='rusanov', extra='',
-               antialias='none'):
+               antialias='none', pts='gauss-legendre'):
     return f'''
 [backend]
 precision = {precision}
@@ -76,10 +77,10 @@ shock-capturing = none
 riemann-solver = {rsolver}
 
 [solver-interfaces-line]
-flux-pts = gauss-legendre
+flux-pts = {pts}
 
 [solver-elements-quad]
-soln-pts = gauss-legendre
+soln-pts = {pts}
 
 [soln-ics]
 rho = pow(1 - S*S*M*M*(gamma - 1)*exp(2*(1 - x*x - y*y)/(2*R*R))/(8*pi*pi), 1/(gamma - 1))

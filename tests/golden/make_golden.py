@@ -70,6 +70,18 @@ HOST_CASES = {
                                                  'csubsz': 8}),
     'vortex_p3_fluxaa': ('vortex', 5, dict(order=3, antialias='flux'),
                          (1, 1), {}),
+    # flux points coinciding with solution points (Gauss-Lobatto)
+    'tgv_p3_gll_beta0_2parts': ('tgv', (4, 2, 2),
+                                dict(order=3, warp=0.1, beta=0.0,
+                                     pts='gauss-legendre-lobatto'),
+                                (2, 1, 1), {}),
+    'tgv_p2_gll_blocked': ('tgv', (3, 2, 2),
+                           dict(order=2, warp=0.1,
+                                pts='gauss-legendre-lobatto'),
+                           (1, 1, 1), {'blocks': 1, 'soasz': 8, 'csubsz': 8}),
+    'vortex_p3_gll': ('vortex', 5, dict(order=3,
+                                        pts='gauss-legendre-lobatto'),
+                      (1, 1), {}),
 }
 
 # Wall-bounded / open-boundary cases: name -> box_case arguments
@@ -584,6 +596,13 @@ def main():
 
         if sys.argv[1:]:
             return
+
+    if sys.argv[1:2] == ['--only']:
+        for name in sys.argv[2].split(','):
+            np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
+                                **ref_host_case(name))
+            print(f'host_{name}.npz written')
+        return
 
     if sys.argv[1:] == ['--mixed']:
         for name in MIXED_CASES:

@@ -679,3 +679,25 @@ def test_fused_stage_update_under_graphs(emulated):
     np.testing.assert_allclose([a[0] for a in ib], [a[0] for a in io],
                                rtol=1e-9)
     assert rel_err(sb, so) < 1e-12
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
+    ('tgv', (3, 2, 2), dict(order=3, warp=0.1, beta=0.0, rsolver='hllc')),
+    ('tgv', (3, 2, 2), dict(order=2)),
+    ('vortex', 5, dict(order=3)),
+], ids=str)
+@pytest.mark.parametrize('opts', [{}, {'fusion': 0}], ids=['fused', 'nofuse'])
+def test_gauss_lobatto_points(emulated, case, n, kw, opts):
+    """Flux points that coincide with solution points (SURVEY appendix B,
+    hex GLL row): ``M0`` is a selection, the common solution lives in its
+    own buffer and interface views address solution-point rows."""
+    kw = dict(kw, pts='gauss-legendre-lobatto')
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box, opts=opts)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+    assert_parity(out, ref[0], ext[0], 1e-12)

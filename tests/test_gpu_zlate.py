@@ -270,3 +270,25 @@ def test_fused_rk_stage_update_matches_oracle(built, case, n, kw, kind):
         np.testing.assert_allclose([a[0] for a in i], [a[0] for a in io],
                                    rtol=1e-9)
         assert rel_err(s, so) < 1e-11
+
+
+GLL_CASES = [
+    ('tgv', (4, 3, 3), dict(order=3, warp=0.1, pts='gauss-legendre-lobatto')),
+    ('tgv', (3, 3, 3), dict(order=2, beta=0.0, rsolver='hllc',
+                            pts='gauss-legendre-lobatto')),
+    ('vortex', 9, dict(order=3, pts='gauss-legendre-lobatto')),
+]
+
+
+@pytest.mark.parametrize('case,n,kw', GLL_CASES, ids=str)
+def test_gauss_lobatto_points_match_oracle(built, case, n, kw):
+    """Flux points coinciding with solution points."""
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+    assert_parity(out, ref[0], ext[0], TOL64)
