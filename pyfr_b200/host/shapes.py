@@ -135,9 +135,8 @@ class TensorShape:
 
         aa = cfg.get('solver', 'anti-alias', 'none')
         self.antialias = {s.strip() for s in aa.split(',')} - {'none'}
-        if self.antialias - {'flux'}:
-            raise NotImplementedError('only flux anti-aliasing is within the '
-                                      'scope of this host mirror')
+        if self.antialias - {'flux', 'surf-flux'}:
+            raise ValueError('Invalid anti-alias options')
 
         n = self.order + 1
         urule = cfg.get(f'solver-elements-{self.name}', 'soln-pts')
@@ -187,6 +186,11 @@ class TensorShape:
         rule = self.cfg.get(sect, 'quad-pts', 'gauss-legendre')
 
         if self.cfg.hasopt(sect, 'quad-deg'):
+            # By degree alone the reference picks the smallest tabulated
+            # (non-tensor) rule; only named tensor rules are built here
+            if not self.cfg.hasopt(sect, 'quad-pts'):
+                raise NotImplementedError('quad-deg needs an explicit '
+                                          'tensor-product quad-pts rule')
             n = self.cfg.getint(sect, 'quad-deg')//2 + 1
         elif self.cfg.hasopt(sect, 'quad-npts'):
             n = round(self.cfg.getint(sect, 'quad-npts')**(1/self.ndims))
@@ -211,6 +215,42 @@ class TensorShape:
     def nqpts(self):
         return len(self.qpts)
 
+    # Surface-flux anti-aliasing: the flux points become the points of a
+    # face quadrature rule and the common flux is L2-projected back onto
+    # the face polynomials inside M3 (reference shapes.py:104-113,182-211)
+    @cached_property
+    def _fq1d(self):
+        fkind = 'line' if self.ndims == 2 else 'quad'
+        sect = f'solver-interfaces-{fkind}'
+        rule = self.cfg.get(sect, 'quad-pts', 'gauss-legendre')
+
+        if self.cfg.hasopt(sect, 'quad-deg'):
+            if fkind != 'line' and not self.cfg.hasopt(sect, 'quad-pts'):
+                raise NotImplementedError('quad-deg needs an explicit '
+                                          'tensor-product quad-pts rule')
+            n = self.cfg.getint(sect, 'quad-deg')//2 + 1
+        elif self.cfg.hasopt(sect, 'quad-npts'):
+            n = round(self.cfg.getint(sect, 'quad-npts')
+                      **(1/(self.ndims - 1)))
+        else:
+            n = self.order + 2
+
+        return _line_rules[rule](n)
+
+    @cached_property
+    def _face_proj(self):
+        """``(nfp, nq)``: values at the face quadrature points -> nodal
+        values at the regular flux points of the degree-p L2 projection."""
+        qx, qw = self._fq1d
+        psi_f = orthonormal_legendre(self.order, self._f1d)      # (nfp, nb)
+        psi_q = orthonormal_legendre(self.order, qx)             # (nq, nb)
+        p1 = psi_f @ (psi_q*qw[:, None]).T
+
+        p = p1
+        for _ in range(self.ndims - 2):
+            p = np.kron(p1, p)
+        return p
+
     @cached_property
     def _face_ref_pts(self):
         # Flux points and quadrature weights on the reference face
@@ -222,7 +262,10 @@ class TensorShape:
 
     @cached_property
     def fpts(self):
-        fp, _ = self._face_ref_pts
+        if 'surf-flux' in self.antialias:
+            fp = self._tensor_pts(self._fq1d[0], self.ndims - 1)
+        else:
+            fp, _ = self._face_ref_pts
         out = []
 
         for kind, proj, norm in self.faces:
@@ -233,7 +276,9 @@ class TensorShape:
 
     @cached_property
     def nfacefpts(self):
-        return [(self.order + 1)**(self.ndims - 1)]*len(self.faces)
+        n = (len(self._fq1d[0]) if 'surf-flux' in self.antialias else
+             self.order + 1)
+        return [n**(self.ndims - 1)]*len(self.faces)
 
     @property
     def nfpts(self):
@@ -355,6 +400,9 @@ class TensorShape:
             psi_q = self._ortho_at(vq)                  # (nq, nb)
             s = np.einsum('q,qf,qb->fb', qwts, lface, psi_q)
             blocks.append(psi_u @ s.T)                  # (nupts, nfp)
+
+        if 'surf-flux' in self.antialias:
+            blocks = [clean(b) @ self._face_proj for b in blocks]
 
         return clean(np.hstack(blocks))
 

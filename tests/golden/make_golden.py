@@ -70,6 +70,16 @@ HOST_CASES = {
                                                  'csubsz': 8}),
     'vortex_p3_fluxaa': ('vortex', 5, dict(order=3, antialias='flux'),
                          (1, 1), {}),
+    # surface-flux anti-aliasing (flux points on a face quadrature rule,
+    # projection folded into M3), alone and with the volume variant
+    'tgv_p2_surfaa': ('tgv', (3, 2, 2), dict(order=2, warp=0.1,
+                                             antialias='surf-flux'),
+                      (1, 1, 1), {}),
+    'vortex_p3_bothaa_2parts': ('vortex', (6, 4),
+                                dict(order=3, rsolver='hllc',
+                                     antialias='flux, surf-flux'),
+                                (2, 1), {'blocks': 1, 'soasz': 8,
+                                         'csubsz': 8}),
     # flux points coinciding with solution points (Gauss-Lobatto)
     'tgv_p3_gll_beta0_2parts': ('tgv', (4, 2, 2),
                                 dict(order=3, warp=0.1, beta=0.0,
