@@ -57,7 +57,40 @@ def translate(src):
     src = src.replace('#define UNROLL _Pragma("unroll")', '#define UNROLL')
 
     name, wrap = _wrapper(src)
-    return name, f'#include "{_here}/emu.h"\n{src}\n{wrap}'
+    return name, f'#include "{_header()}"\n{src}\n{wrap}'
+
+
+_flags = ['-std=c++17', '-O1', '-fPIC', '-pthread', '-w']
+
+
+def _header(tsan=None):
+    """The execution-model header, copied next to a precompiled form of
+    itself (parsing <thread>, <mutex>, ... is most of the compile time of a
+    small kernel).  Keyed by content and build flavour."""
+    if tsan is None:
+        tsan = bool(os.environ.get('PYFR_B200_EMU_TSAN'))
+
+    with open(os.path.join(_here, 'emu.h')) as f:
+        text = f.read()
+
+    key = hashlib.sha256(text.encode()).hexdigest()[:16]
+    os.makedirs(_cache, exist_ok=True)
+    hdr = os.path.join(_cache, f'emu-{key}{"-tsan" if tsan else ""}.h')
+
+    if not os.path.exists(hdr + '.gch'):
+        tmp = f'{hdr}.{os.getpid()}'
+        with open(tmp, 'w') as f:
+            f.write(text)
+        os.replace(tmp, hdr)
+
+        extra = ['-fsanitize=thread', '-g'] if tsan else []
+        res = subprocess.run(['g++', *_flags, *extra, '-x', 'c++-header',
+                              hdr, '-o', f'{tmp}.gch'],
+                             capture_output=True, text=True)
+        if res.returncode == 0:
+            os.replace(f'{tmp}.gch', hdr + '.gch')
+
+    return hdr
 
 
 def compile_source(src):
@@ -75,27 +108,49 @@ def compile_source(src):
         so = so[:-3] + '-tsan.so'
 
     if not os.path.exists(so):
-        cpp = so[:-3] + '.cpp'
+        import threading
+        uniq = f'{os.getpid()}-{threading.get_ident()}'
+        cpp = f'{so[:-3]}.{uniq}.cpp'
         with open(cpp, 'w') as f:
             f.write(text)
         res = subprocess.run(
-            ['g++', '-std=c++17', '-O1', '-shared', '-fPIC', '-pthread',
-             '-w', *(['-fsanitize=thread', '-g'] if tsan else []),
-             '-o', so + '.tmp', cpp], capture_output=True, text=True
+            ['g++', *_flags, '-shared',
+             *(['-fsanitize=thread', '-g'] if tsan else []),
+             '-o', f'{so}.{uniq}.tmp', cpp], capture_output=True, text=True
         )
         if res.returncode:
             raise RuntimeError(f'g++ failed for {name}:\n{res.stderr[:3000]}')
-        os.replace(so + '.tmp', so)
+        os.replace(f'{so}.{uniq}.tmp', so)
+        os.replace(cpp, so[:-3] + '.cpp')
 
     return so
 
 
+# A system creates all of its kernels before it launches any: compile them
+# concurrently and only wait for a shared object at its first launch
+_pool = None
+
+
 class _Module:
-    def __init__(self, so):
-        self.lib = ct.CDLL(so)
-        self.entry = self.lib.emu_entry
-        self.entry.restype = None
-        self.entry.argtypes = [ct.c_void_p] + [ct.c_uint]*6
+    def __init__(self, src):
+        global _pool
+        if _pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _pool = ThreadPoolExecutor(max_workers=os.cpu_count() or 4)
+
+        _header()                       # (precompiled once, not per worker)
+        self._fut = _pool.submit(compile_source, src)
+        self._entry = None
+
+    @property
+    def entry(self):
+        if self._entry is None:
+            self.lib = ct.CDLL(self._fut.result())
+            self._entry = self.lib.emu_entry
+            self._entry.restype = None
+            self._entry.argtypes = [ct.c_void_p] + [ct.c_uint]*6
+
+        return self._entry
 
 
 class EmuRuntime:
@@ -194,7 +249,7 @@ class EmuRuntime:
 
     # -- kernels --------------------------------------------------------------
     def module_load(self, image):
-        m = _Module(compile_source(bytes(image).decode()))
+        m = _Module(bytes(image).decode())
         self._mods.append(m)
         return m
 

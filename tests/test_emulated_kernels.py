@@ -584,13 +584,14 @@ def test_field_reductions_with_coordinates(emulated):
     assert res['oracle', 'min'][0] < res['oracle', 'max'][0]
 
 
-@pytest.mark.parametrize('case,n,kw,kind', [
-    ('tgv', (3, 2, 2), dict(order=2, warp=0.1), 'mul+negdivconf+rkvdh2'),
-    ('vortex', (4, 4), dict(order=3), 'fluxdiv+rkvdh2'),
+@pytest.mark.parametrize('case,n,kw,kind,errest', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1), 'mul+negdivconf+rkvdh2',
+     False),
+    ('vortex', (4, 4), dict(order=3), 'fluxdiv+rkvdh2', False),
+    ('vortex', (4, 4), dict(order=3), 'fluxdiv+rkvdh2', True),
     ('tgv', (3, 2, 2), dict(order=2, warp=0.1, curved=0.5),
-     'mul+negdivconf+rkvdh2'),
+     'mul+negdivconf+rkvdh2', True),
 ], ids=str)
-@pytest.mark.parametrize('errest', [False, True])
 def test_rk_stage_update_fused_into_last_rhs_kernel(emulated, case, n, kw,
                                                     kind, errest):
     """the rkvdh2 stage update applied in the epilogue of
@@ -703,13 +704,15 @@ def test_fused_stage_update_under_graphs(emulated):
     assert rel_err(sb, so) < 1e-12
 
 
-@pytest.mark.parametrize('case,n,kw', [
-    ('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
-    ('tgv', (3, 2, 2), dict(order=3, warp=0.1, beta=0.0, rsolver='hllc')),
-    ('tgv', (3, 2, 2), dict(order=2)),
-    ('vortex', 5, dict(order=3)),
+@pytest.mark.parametrize('case,n,kw,opts', [
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1), {}),
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1), {'fusion': 0}),
+    ('tgv', (3, 2, 2), dict(order=3, warp=0.1, beta=0.0, rsolver='hllc'),
+     {}),
+    ('tgv', (3, 2, 2), dict(order=2), {}),
+    ('vortex', 5, dict(order=3), {}),
+    ('vortex', 5, dict(order=3), {'fusion': 0}),
 ], ids=str)
-@pytest.mark.parametrize('opts', [{}, {'fusion': 0}], ids=['fused', 'nofuse'])
 def test_gauss_lobatto_points(emulated, case, n, kw, opts):
     """Flux points that coincide with solution points (SURVEY appendix B,
     hex GLL row): ``M0`` is a selection, the common solution lives in its
