@@ -52,57 +52,23 @@ CFL_CASES = [
 ]
 
 
-@pytest.mark.parametrize('case,n,kw', AA_CASES, ids=str)
-def test_flux_antialiasing_matches_oracle(built, case, n, kw):
-    cfg, box = cases.make(case, n, **kw)
-    sysm = _b200(cfg, box)
-    sysm.rhs(0.0, 0, 1)
-    sysm.backend.wait()
-    out = sysm.ele_scal_upts(1)[0]
-
-    _, ref = oracle_rhs(case, n, **kw)
-    _, ext = oracle_rhs(case, n, extended=True, **kw)
-
-    assert_parity(out, ref[0], ext[0], TOL64)
-    if 'surf-flux' not in kw['antialias']:
-        assert 'tflux' in _kinds(sysm) and 'gradflux' not in _kinds(sysm)
+MIXED_CASES = [
+    ('quad+tri', (12, 9), dict(order=3, rsolver='hllc')),
+    ('hex+pri', (4, 4, 3), dict(order=2, beta=0.0)),
+    ('hex+pri+pyr+tet', (4, 4, 3), dict(order=3)),
+]
 
 
-def test_sutherland_viscosity_matches_oracle(built):
-    _, n, kw = SUTHERLAND_CASE
-    cfg, box = cases.make('tgv', n, **kw)
-    sysm = _b200(cfg, box)
-    sysm.rhs(0.0, 0, 1)
-    sysm.backend.wait()
-    out = sysm.ele_scal_upts(1)[0]
-
-    _, ref = oracle_rhs('tgv', n, **kw)
-    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
-    _, const = oracle_rhs('tgv', n, **{**kw, 'visc_corr': 'none'})
-
-    assert 'gradflux' in _kinds(sysm)
-    assert_parity(out, ref[0], ext[0], TOL64)
-    assert rel_err(ref[0], const[0]) > 1e-7
+GLL_CASES = [
+    ('tgv', (4, 3, 3), dict(order=3, warp=0.1, pts='gauss-legendre-lobatto')),
+    ('tgv', (3, 3, 3), dict(order=2, beta=0.0, rsolver='hllc',
+                            pts='gauss-legendre-lobatto')),
+    ('vortex', 9, dict(order=3, pts='gauss-legendre-lobatto')),
+]
 
 
-def test_total_pressure_inflow_matches_oracle(built):
-    system, n, bcs, kw = FTPTTANG_CASE
-    outs = []
-    for which in ('oracle', 'oracle-ext', 'b200'):
-        cfg, box, _ = cases.box_case(system, n, bcs, **kw)
-        if which == 'b200':
-            sysm = _b200(cfg, box)
-        else:
-            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
-            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
-        sysm.rhs(0.5, 0, 1)
-        if which == 'b200':
-            sysm.backend.wait()
-        outs.append(sysm.ele_scal_upts(1)[0])
-
-    assert_parity(outs[2], outs[0], outs[1], TOL64)
-
-
+# Order: the simplest kernels first (the driver runs with -x: whatever comes
+# before a device-only failure still reports)
 def test_reduction_kernel(built):
     """sum / max of expressions with a scalar and per-variable constants;
     the padding columns of the ragged last block must not contribute."""
@@ -205,11 +171,69 @@ def test_wavespeed_and_cfl_controller_match_oracle(built, case, n, kw):
     assert rel_err(sb, so) < 1e-11
 
 
-MIXED_CASES = [
-    ('quad+tri', (12, 9), dict(order=3, rsolver='hllc')),
-    ('hex+pri', (4, 4, 3), dict(order=2, beta=0.0)),
-    ('hex+pri+pyr+tet', (4, 4, 3), dict(order=3)),
-]
+def test_sutherland_viscosity_matches_oracle(built):
+    _, n, kw = SUTHERLAND_CASE
+    cfg, box = cases.make('tgv', n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs('tgv', n, **kw)
+    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+    _, const = oracle_rhs('tgv', n, **{**kw, 'visc_corr': 'none'})
+
+    assert 'gradflux' in _kinds(sysm)
+    assert_parity(out, ref[0], ext[0], TOL64)
+    assert rel_err(ref[0], const[0]) > 1e-7
+
+
+def test_total_pressure_inflow_matches_oracle(built):
+    system, n, bcs, kw = FTPTTANG_CASE
+    outs = []
+    for which in ('oracle', 'oracle-ext', 'b200'):
+        cfg, box, _ = cases.box_case(system, n, bcs, **kw)
+        if which == 'b200':
+            sysm = _b200(cfg, box)
+        else:
+            cfg.set('backend-oracle', 'extended-mul', which != 'oracle')
+            sysm = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+        sysm.rhs(0.5, 0, 1)
+        if which == 'b200':
+            sysm.backend.wait()
+        outs.append(sysm.ele_scal_upts(1)[0])
+
+    assert_parity(outs[2], outs[0], outs[1], TOL64)
+
+
+@pytest.mark.parametrize('case,n,kw', GLL_CASES, ids=str)
+def test_gauss_lobatto_points_match_oracle(built, case, n, kw):
+    """Flux points coinciding with solution points (SURVEY appendix B)."""
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+    assert_parity(out, ref[0], ext[0], TOL64)
+
+
+@pytest.mark.parametrize('case,n,kw', AA_CASES, ids=str)
+def test_flux_antialiasing_matches_oracle(built, case, n, kw):
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    _, ext = oracle_rhs(case, n, extended=True, **kw)
+
+    assert_parity(out, ref[0], ext[0], TOL64)
+    if 'surf-flux' not in kw['antialias']:
+        assert 'tflux' in _kinds(sysm) and 'gradflux' not in _kinds(sysm)
 
 
 @pytest.mark.parametrize('pattern,n,kw', MIXED_CASES, ids=str)
@@ -273,25 +297,3 @@ def test_fused_rk_stage_update_matches_oracle(built, case, n, kw, kind):
         np.testing.assert_allclose([a[0] for a in i], [a[0] for a in io],
                                    rtol=1e-9)
         assert rel_err(s, so) < 1e-11
-
-
-GLL_CASES = [
-    ('tgv', (4, 3, 3), dict(order=3, warp=0.1, pts='gauss-legendre-lobatto')),
-    ('tgv', (3, 3, 3), dict(order=2, beta=0.0, rsolver='hllc',
-                            pts='gauss-legendre-lobatto')),
-    ('vortex', 9, dict(order=3, pts='gauss-legendre-lobatto')),
-]
-
-
-@pytest.mark.parametrize('case,n,kw', GLL_CASES, ids=str)
-def test_gauss_lobatto_points_match_oracle(built, case, n, kw):
-    """Flux points coinciding with solution points (SURVEY appendix B)."""
-    cfg, box = cases.make(case, n, **kw)
-    sysm = _b200(cfg, box)
-    sysm.rhs(0.0, 0, 1)
-    sysm.backend.wait()
-    out = sysm.ele_scal_upts(1)[0]
-
-    _, ref = oracle_rhs(case, n, **kw)
-    _, ext = oracle_rhs(case, n, extended=True, **kw)
-    assert_parity(out, ref[0], ext[0], TOL64)
