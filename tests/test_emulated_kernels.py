@@ -726,3 +726,20 @@ def test_gauss_lobatto_points(emulated, case, n, kw, opts):
     _, ref = oracle_rhs(case, n, **kw)
     _, ext = oracle_rhs(case, n, extended=True, **kw)
     assert_parity(out, ref[0], ext[0], 1e-12)
+
+
+def test_standalone_driver_rk45_cfl_fused(emulated, capsys):
+    """The combination the prepared GPU job times (tools/gpu/r02a.sh)."""
+    from pyfr_b200.__main__ import main
+
+    res = []
+    for extra in ([], ['--fused-update']):
+        main(['tgv', '--n', '2', '--order', '2', '--scheme', 'rk45', '--cfl',
+              '0.3', '--dt', '0.01', '--steps', '2', '--every', '2', *extra])
+        out = capsys.readouterr().out.splitlines()
+        res.append([l.split() for l in out if l and not l.startswith('#')])
+
+    assert res[0][-1][:2] == res[1][-1][:2]            # same steps, same time
+    np.testing.assert_allclose([float(v) for v in res[1][-1][2:]],
+                               [float(v) for v in res[0][-1][2:]],
+                               rtol=1e-12)
