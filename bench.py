@@ -45,8 +45,8 @@ def parse():
     ap.add_argument('--case', default='tgv',
                     choices=['tgv', 'hex+pri', 'hex+pri+pyr+tet'],
                     help='tgv: the headline workload; the others time '
-                    'BASELINE configs[3]-style mixed meshes of --n^3 cells on '
-                    'one GPU (device-resident figure only)')
+                    'BASELINE configs[3]-style mixed meshes of --n^3 cells per '
+                    'GPU (device-resident figure only)')
     ap.add_argument('--order', type=int, default=4)
     ap.add_argument('--precision', default='double')
     ap.add_argument('--rsolver', default='rusanov')
@@ -220,9 +220,10 @@ def workload_config(args):
                         f'cells of mixed type ({args.case}), p={args.order}, '
                         f'{"fp64" if args.precision == "double" else "fp32"}'
                         f', {args.rsolver}, one RHS evaluation per step',
-            'mesh': f'{args.n}^3 cells, one partition',
+            'mesh': f'{args.n}^3 cells per GPU, brick partition',
             'l2': 'inputs larger than L2 for n >= 32',
-            'parallelism': 'single GPU'
+            'parallelism': f'domain decomposition, {args.gpus} rank(s), NCCL '
+                           'send/recv halo exchange'
         }
 
     return {
@@ -267,10 +268,9 @@ def main():
                               order=args.order, precision=args.precision,
                               rsolver=args.rsolver)
     else:
-        if world > 1:
-            raise SystemExit('mixed-element cases run on one GPU')
         args.no_e2e = args.no_cpu = True
-        cfg, box, _ = cases.mixed_case(args.case, (args.n,)*3,
+        cfg, box, _ = cases.mixed_case(args.case,
+                                       tuple(args.n*p for p in parts),
                                        order=args.order,
                                        precision=args.precision,
                                        rsolver=args.rsolver)

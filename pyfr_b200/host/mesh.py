@@ -295,7 +295,7 @@ class MixedBoxMesh:
     (ditto, top and bottom pyramid cut into two tetrahedra each) in 3-D.
     Cells stacked in z must share their kind (``columns`` builds such
     arrays) so that neighbouring columns meet in whole quadrilaterals.
-    Single partition only."""
+    Partitions are bricks of cells (``brick_partition``)."""
 
     def __init__(self, kinds, h=1.0, warp=0.0):
         self.kinds = kinds = np.asarray(kinds, dtype=object)
@@ -303,7 +303,7 @@ class MixedBoxMesh:
         self.n, self.h, self.warp = kinds.shape, h, warp
         self.L = np.array(self.n, dtype=float)*h
 
-        verts = {}
+        verts, cells = {}, {}
         for idx in np.ndindex(*self.n):
             org = np.array(idx, dtype=float)
             for et, lists in _cell_elements(kinds[idx]).items():
@@ -312,6 +312,10 @@ class MixedBoxMesh:
                         [(org + 0.5 if isinstance(v, str) else
                           org + np.array(v))*h for v in vl]
                     )
+                    cells.setdefault(et, []).append(idx)
+
+        # Cell (i, j[, k]) of every element
+        self._cell = {et: np.array(c) for et, c in cells.items()}
 
         self.etypes = etypes = sorted(verts)
         # (nverts, neles, ndims), unwarped: face pairing works on these
@@ -367,37 +371,120 @@ class MixedBoxMesh:
 
         return np.ascontiguousarray(x)
 
-    def local_mesh(self, vparts=None, rank=0):
-        if vparts is not None and np.any(np.asarray(vparts) != 0):
-            raise NotImplementedError('partitioned mixed meshes')
+    def brick_partition(self, parts):
+        """``{etype: partition of each element}`` for ``prod(parts)`` equal
+        bricks of cells."""
+        parts = tuple(parts)
+        if any(n % p for n, p in zip(self.n, parts)):
+            raise ValueError('Brick partition must divide the box')
 
-        mesh = Mesh(ndims=self.ndims, codec=self.codec,
-                    etypes=list(self.etypes), cidxmap=self.cidxmap,
-                    uuid='mixed')
+        out = {}
+        for et, c in self._cell.items():
+            pid, mul = np.zeros(len(c), dtype=np.int32), 1
+            for ax, p in enumerate(parts):
+                pid += mul*(c[:, ax] // (self.n[ax] // p))
+                mul *= p
+            out[et] = pid
+
+        return out
+
+    def partition_order(self, vparts):
+        """Per rank and element type, the global element numbers in storage
+        order: partition-boundary elements first, then by number
+        (pyfr/partitioners/base.py:286-290)."""
+        nparts = max(int(v.max()) for v in vparts.values()) + 1
+        etidx = {self.codec.index(f'eles/{et}/face/{f}'): et
+                 for et in self.etypes
+                 for f in range(self.faces[et].shape[1])}
+
+        order = [{} for _ in range(nparts)]
+        for et in self.etypes:
+            fc = self.faces[et]
+            nbp = np.empty(fc.shape[:2], dtype=np.int32)
+            for f in range(fc.shape[1]):
+                for c in np.unique(fc[:, f, 0]):
+                    sel = fc[:, f, 0] == c
+                    nbp[sel, f] = vparts[etidx[c]][fc[sel, f, 1]]
+
+            internal = np.all(nbp == vparts[et][:, None], axis=1)
+            idx = np.lexsort((internal, vparts[et]))
+            bounds = np.searchsorted(vparts[et][idx], np.arange(nparts + 1))
+            for p in range(nparts):
+                if bounds[p + 1] > bounds[p]:
+                    order[p][et] = idx[bounds[p]:bounds[p + 1]]
+
+        return order
+
+    def local_mesh(self, vparts=None, rank=0):
+        if vparts is None:
+            vparts = {et: np.zeros(self._x0[et].shape[1], dtype=np.int32)
+                      for et in self.etypes}
+
+        gidx = self.partition_order(vparts)[rank]
+        etypes = [et for et in self.etypes if et in gidx]
+        etof = {c: et for c, (et, f) in self.cidxmap.items()}
+
+        mesh = Mesh(ndims=self.ndims, codec=self.codec, etypes=etypes,
+                    cidxmap=self.cidxmap, uuid='mixed')
+
+        g2l = {}
+        for et in etypes:
+            g = gidx[et]
+            mesh.eidxs[et] = g
+            mesh.spts[et] = self.vertices(et)[:, g]
+            mesh.spts_curved[et] = np.zeros(len(g), dtype=bool)
+            g2l[et] = np.full(self._x0[et].shape[1], -1, dtype=np.int64)
+            g2l[et][g] = np.arange(len(g))
 
         # Flatten: type by type, face by face, element by element
         # (pyfr/readers/native.py:430-443)
         parts = []
-        for et in self.etypes:
-            ne = self._x0[et].shape[1]
-            mesh.eidxs[et] = np.arange(ne)
-            mesh.spts[et] = self.vertices(et)
-            mesh.spts_curved[et] = np.zeros(ne, dtype=bool)
-
+        for et in etypes:
+            g, ne = gidx[et], len(gidx[et])
             for f in range(self.faces[et].shape[1]):
                 lc = self.codec.index(f'eles/{et}/face/{f}')
-                parts.append((np.full(ne, lc), np.arange(ne),
-                              self.faces[et][:, f, 0],
-                              self.faces[et][:, f, 1]))
+                parts.append((np.full(ne, lc), np.arange(ne), g,
+                              self.faces[et][g, f, 0],
+                              self.faces[et][g, f, 1]))
 
-        lcidx, leidx, rcidx, reidx = map(np.concatenate, zip(*parts))
+        lcidx, leidx, lgidx, rcidx, rgidx = map(np.concatenate, zip(*parts))
+
+        # Neighbour's partition and (where it is ours) local number
+        rpart = np.empty(len(rcidx), dtype=np.int32)
+        reidx = np.full(len(rcidx), -1, dtype=np.int64)
+        for c in np.unique(rcidx):
+            sel, net = rcidx == c, etof[c]
+            rpart[sel] = vparts[net][rgidx[sel]]
+            if net in g2l:
+                reidx[sel] = g2l[net][rgidx[sel]]
+
+        is_loc = reidx >= 0
 
         # Interior faces once, smaller (cidx, element) key on the left
-        stride = max(leidx.max(), reidx.max()) + 1
-        keep = np.flatnonzero(lcidx*stride + leidx < rcidx*stride + reidx)
+        stride = max(leidx[is_loc].max(initial=-1),
+                     reidx[is_loc].max(initial=-1)) + 1
+        lkey = lcidx[is_loc]*stride + leidx[is_loc]
+        rkey = rcidx[is_loc]*stride + reidx[is_loc]
+        keep = np.flatnonzero(is_loc)[lkey < rkey]
 
         mesh.con = (Connectivity(lcidx[keep], leidx[keep], self.cidxmap),
                     Connectivity(rcidx[keep], reidx[keep], self.cidxmap))
+
+        # Inter-partition faces: both sides sort on the lower rank's
+        # (cidx, global element) key (pyfr/readers/native.py:518-521)
+        m = np.flatnonzero(~is_loc)
+        gstride = max(x.shape[1] for x in self._x0.values())
+        for p in np.unique(rpart[m]):
+            ix = m[rpart[m] == p]
+
+            if rank < p:
+                key = rcidx[ix]*gstride + rgidx[ix]
+            else:
+                key = lcidx[ix]*gstride + lgidx[ix]
+
+            ix = ix[np.argsort(key, kind='stable')]
+            mesh.con_p[int(p)] = Connectivity(lcidx[ix], leidx[ix],
+                                              self.cidxmap)
 
         return mesh
 

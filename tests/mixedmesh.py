@@ -154,3 +154,103 @@ def columns(nx, ny, nz, pattern):
     k2 = np.array([[pattern[(i + 2*j) % len(pattern)] for j in range(ny)]
                    for i in range(nx)], dtype=object)
     return k2 if nz is None else np.repeat(k2[:, :, None], nz, axis=2)
+
+
+def ref_partitioned_con(box, vparts):
+    """Interior and inter-partition connectivity of every rank of a
+    partitioned ``pyfr_b200.host.mesh.MixedBoxMesh``, derived by the
+    reference's ``NativeReader._construct_con`` -- every rank in a thread
+    with an in-process stand-in for the MPI neighbourhood collectives (as
+    tests/golden/make_golden.py does for the hex boxes).  Returns one
+    namespace per rank with ``eidxs``, ``con`` and ``con_p``."""
+    import threading
+
+    rh.install_stubs()
+    import pyfr.readers.native as rnative
+
+    order = box.partition_order(vparts)
+    nparts = len(order)
+    etof = {c: et for c, (et, f) in box.cidxmap.items()}
+
+    tls = threading.local()
+    barrier = threading.Barrier(nparts)
+    mail = {}
+
+    class NComm:
+        handle = 0
+
+        def __init__(self, nbrs):
+            self.nbrs = nbrs
+
+        @staticmethod
+        def fromhandle(h):
+            return SimpleNamespace(free=lambda: None)
+
+        def neighbor_allgather(self, obj):
+            mail['g', tls.rank] = obj
+            barrier.wait()
+            out = [mail['g', p] for p in self.nbrs]
+            barrier.wait()
+            return out
+
+        def neighbor_alltoall(self, objs):
+            for p, o in zip(self.nbrs, objs):
+                mail['a', tls.rank, p] = o
+            barrier.wait()
+            out = [mail['a', p, tls.rank] for p in self.nbrs]
+            barrier.wait()
+            return out
+
+    class Comm:
+        def Create_dist_graph_adjacent(self, src, dst):
+            return NComm(list(src))
+
+    orig = rnative.get_comm_rank_root
+    rnative.get_comm_rank_root = lambda: (Comm(), tls.rank, 0)
+
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            tls.rank = rank
+            gidx = order[rank]
+            eles, nbrs = {}, set()
+
+            for et, g in gidx.items():
+                fc = box.faces[et][g]
+                faces = np.empty(fc.shape[:2], dtype=[('cidx', np.int16),
+                                                      ('off', np.int64)])
+                faces['cidx'], faces['off'] = fc[..., 0], fc[..., 1]
+                eles[et] = {'faces': faces}
+
+                for c in np.unique(fc[..., 0]):
+                    sel = fc[..., 0] == c
+                    nbrs |= set(vparts[etof[c]][fc[..., 1][sel]].tolist())
+
+            rd = rnative.NativeReader.__new__(rnative.NativeReader)
+            rd.mesh = SimpleNamespace(codec=list(box.codec),
+                                      etypes=list(box.etypes),
+                                      eidxs=dict(gidx), bcon={}, con_p={})
+            rd.eles = eles
+            rd.f = {f'eles/{et}': np.empty(box._x0[et].shape[1])
+                    for et in box.etypes}
+            rd.neighbours = sorted(nbrs - {rank})
+            rd._construct_con()
+            results[rank] = rd.mesh
+        except Exception as e:                          # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(nparts)]
+    try:
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        rnative.get_comm_rank_root = orig
+
+    if errors:
+        raise errors[0]
+
+    return [results[r] for r in range(nparts)]

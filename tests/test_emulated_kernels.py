@@ -743,3 +743,51 @@ def test_standalone_driver_rk45_cfl_fused(emulated, capsys):
     np.testing.assert_allclose([float(v) for v in res[1][-1][2:]],
                                [float(v) for v in res[0][-1][2:]],
                                rtol=1e-12)
+
+
+@pytest.mark.parametrize('pattern,n,parts,kw', [
+    ('quad+tri', (4, 4), (2, 2), dict(order=3)),
+    ('hex+pri+pyr+tet', (4, 2, 2), (2, 1, 1), dict(order=2, beta=0.0)),
+], ids=str)
+def test_partitioned_mixed_mesh(emulated, pattern, n, parts, kw):
+    """Mixed element types across partitions: halo views over several
+    element types, on the oracle (against the unpartitioned run: with a
+    central LDG flux or none at all the RHS does not depend on the
+    partitioning) and through the generated kernels."""
+    from oracle.npbackend import LocalComm
+    from util import run_lockstep
+
+    nparts = int(np.prod(parts))
+    cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+    vparts = box.brick_partition(parts)
+    order = box.partition_order(vparts)
+
+    # unpartitioned oracle
+    whole = get_system(OracleBackend(cfg), box.local_mesh(), cfg, 2)
+    whole.rhs(0.0, 0, 1)
+    wrhs = dict(zip(box.etypes, whole.ele_scal_upts(1)))
+
+    # partitioned oracle
+    lworld = LocalComm(0, nparts)
+    osys = []
+    for r in range(nparts):
+        cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+        osys.append(get_system(OracleBackend(cfg), box.local_mesh(vparts, r),
+                               cfg, 2, comm=lworld.peer(r)))
+    run_lockstep(osys, lworld, 0.0, 0, 1)
+
+    # partitioned, generated kernels
+    eworld = EmuWorld(nparts)
+    bsys = []
+    for r in range(nparts):
+        cfg, box, _ = cases.mixed_case(pattern, n, **kw)
+        bsys.append(_b200(cfg, box, vparts, r, comm=eworld.peer(r)))
+    run_lockstep(bsys, eworld, 0.0, 0, 1)
+
+    scale = max(np.abs(a).max() for a in wrhs.values())
+    for r in range(nparts):
+        ets = [et for et in box.etypes if et in order[r]]
+        for et, o, b in zip(ets, osys[r].ele_scal_upts(1),
+                            bsys[r].ele_scal_upts(1)):
+            assert np.abs(o - wrhs[et][..., order[r][et]]).max() < 1e-12*scale
+            assert np.abs(b - o).max() < 1e-12*scale
