@@ -1,0 +1,117 @@
+"""Property tests of the storage layout and view index arithmetic
+("int -- must be bit-exact"): the contract
+mirror ``pyfr_b200.base`` against the reference's own
+``pyfr.backends.base`` on random shapes, SoA widths, block sizes and view
+maps.  Both are instantiated over the NumPy oracle storage, so raw bytes,
+``get()`` round trips and the ``mapping`` / ``rstrides`` arrays handed to
+kernels can be compared directly.  Needs /root/reference."""
+
+import os
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import refharness as rh
+from oracle.npbackend import make_backend
+from pyfr_b200 import base
+from pyfr_b200.host.config import Config
+
+pytestmark = pytest.mark.skipif(not rh.available(),
+                                reason='needs /root/reference')
+
+
+def _backends(soasz, csubsz, blocks):
+    rh.install_stubs()
+    import pyfr.backends.base as rbase
+    from pyfr.inifile import Inifile
+
+    txt = (f'[backend]\nprecision = double\n[backend-oracle]\n'
+           f'soasz = {soasz}\ncsubsz = {csubsz}\nblocks = {int(blocks)}\n')
+    return (make_backend(rbase, name='oracle-ref')(Inifile(txt)),
+            make_backend(base)(Config(txt)))
+
+
+layout = st.tuples(st.sampled_from([2, 4, 8, 16]), st.integers(1, 4),
+                   st.booleans())
+
+
+@settings(max_examples=60, deadline=None,
+          suppress_health_check=[HealthCheck.too_slow])
+@given(layout=layout, nrow=st.integers(1, 9), nvars=st.integers(1, 5),
+       neles=st.integers(1, 70), seed=st.integers(0, 2**31))
+def test_matrix_layout_matches_reference(layout, nrow, nvars, neles, seed):
+    soasz, mult, blocks = layout
+    rbe, mbe = _backends(soasz, soasz*mult, blocks)
+    ary = np.random.default_rng(seed).standard_normal((nrow, nvars, neles))
+
+    mats = []
+    for be in (rbe, mbe):
+        m = be.matrix((nrow, nvars, neles), ary, tags={'align'})
+        x = be.xchg_matrix((nvars, neles), ary[0])
+        c = be.const_matrix(ary[:, 0], tags={'align'})
+        be.commit()
+        mats.append((m, x, c))
+
+    for r, m in zip(*mats):
+        for a in ('nrow', 'ncol', 'leaddim', 'nblocks', 'blocksz', 'nbytes',
+                  'datashape', 'ioshape', 'itemsize'):
+            assert getattr(r, a) == getattr(m, a), a
+        assert tuple(r.traits) == tuple(m.traits)
+        assert np.array_equal(r.data, m.data)            # raw storage image
+        assert np.array_equal(r.get(), m.get())
+
+    # row slices address the same storage
+    (rm, *_), (mm, *_) = mats
+    ra, rb = sorted(np.random.default_rng(seed + 1).integers(0, nrow + 1, 2))
+    if rb > ra:
+        rs, ms = rm.slice(ra, rb), mm.slice(ra, rb)
+        assert (rs.offset, rs.nrow, rs.ncol) == (ms.offset, ms.nrow, ms.ncol)
+
+
+@settings(max_examples=60, deadline=None,
+          suppress_health_check=[HealthCheck.too_slow])
+@given(layout=layout, nrow=st.integers(2, 9), nvars=st.integers(1, 5),
+       neles=st.integers(1, 70), n=st.integers(1, 40), nvrow=st.integers(1, 3),
+       seed=st.integers(0, 2**31))
+def test_view_indices_match_reference(layout, nrow, nvars, neles, n, nvrow,
+                                      seed):
+    """``View.mapping`` / ``rstrides`` (pyfr/backends/base/types.py:
+    294-320) and the packed layout of an exchange view, over two matrices
+    in one extent."""
+    soasz, mult, blocks = layout
+    rbe, mbe = _backends(soasz, soasz*mult, blocks)
+    rng = np.random.default_rng(seed)
+
+    nvrow = min(nvrow, nrow)
+    which = rng.integers(0, 2, n)
+    rmap = rng.integers(0, nrow - nvrow + 1, n)
+    cmap = rng.integers(0, neles, n)
+    # row strides that keep every view row inside the matrix
+    rmax = np.maximum((nrow - 1 - rmap)//max(nvrow - 1, 1), 1)
+    rstri = 1 + rng.integers(0, 1 << 30, n) % rmax
+
+    out = []
+    for be in (rbe, mbe):
+        ms = [be.matrix((nrow, nvars, neles), extent='shared',
+                        tags={'align'}) for _ in range(2)]
+        be.commit()
+        matmap = np.array([ms[w].mid for w in which])
+
+        vshape = (nvrow, nvars) if nvrow > 1 else (nvars,)
+        kw = dict(rstridemap=rstri) if nvrow > 1 else {}
+        v = be.view(matmap, rmap, cmap, vshape=vshape, **kw)
+        xv = be.xchg_view(matmap, rmap, cmap, vshape=vshape, **kw)
+        be.commit()
+
+        # matrix ids differ between the two backends: compare offsets
+        # relative to the first matrix of the extent
+        out.append((v.mapping.get() - ms[0].offset//ms[0].itemsize,
+                    v.rstrides.get() if nvrow > 1 else None,
+                    (xv.xchgmat.nrow, xv.xchgmat.ncol, xv.xchgmat.leaddim),
+                    (v.n, v.nvrow, v.nvcol)))
+
+    (rmapg, rstr, rx, rv), (mmapg, mstr, mx, mv) = out
+    assert np.array_equal(rmapg, mmapg)
+    assert (rstr is None and mstr is None) or np.array_equal(rstr, mstr)
+    assert rx == mx and rv == mv
