@@ -115,3 +115,36 @@ def test_view_indices_match_reference(layout, nrow, nvars, neles, n, nvrow,
     assert np.array_equal(rmapg, mmapg)
     assert (rstr is None and mstr is None) or np.array_equal(rstr, mstr)
     assert rx == mx and rv == mv
+
+
+@settings(max_examples=80, deadline=None)
+@given(n=st.integers(1, 60), ndims=st.integers(1, 3),
+       ngrid=st.integers(1, 6), seed=st.integers(0, 2**31))
+def test_fuzzy_sort_and_clean_match_reference(n, ndims, ngrid, seed):
+    """``fuzzy_lexsort`` (flux-point ordering agreed by both sides of an
+    interface) against ``pyfr.nputil.fuzzysort`` on point clouds with many
+    nearly-coincident coordinates, and ``clean`` (constants snapped before
+    they are baked into kernels) against ``pyfr.nputil.clean``."""
+    rh.install_stubs()
+    from pyfr.nputil import batched_fuzzysort, clean as rclean
+
+    from pyfr_b200.host.elements import fuzzy_lexsort
+    from pyfr_b200.host.shapes import clean
+
+    rng = np.random.default_rng(seed)
+
+    # points on a coarse lattice plus round-off sized noise: ties in the
+    # leading coordinates must be broken by the later ones
+    pts = rng.integers(0, ngrid, (n, ndims)).astype(float)
+    pts += 1e-12*rng.standard_normal(pts.shape)
+    _, ix = np.unique(np.round(pts, 6), axis=0, return_index=True)
+    pts = pts[np.sort(ix)]                      # distinct lattice sites
+
+    # (neles, ndims, npts): the same cloud seen by three elements, two of
+    # them with their own round-off
+    coords = np.stack([pts.T, pts.T + 1e-13, pts.T[:, ::-1]])
+    assert np.array_equal(fuzzy_lexsort(coords), batched_fuzzysort(coords))
+
+    a = rng.choice([0.0, 1e-13, 0.5, -0.5, 0.5 + 1e-12, 1/3, -1/3 + 2e-13,
+                    2.0, rng.standard_normal()], size=(n, 3))
+    assert np.array_equal(clean(a), rclean(lambda: a)())
