@@ -148,3 +148,68 @@ def test_fuzzy_sort_and_clean_match_reference(n, ndims, ngrid, seed):
     a = rng.choice([0.0, 1e-13, 0.5, -0.5, 0.5 + 1e-12, 1/3, -1/3 + 2e-13,
                     2.0, rng.standard_normal()], size=(n, 3))
     assert np.array_equal(clean(a), rclean(lambda: a)())
+
+
+@settings(max_examples=120, deadline=None)
+@given(nk=st.integers(1, 14), seed=st.integers(0, 2**31))
+def test_graph_schedule_matches_reference(nk, seed):
+    """Row a20: the kernel order a graph commits to -- dependency DAG,
+    kernels an exchange send waits on scheduled first, grouped kernels kept
+    together (pyfr/backends/base/types.py:343-533) -- on random graphs:
+    random hard / pseudo dependencies, sends hanging off random kernels,
+    receives, random contiguous groups."""
+    rh.install_stubs()
+    import pyfr.backends.base as rbase
+
+    rng = np.random.default_rng(seed)
+    deps = [sorted(rng.choice(i, rng.integers(0, min(i, 3) + 1),
+                              replace=False).tolist()) if i else []
+            for i in range(nk)]
+    pdeps = [sorted(rng.choice(i, rng.integers(0, 2), replace=False).tolist())
+             if i else [] for i in range(nk)]
+    sends = [sorted(rng.choice(nk, min(nk, int(rng.integers(1, 3))),
+                               replace=False).tolist())
+             for _ in range(rng.integers(0, 3))]
+    nrecv = int(rng.integers(0, 3))
+
+    # groups: chains k -> k+1 (-> k+2) where each member depends on the one
+    # before it, as the solvers hand them over
+    groups, used, i = [], set(), 0
+    while i < nk - 1:
+        glen = int(rng.integers(1, 4))
+        g = list(range(i, min(i + glen, nk)))
+        if len(g) > 1 and rng.random() < 0.5:
+            for a, b in zip(g, g[1:]):
+                if a not in deps[b]:
+                    deps[b] = sorted(deps[b] + [a])
+            groups.append(g)
+        i += glen
+
+    programs = []
+    for b in (rbase, base):
+        be = make_backend(b)(Config('[backend]\nprecision = double\n')
+                             if b is base else
+                             __import__('pyfr.inifile').inifile.Inifile(
+                                 '[backend]\nprecision = double\n'))
+        ks = [be.kernel_cls(lambda: None) for _ in range(nk)]
+        label = {id(k): f'k{i}' for i, k in enumerate(ks)}
+
+        class Req:
+            def __init__(self, name):
+                self.name = name
+
+        g = be.graph()
+        g.add_mpi_reqs([Req(f'r{j}') for j in range(nrecv)])
+        for i, k in enumerate(ks):
+            g.add(k, deps=[ks[d] for d in deps[i]],
+                  pdeps=[ks[d] for d in pdeps[i]])
+        for j, sd in enumerate(sends):
+            g.add_mpi_req(Req(f's{j}'), deps=[ks[d] for d in sd])
+        for grp in groups:
+            g.group([ks[i] for i in grp])
+        g.commit()
+
+        programs.append([label[id(o)] if w == 'kernel' else o.name
+                         for w, o in g.program])
+
+    assert programs[0] == programs[1]
