@@ -180,3 +180,117 @@ def test_interface_kernels_match_reference_templates(cflux_lib, i):
         want = np.array([f[0] for f in fn])
         _close(out['ul'], want)
         _close(out['ur'], -want)
+
+
+# -- boundary kernels ------------------------------------------------------------
+def _record_bc_tplargs(system, n, bcs, edits=(), **kw):
+    """The template arguments the host code hands to the boundary kernels
+    (section constants compiled to C expressions included)."""
+    from pyfr_b200 import cases
+    from pyfr_b200.host.system import get_system
+    from util import OracleBackend
+
+    cfg, box, _ = cases.box_case(system, n, bcs, **kw)
+    for sect, opt, val in edits:
+        cfg.set(sect, opt, val)
+
+    be = OracleBackend(cfg)
+    seen, orig = [], be.kernel
+
+    def kernel(name, *a, **k):
+        if name in ('bcconu', 'bccflux'):
+            seen.append((name, k['tplargs']))
+        return orig(name, *a, **k)
+
+    be.kernel = kernel
+    get_system(be, box.local_mesh(), cfg, 2)
+    return seen
+
+
+BC_SETS = [
+    ('navier-stokes', (2, 2, 2),
+     {'xlo': 'sub-in-frv', 'xhi': 'sub-out-fp', 'ylo': 'no-slp-adia-wall',
+      'yhi': 'char-riem-inv', 'zlo': 'slp-adia-wall',
+      'zhi': 'no-slp-isot-wall'},
+     [('soln-bcs-xlo', 'u', '0.2 + 0.1*sin(3*t) + 0.05*y'),
+      ('soln-bcs-zhi', 'u', '0.1 + 0.02*x*cos(t)')],
+     dict(order=1, rsolver='hllc', beta=0.0)),
+    ('navier-stokes', (2, 2, 2),
+     {'xlo': 'sub-in-ftpttang', 'xhi': 'sup-out-fn', 'ylo': 'sup-in-fa',
+      'yhi': 'sub-out-fp'},
+     [('soln-bcs-yhi', 'p', '71.0 + 0.5*cos(t)')],
+     dict(order=1)),
+    ('euler', (2, 2),
+     {'xlo': 'char-riem-inv', 'xhi': 'sup-out-fn', 'ylo': 'slp-adia-wall',
+      'yhi': 'sup-in-fa'},
+     [('soln-bcs-yhi', 'rho', '1.0 + 0.1*x*t')], dict(order=1)),
+]
+
+
+def _bc_kernels():
+    out = []
+    for system, n, bcs, edits, kw in BC_SETS:
+        for name, tpl in _record_bc_tplargs(system, n, bcs, edits, **kw):
+            out.append((system, name, tpl))
+    return out
+
+
+@pytest.fixture(scope='module')
+def bc_lib():
+    lib, specs = CLib(), _bc_kernels()
+    for i, (system, name, tpl) in enumerate(specs):
+        nd = tpl['ndims']
+        sysmod = 'navstokes' if system == 'navier-stokes' else 'euler'
+        from oracle.minimako import Renderer
+
+        r = Renderer(tpl, extrns=('t', 'ploc'))
+        r.include(f'pyfr.solvers.{sysmod}.kernels.{name}')
+        attrs, body = r.kernels[name]
+        args = {a: _spec(v) for a, v in attrs.items()}
+        args['ploc'], args['t'] = ('in', (nd,)), ('in', ())
+        lib.add(f'bc_{i}', args, body)
+    return lib.build(), specs
+
+
+def test_boundary_kernels_match_reference_templates(bc_lib):
+    lib, specs = bc_lib
+    types = set()
+
+    for i, (system, name, tpl) in enumerate(specs):
+        nd, nv, c = tpl['ndims'], tpl['nvars'], tpl['c']
+        viscous = system == 'navier-stokes'
+        rng = np.random.default_rng(500 + i)
+        types.add(tpl['bctype'])
+
+        for _ in range(12):
+            # mean flow through the face: keeps the states away from the
+            # sign switches of the characteristic conditions
+            ul = _state(rng, nd, mach=0.2)
+            gl = rng.standard_normal((nd, nv))
+            nl = rng.standard_normal(nd)
+            ploc, t = rng.standard_normal(nd), float(rng.random())
+            env = {'t': t, 'ploc': _cols(ploc)}
+
+            if name == 'bcconu':
+                out = lib.call(f'bc_{i}', ulin=ul, ulout=np.zeros(nv),
+                               nlin=nl, ploc=ploc, t=t)
+                mag = np.sqrt(nl @ nl)
+                want = ph.bc_ldg_state(tpl['bctype'], _cols(ul),
+                                       _cols(nl/mag), nd, nv, c, env)
+                _close(out['ulout'], [np.ravel(x)[0] for x in want])
+            else:
+                kw = dict(ul=ul, nl=nl, ploc=ploc, t=t)
+                if viscous:
+                    kw.update(gradul=gl, artvisc=0.0)
+                out = lib.call(f'bc_{i}', **kw)
+                want = ph.bc_common_flux(
+                    tpl['bctype'], tpl.get('bccfluxstate'), _cols(ul),
+                    [_cols(g) for g in gl] if viscous else None, _cols(nl),
+                    nd, nv, c, tpl['rsolver'], env, viscous,
+                    tpl.get('visc_corr', 'none')
+                )
+                _close(out['ul'], [np.ravel(x)[0] for x in want])
+
+    assert types >= {'no-slp-adia-wall', 'no-slp-isot-wall', 'slp-adia-wall',
+                     'char-riem-inv', 'sup-in-fa', 'sup-out-fn', 'sub-in-frv',
+                     'sub-out-fp', 'sub-in-ftpttang'}
