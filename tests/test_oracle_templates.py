@@ -52,16 +52,16 @@ class CLib:
         for i, (a, (intent, dims)) in enumerate(args.items()):
             if dims:
                 shp = ''.join(f'[{d}]' for d in dims)
-                pre.append(f'fpdtype_t {a}{shp}; memcpy({a}, p[{i}], '
+                pre.append(f'fpdtype_t {a}{shp}; memcpy({a}, _argv[{i}], '
                            f'sizeof({a}));')
                 if 'out' in intent:
-                    post.append(f'memcpy(p[{i}], {a}, sizeof({a}));')
+                    post.append(f'memcpy(_argv[{i}], {a}, sizeof({a}));')
             else:
-                pre.append(f'fpdtype_t {a} = *p[{i}];')
+                pre.append(f'fpdtype_t {a} = *_argv[{i}];')
                 if 'out' in intent:
-                    post.append(f'*p[{i}] = {a};')
+                    post.append(f'*_argv[{i}] = {a};')
 
-        self.src.append(f'void {name}(double **p)\n{{\n' + '\n'.join(pre) +
+        self.src.append(f'void {name}(double **_argv)\n{{\n' + '\n'.join(pre) +
                         f'\n{body}\n' + '\n'.join(post) + '\n}\n')
         self.fns[name] = args
 
@@ -294,3 +294,294 @@ def test_boundary_kernels_match_reference_templates(bc_lib):
     assert types >= {'no-slp-adia-wall', 'no-slp-isot-wall', 'slp-adia-wall',
                      'char-riem-inv', 'sup-in-fa', 'sup-out-fn', 'sub-in-frv',
                      'sub-out-fp', 'sub-in-ftpttang'}
+
+
+# -- element kernels (through the oracle backend's kernel objects) --------------
+ELE = [(nd, ktype, vc) for nd in (2, 3)
+       for ktype, vc in [('curved', 'none'), ('linear', 'sutherland'),
+                         ('curved-fused', 'sutherland'),
+                         ('linear-fused', 'none')]]
+
+
+def _ref_jac_exprs(nd):
+    rh.install_stubs()
+    from pyfr.shapes import HexShape, QuadShape
+    return (QuadShape if nd == 2 else HexShape).jac_exprs
+
+
+@pytest.fixture(scope='module')
+def ele_lib():
+    lib = CLib()
+    for i, (nd, ktype, vc) in enumerate(ELE):
+        tpl = dict(ndims=nd, nvars=nd + 2, nverts=2**nd, c=dict(CONSTS),
+                   jac_exprs=_ref_jac_exprs(nd), ktype=ktype, visc_corr=vc,
+                   shock_capturing='none', src_macros=[])
+        _kernel(lib, f'ns_tflux_{i}', 'pyfr.solvers.navstokes.kernels.tflux',
+                'tflux', tpl)
+        if 'fused' not in ktype:
+            _kernel(lib, f'eu_tflux_{i}', 'pyfr.solvers.euler.kernels.tflux',
+                    'tflux', tpl)
+            _kernel(lib, f'gradcoru_{i}',
+                    'pyfr.solvers.baseadvecdiff.kernels.gradcoru', 'gradcoru',
+                    tpl)
+            _kernel(lib, f'wavespeed_{i}',
+                    'pyfr.solvers.euler.kernels.wavespeed', 'wavespeed', tpl)
+    _kernel(lib, 'negdivconf', 'pyfr.solvers.baseadvec.kernels.negdivconf',
+            'negdivconf', dict(ndims=3, nvars=5, src_macros=[], c=CONSTS),
+            extrns=('t', 'ploc', 'u'))
+    return lib.build()
+
+
+@pytest.mark.parametrize('i', range(len(ELE)))
+def test_element_kernels_match_reference_templates(ele_lib, i):
+    """tflux (Navier-Stokes and Euler, stored and vertex-derived metric
+    terms, with and without the fused gradient transform), gradcoru and
+    wavespeed: the oracle backend's kernels, run on its blocked storage
+    over K one-point elements, against the rendered templates point by
+    point."""
+    from pyfr_b200.host.config import Config
+    from util import OracleBackend
+
+    nd, ktype, vc = ELE[i]
+    nv, nverts, K = nd + 2, 2**nd, 21
+    linear, fused = 'linear' in ktype, 'fused' in ktype
+    rng = np.random.default_rng(900 + i)
+    jac = _ref_jac_exprs(nd)
+    tpl = dict(ndims=nd, nvars=nv, nverts=nverts, c=dict(CONSTS),
+               jac_exprs=jac, ktype=ktype, visc_corr=vc,
+               shock_capturing='none', src_macros=[])
+
+    # Random well-conditioned inputs
+    u = np.stack([_state(rng, nd) for _ in range(K)], axis=-1)[None]
+    g = rng.standard_normal((nd, 1, nv, K))
+    ref = np.array([[-1.0, 1.0][(n >> d) & 1] for n in range(nverts)
+                    for d in range(nd)]).reshape(nverts, nd)
+    verts = (ref[:, :, None]*(1 + 0.2*rng.random((1, nd, K)))
+             + 0.15*rng.standard_normal((nverts, nd, K)))
+    upts = 0.6*rng.uniform(-1, 1, (1, nd))
+    smats = (np.eye(nd)[:, None, :, None]
+             + 0.3*rng.standard_normal((nd, 1, nd, K)))
+    rcp = 1/(1 + rng.random((1, K)))
+
+    be = OracleBackend(Config('[backend]\nprecision = double\n'
+                              '[backend-oracle]\nblocks = 1\nsoasz = 4\n'
+                              'csubsz = 8\n'))
+    be.pointwise.register('pyfr.solvers.navstokes.kernels.tflux')
+    mu, mf = be.matrix(u.shape, u), be.matrix((nd, 1, nv, K), g)
+    mg = be.matrix((nd, 1, nv, K), g)
+    geo = (dict(verts=be.const_matrix(verts), upts=be.const_matrix(upts))
+           if linear else
+           dict(smats=be.const_matrix(smats), rcpdjac=be.const_matrix(rcp)))
+    be.commit()
+
+    kern = be.kernel('tflux', tplargs=tpl, dims=[1, K], u=mu, f=mf,
+                     **(dict(gradu=mg) if fused else {}), **geo)
+    kern.run()
+    fo, go = mf.get(), mg.get()
+
+    for e in range(K):
+        args = dict(u=u[0, :, e], f=g[:, 0, :, e], gradu=g[:, 0, :, e],
+                    smats=smats[:, 0, :, e], rcpdjac=rcp[0, e],
+                    verts=verts[:, :, e], upts=upts[0],
+                    artvisc_vtx=0.0)
+        out = ele_lib.call(f'ns_tflux_{i}', **args)
+        _close(fo[:, 0, :, e], out['f'])
+        if fused:
+            _close(go[:, 0, :, e], out['gradu'])
+
+    if fused:
+        return
+
+    # Euler flux, gradient transform and wave speed on the same inputs
+    be.pointwise._mods.clear()
+    for mod in ('pyfr.solvers.euler.kernels.tflux',
+                'pyfr.solvers.baseadvecdiff.kernels.gradcoru',
+                'pyfr.solvers.euler.kernels.wavespeed'):
+        be.pointwise.register(mod)
+
+    mf2, mg2 = be.matrix((nd, 1, nv, K)), be.matrix((nd, 1, nv, K), g)
+    mw = be.matrix((1, K))
+    be.commit()
+    sgeo = {k: v for k, v in geo.items() if k != 'rcpdjac'}
+    be.kernel('tflux', tplargs=tpl, dims=[1, K], u=mu, f=mf2, **sgeo).run()
+    be.kernel('gradcoru', tplargs=tpl, dims=[1, K], gradu=mg2, **geo).run()
+    be.kernel('wavespeed', tplargs=tpl, dims=[1, K], u=mu, wspd=mw,
+              **geo).run()
+    f2, g2, w = mf2.get(), mg2.get(), mw.get()
+
+    for e in range(K):
+        args = dict(u=u[0, :, e], f=np.zeros((nd, nv)),
+                    gradu=g[:, 0, :, e], smats=smats[:, 0, :, e],
+                    rcpdjac=rcp[0, e], verts=verts[:, :, e], upts=upts[0],
+                    wspd=0.0)
+        _close(f2[:, 0, :, e], ele_lib.call(f'eu_tflux_{i}', **args)['f'])
+        _close(g2[:, 0, :, e],
+               ele_lib.call(f'gradcoru_{i}', **args)['gradu'])
+        _close(w[0, e], ele_lib.call(f'wavespeed_{i}', **args)['wspd'])
+
+
+# -- inter-partition kernels, time stepping and diagnostics ---------------------
+@pytest.fixture(scope='module')
+def misc_lib():
+    from pyfr_b200.host.integrator import RK45Stepper as S
+
+    lib = CLib()
+    for i, (nd, rs, beta, tau, vc) in enumerate(CFLUX):
+        c = dict(CONSTS, **{'ldg-beta': beta, 'ldg-tau': tau})
+        tpl = dict(ndims=nd, nvars=nd + 2, c=c, rsolver=rs, visc_corr=vc,
+                   shock_capturing='none')
+        for k in ('mpicflux', 'mpiconu'):
+            _kernel(lib, f'ns_{k}_{i}',
+                    f'pyfr.solvers.navstokes.kernels.{k}', k, tpl)
+        _kernel(lib, f'eu_mpicflux_{i}',
+                'pyfr.solvers.euler.kernels.mpicflux', 'mpicflux', tpl)
+
+    e = [b - bh for b, bh in zip(S.b, S.bhat)]
+    for stage in range(5):
+        for errest in (False, True):
+            _kernel(lib, f'rkvdh2_{stage}_{int(errest)}',
+                    'pyfr.integrators.explicit.kernels.rkvdh2', 'rkvdh2',
+                    dict(a=S.a, b=S.b, e=e, stage=stage, nstages=5, nvars=4,
+                         errest=errest))
+
+    _kernel(lib, 'negdivconf', 'pyfr.solvers.baseadvec.kernels.negdivconf',
+            'negdivconf', dict(ndims=3, nvars=5, src_macros=[], c=CONSTS),
+            extrns=('t', 'ploc', 'u'))
+
+    for nd in (2, 3):
+        exprs = ['pri[0]*pri[1] + pri[%d]' % (nd + 1),
+                 'grad_pri[1][0]*grad_pri[%d][1] - t*grad_pri[0][%d]'
+                 % (nd + 1, nd - 1)]
+        _kernel(lib, f'fieldeval_{nd}', 'pyfr.plugins.kernels.fieldeval',
+                'fieldeval',
+                dict(ndims=nd, nvars=nd + 2, nexprs=2, exprs=exprs,
+                     reduceop='sum', c=CONSTS, has_grads=True,
+                     use_views=False, has_wts=True, fpdtype_max='1e300',
+                     eos_mod='pyfr.solvers.euler.kernels.eos'))
+    return lib.build()
+
+
+def test_mpi_interface_kernels_match_reference_templates(misc_lib):
+    """mpicflux / mpiconu: the left-hand side's view of an inter-partition
+    interface (the host flips the sign of beta on one of the two ranks)."""
+    for i, (nd, rs, beta, tau, vc) in enumerate(CFLUX):
+        nv = nd + 2
+        c = dict(CONSTS, **{'ldg-beta': beta, 'ldg-tau': tau})
+        rng = np.random.default_rng(300 + i)
+
+        for _ in range(10):
+            ul, ur = _state(rng, nd), _state(rng, nd)
+            gl, gr = rng.standard_normal((2, nd, nv))
+            nl = rng.standard_normal(nd)
+
+            out = misc_lib.call(f'ns_mpicflux_{i}', ul=ul, ur=ur, gradul=gl,
+                                gradur=gr, artvisc=0.0, nl=nl)
+            fn = ph.ns_common_flux(_cols(ul), _cols(ur),
+                                   [_cols(g) for g in gl],
+                                   [_cols(g) for g in gr], _cols(nl), nd, nv,
+                                   c, rs, vc)
+            _close(out['ul'], [f[0] for f in fn])
+
+            # mpiconu always writes its side (the oracle kernel spells the
+            # three cases out: oracle/npbackend.py _mpiconu)
+            out = misc_lib.call(f'ns_mpiconu_{i}', ulin=ul, urin=ur,
+                                ulout=np.full(nv, 7.0))
+            want = (ul if beta == -0.5 else ur if beta == 0.5 else
+                    ur*(0.5 + beta) + ul*(0.5 - beta))
+            _close(out['ulout'], want)
+
+            out = misc_lib.call(f'eu_mpicflux_{i}', ul=ul, ur=ur, nl=nl)
+            fn = ph.euler_common_flux(_cols(ul), _cols(ur), _cols(nl), nd, nv,
+                                      c, rs)
+            _close(out['ul'], [f[0] for f in fn])
+
+
+def test_time_stepping_kernels_match_reference_templates(misc_lib):
+    """rkvdh2 (every stage, with and without the error estimate) and
+    negdivconf, through the oracle backend's kernel objects."""
+    from pyfr_b200.host.config import Config
+    from pyfr_b200.host.integrator import RK45Stepper as S
+    from util import OracleBackend
+
+    rng = np.random.default_rng(77)
+    K, nv, dt = 13, 4, 0.037
+    e = [b - bh for b, bh in zip(S.b, S.bhat)]
+
+    be = OracleBackend(Config('[backend]\nprecision = double\n'
+                              '[backend-oracle]\nblocks = 1\nsoasz = 4\n'
+                              'csubsz = 8\n'))
+    be.pointwise.register('pyfr.integrators.explicit.kernels.rkvdh2')
+    be.pointwise.register('pyfr.solvers.baseadvec.kernels.negdivconf')
+
+    for stage in range(5):
+        for errest in (False, True):
+            vals = rng.standard_normal((4, 1, nv, K))
+            ms = [be.matrix((1, nv, K), v) for v in vals]
+            be.commit()
+
+            names = ('r1', 'r2', 'rold', 'rerr')[:4 if errest else 2]
+            k = be.kernel('rkvdh2', tplargs=dict(
+                a=S.a, b=S.b, e=e, stage=stage, nstages=5, nvars=nv,
+                errest=errest), dims=[1, K], **dict(zip(names, ms)))
+            k.bind(dt=dt)
+            k.run()
+            got = [m.get() for m in ms]
+
+            for el in range(K):
+                out = misc_lib.call(
+                    f'rkvdh2_{stage}_{int(errest)}', dt=dt,
+                    **{n: vals[j, 0, :, el] for j, n in
+                       enumerate(('r1', 'r2', 'rold', 'rerr'))})
+                for j, n in enumerate(names):
+                    _close(got[j][0, :, el], out[n])
+
+    # negdivconf
+    d, r = rng.standard_normal((1, 5, K)), 1/(1 + rng.random((1, K)))
+    md, mr = be.matrix(d.shape, d), be.const_matrix(r)
+    be.commit()
+    k = be.kernel('negdivconf', tplargs=dict(ndims=3, nvars=5, src_macros=[],
+                                             c=CONSTS),
+                  dims=[1, K], tdivtconf=md, rcpdjac=mr)
+    k.run()
+    for el in range(K):
+        out = misc_lib.call('negdivconf', tdivtconf=d[0, :, el],
+                            rcpdjac=r[0, el], ploc=np.zeros(3),
+                            u=np.zeros(5), t=0.0)
+        _close(md.get()[0, :, el], out['tdivtconf'])
+
+
+@pytest.mark.parametrize('nd', [2, 3])
+def test_fieldeval_matches_reference_template(misc_lib, nd):
+    """fieldeval with con_to_pri / grad_con_to_pri of the reference's eos
+    template: per-point weighted expression values."""
+    from pyfr_b200.host.config import Config
+    from util import OracleBackend
+
+    nv, K = nd + 2, 9
+    rng = np.random.default_rng(40 + nd)
+    exprs = ['pri[0]*pri[1] + pri[%d]' % (nd + 1),
+             'grad_pri[1][0]*grad_pri[%d][1] - t*grad_pri[0][%d]'
+             % (nd + 1, nd - 1)]
+    tpl = dict(ndims=nd, nvars=nv, nexprs=2, exprs=exprs, reduceop='sum',
+               c=CONSTS, has_grads=True, use_views=False, has_wts=True,
+               eos_mod='pyfr.solvers.euler.kernels.eos')
+
+    u = np.stack([_state(rng, nd) for _ in range(K)], axis=-1)[None]
+    g = rng.standard_normal((nd, 1, nv, K))
+    w = rng.random((1, K))
+
+    be = OracleBackend(Config('[backend]\nprecision = double\n'))
+    be.pointwise.register('pyfr.plugins.kernels.fieldeval')
+    mu, mg = be.matrix(u.shape, u), be.matrix(g.shape, g)
+    mw, mo = be.const_matrix(w), be.matrix((2, K))
+    be.commit()
+    k = be.kernel('fieldeval', tplargs=tpl, dims=[1, K], u=mu, gradu=mg,
+                  wts=mw, out=mo)
+    k.bind(t=0.3)
+    k.run()
+
+    for el in range(K):
+        out = misc_lib.call(f'fieldeval_{nd}', u=u[0, :, el],
+                            gradu=g[:, 0, :, el], ploc=np.zeros(nd),
+                            wts=w[0, el], out=np.zeros(2), t=0.3)
+        _close(mo.get()[:, el], out['out'])
