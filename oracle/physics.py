@@ -6,12 +6,18 @@ it.  Each function restates one Mako macro/kernel of the reference
 point-for-point (same operation order where it matters for rounding),
 operating on lists of NumPy arrays, one array per variable.
 
-PARITY STATUS: *unpinned by the reference's own tests* -- the reference
-ships no golden vectors for flux, Riemann, gradient or RHS values
-(only operator matrices, see tests/test_oracle_golden.py), and its kernels
-are Mako templates that cannot be rendered in this environment (no
-``mako``).  The restatement is therefore checked by analytic properties
-instead (tests/test_oracle_physics.py: the viscous flux against the
+PARITY STATUS: *pinned on the reference's own kernel templates.*  The
+reference ships no golden vectors for flux, Riemann, gradient or RHS values
+(only operator matrices, see tests/test_oracle_golden.py) and ``mako`` is
+not installable here, so ``oracle/minimako.py`` renders the reference's
+``.mako`` kernel files with a minimal interpreter of the template language
+(macro expansion by the reference's own ``makoutil``); the rendered
+kernels -- intcflux / mpicflux / intconu / mpiconu, bcconu / bccflux for
+every boundary type, tflux in all its variants, gradcoru, wavespeed,
+negdivconf, rkvdh2, fieldeval -- are compiled as C and this restatement
+must reproduce them to 2e-13 on random states
+(tests/test_oracle_templates.py).  Beside that it is checked by analytic
+properties (tests/test_oracle_physics.py: the viscous flux against the
 analytic Newtonian stress tensor and Fourier heat flux, the inviscid flux
 against the Euler flux, exact upwinding of HLLC for supersonic states,
 impermeable and adiabatic walls, far-field transparency; tests/
