@@ -21,7 +21,7 @@ from types import SimpleNamespace
 
 import numpy as np
 
-REFROOT = '/root/reference'
+REFROOT = os.environ.get('PYFR_B200_REFROOT', '/root/reference')
 
 
 def available():

@@ -19,8 +19,17 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def _ref_available():
+    sys.path.insert(0, ROOT)
+    try:
+        from oracle import refharness
+        return refharness.available()
+    finally:
+        sys.path.pop(0)
+
 pytestmark = pytest.mark.skipif(
-    not os.path.isdir('/root/reference/pyfr'), reason='needs /root/reference'
+    not _ref_available(), reason='needs /root/reference'
 )
 
 _script = r'''

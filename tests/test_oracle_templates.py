@@ -20,8 +20,33 @@ import pytest
 from oracle import physics as ph
 from oracle import refharness as rh
 
-pytestmark = pytest.mark.skipif(not rh.available(),
-                                reason='needs /root/reference')
+# Where the reference is present the rendered kernels are compiled and run;
+# elsewhere (the GPU box) the same tests replay the committed input/output
+# vectors of such a run (tests/golden/kernel_vectors.npz, written by
+# ``make_golden.py --kernels``)
+HERE = os.path.dirname(os.path.abspath(__file__))
+VECTORS = os.path.join(HERE, 'golden', 'kernel_vectors.npz')
+LIVE = rh.available()
+RECORD = os.environ.get('PYFR_B200_RECORD_KERNELS')
+
+_recorded, _replay, _cursor = {}, None, {}
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _vectors():
+    global _replay
+    if not LIVE:
+        _replay = np.load(VECTORS)
+    yield
+    if RECORD:
+        out = {}
+        for name, calls in _recorded.items():
+            for kind, idx in (('in', 0), ('out', 1)):
+                for a in calls[0][idx]:
+                    out[f'{name}|{kind}|{a}'] = np.stack(
+                        [np.asarray(c[idx][a], dtype=float) for c in calls])
+        np.savez_compressed(RECORD, **out)
+
 
 CONSTS = {'gamma': 1.4, 'mu': 3e-3, 'Pr': 0.71, 'cpTref': 2.5, 'cpTs': 1.1}
 RTOL = 2e-13
@@ -48,6 +73,8 @@ class CLib:
 
     def add(self, name, args, body):
         """``args``: {arg: (intent, dims)} in call order."""
+        if not LIVE:
+            return
         pre, post = [], []
         for i, (a, (intent, dims)) in enumerate(args.items()):
             if dims:
@@ -66,6 +93,8 @@ class CLib:
         self.fns[name] = args
 
     def build(self):
+        if not LIVE:
+            return self
         d = tempfile.mkdtemp(prefix='pyfr_b200_tpl_')
         c, so = os.path.join(d, 'k.c'), os.path.join(d, 'k.so')
         with open(c, 'w') as f:
@@ -79,17 +108,44 @@ class CLib:
 
     def call(self, name, **vals):
         """Returns {arg: array} after the call (inputs copied)."""
+        if not LIVE:
+            # replay: same call sequence, same (seeded) inputs
+            i = _cursor[name] = _cursor.get(name, -1) + 1
+            pre = f'{name}|'
+            for k in _replay.files:
+                if k.startswith(pre + 'in|'):
+                    a = k[len(pre) + 3:]
+                    want = _replay[k][i]
+                    got = np.asarray(vals[a], dtype=float).reshape(want.shape)
+                    assert np.allclose(got, want, rtol=1e-14, atol=0), \
+                        f'{name}: input {a} differs from the recorded call'
+            return {k[len(pre) + 4:]: _replay[k][i] for k in _replay.files
+                    if k.startswith(pre + 'out|')}
+
         args = self.fns[name]
         bufs = [np.array(vals[a], dtype=float).reshape(dims or (1,)).copy()
                 for a, (_, dims) in args.items()]
         ptrs = (ct.POINTER(ct.c_double)*len(bufs))(
             *[b.ctypes.data_as(ct.POINTER(ct.c_double)) for b in bufs])
+        ins = [b.copy() for b in bufs]
         getattr(self.lib, name)(ptrs)
-        return {a: (b if dims else b[0])
-                for (a, (_, dims)), b in zip(args.items(), bufs)}
+        res = {a: (b if dims else b[0])
+               for (a, (_, dims)), b in zip(args.items(), bufs)}
+
+        if RECORD:
+            _recorded.setdefault(name, []).append((
+                {a: (b if dims else b[0])
+                 for (a, (_, dims)), b in zip(args.items(), ins)},
+                {a: v for a, v in res.items() if 'out' in args[a][0]}
+            ))
+
+        return res
 
 
 def _kernel(lib, fname, mod, kname, tplargs, extrns=()):
+    if not LIVE:
+        return None
+
     from oracle.minimako import Renderer
 
     r = Renderer(tplargs, extrns)
@@ -239,6 +295,9 @@ def _bc_kernels():
 def bc_lib():
     lib, specs = CLib(), _bc_kernels()
     for i, (system, name, tpl) in enumerate(specs):
+        if not LIVE:
+            break
+
         nd = tpl['ndims']
         sysmod = 'navstokes' if system == 'navier-stokes' else 'euler'
         from oracle.minimako import Renderer
@@ -304,8 +363,12 @@ ELE = [(nd, ktype, vc) for nd in (2, 3)
 
 
 def _ref_jac_exprs(nd):
-    rh.install_stubs()
-    from pyfr.shapes import HexShape, QuadShape
+    if not LIVE:
+        # (pinned against the reference's by the host fixtures)
+        from pyfr_b200.host.shapes import HexShape, QuadShape
+    else:
+        rh.install_stubs()
+        from pyfr.shapes import HexShape, QuadShape
     return (QuadShape if nd == 2 else HexShape).jac_exprs
 
 

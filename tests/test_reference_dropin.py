@@ -20,6 +20,15 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def _ref_available():
+    sys.path.insert(0, ROOT)
+    try:
+        from oracle import refharness
+        return refharness.available()
+    finally:
+        sys.path.pop(0)
+
 _script = r'''
 import json, os, sys
 os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
@@ -56,7 +65,7 @@ print('RESULT ' + json.dumps(out))
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_b200_backend_under_reference_host(built):
     res = subprocess.run([sys.executable, '-c', _script % {'root': ROOT}],
@@ -73,7 +82,7 @@ def test_b200_backend_under_reference_host(built):
     assert eu[-1] == ['fluxdiv']
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_memory_info_under_reference_base(built):
     """memory_info() goes through whichever base class is in use."""
@@ -157,7 +166,7 @@ for case, n, kw in [('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_reference_host_executes_on_b200_backend(built):
     """The complete drop-in, executed: the reference's unmodified systems
@@ -236,7 +245,7 @@ for name, (case, n, kw, sect, tend) in INTG.items():
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_reference_integrators_execute_on_b200_backend(built):
     """The reference's composed integrator classes (RK45 + PI controller,
@@ -329,7 +338,7 @@ print('RESULT', rows['oracle'].shape[0],
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_reference_integrate_plugin_on_b200_backend(built):
     """The reference's ``[soln-plugin-integrate]`` (``BackendFieldReducer``,
@@ -419,7 +428,7 @@ for case, n, parts, kw in [('tgv', (4, 2, 2), (2, 1, 1), dict(order=2, warp=0.1)
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_reference_mpi_interfaces_on_b200_backend(built):
     """Partitioned runs under the reference's own host code: its
@@ -503,7 +512,7 @@ for system, n, bcs, kw in CASES:
 '''
 
 
-@pytest.mark.skipif(not os.path.isdir('/root/reference/pyfr'),
+@pytest.mark.skipif(not _ref_available(),
                     reason='needs /root/reference')
 def test_reference_boundary_interfaces_on_b200_backend(built):
     """The reference's boundary-interface classes (``pyfr/solvers/*/
