@@ -607,6 +607,24 @@ def main():
         if sys.argv[1:]:
             return
 
+    if sys.argv[1:] in ([], ['--kernels']):
+        # Input/output vectors of the reference's kernel templates, rendered
+        # by oracle/minimako.py and compiled as C: recorded while
+        # tests/test_oracle_templates.py runs against the live templates
+        import subprocess
+
+        path = os.path.join(HERE, 'kernel_vectors.npz')
+        subprocess.run(
+            [sys.executable, '-m', 'pytest', '-q', '-x',
+             os.path.join(ROOT, 'tests', 'test_oracle_templates.py')],
+            env=dict(os.environ, PYFR_B200_RECORD_KERNELS=path), check=True,
+            cwd=ROOT
+        )
+        print('kernel_vectors.npz written')
+
+        if sys.argv[1:]:
+            return
+
     if sys.argv[1:2] == ['--only']:
         for name in sys.argv[2].split(','):
             np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
