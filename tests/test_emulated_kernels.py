@@ -791,3 +791,34 @@ def test_partitioned_mixed_mesh(emulated, pattern, n, parts, kw):
                             bsys[r].ele_scal_upts(1)):
             assert np.abs(o - wrhs[et][..., order[r][et]]).max() < 1e-12*scale
             assert np.abs(b - o).max() < 1e-12*scale
+
+
+def test_eight_partitions_as_in_the_scaling_run(emulated):
+    """The 2 x 2 x 2 brick layout bench.py uses at 8 GPUs: every rank has
+    three neighbours and meets each of them across *two* opposite faces
+    (periodic box, two bricks per axis).  Generated kernels with graphs on,
+    against the partitioned oracle."""
+    n, parts, kw = (4, 4, 4), (2, 2, 2), dict(order=1, warp=0.05)
+    _, box = cases.make('tgv', n, **kw)
+    vparts = box.brick_partition(parts)
+    world = EmuWorld(8)
+
+    systems = []
+    for r in range(8):
+        cfg, box = cases.make('tgv', n, **kw)
+        systems.append(_b200(cfg, box, vparts, r, comm=world.peer(r),
+                             opts={'graphs': 'true'}))
+        assert sorted(box.local_mesh(vparts, r).con_p) == sorted(
+            {r ^ 1, r ^ 2, r ^ 4})
+
+    for _ in range(2):                           # capture, then replay
+        for stage in zip(*[s.rhs_graphs(0, 1) for s in systems]):
+            for g in stage:
+                g.run()
+            world.deliver()
+
+    _, ref = oracle_rhs('tgv', n, vparts=vparts, nparts=8, **kw)
+    _, ext = oracle_rhs('tgv', n, vparts=vparts, nparts=8, extended=True,
+                        **kw)
+    for r, s in enumerate(systems):
+        assert_parity(s.ele_scal_upts(1)[0], ref[r], ext[r], 1e-12)
