@@ -159,6 +159,7 @@ def _compile(text):
             else:
                 ka = ', '.join(f'{k!r}: {_attr_expr(v)}' for k, v in a.items()
                                if k not in ('name', 'ndim'))
+                g.emit(f'_ndim[{a["name"]!r}] = {a.get("ndim", "1")!r}')
                 g.emit(f'_kernel({a["name"]!r}, {{{ka}}}, {fn})')
         elif name in ('inherit', 'namespace'):
             continue
@@ -190,7 +191,13 @@ class Renderer:
     (``'pyfr.solvers.euler.kernels.flux'``) with the template arguments
     ``tplargs``; collects macros and kernel bodies."""
 
-    def __init__(self, tplargs, extrns=()):
+    def __init__(self, tplargs, extrns=(), generator=None, fpdtype=None,
+                 ixdtype=None):
+        """With ``generator`` (a kernel generator class of the reference,
+        e.g. its OpenMP one) ``<%pyfr:kernel>`` tags are turned into
+        complete kernels exactly as ``makoutil.kernel`` does; they land in
+        ``self.sources`` / ``self.argspecs``.  ``extrns`` is then the
+        mapping of external argument specs."""
         rh.install_stubs()
         import pyfr.backends.base.makoutil as mu
         import pyfr.util as util
@@ -201,7 +208,9 @@ class Renderer:
 
         self.mu = mu
         self.kernels, self._seen = {}, set()
-        self.ctx = {'_macros': {}, '_extrns': {e: None for e in extrns}}
+        self.sources, self.argspecs = {}, {}
+        self.ctx = {'_macros': {}, '_extrns': (dict(extrns) if generator else
+                                               {e: None for e in extrns})}
 
         ctx = self.ctx
 
@@ -226,11 +235,25 @@ class Renderer:
             ctx['_macros'][name] = ctx['_macros'][func]
 
         def kernel(name, attrs, body):
-            self.kernels[name] = (attrs, body())
+            text = body()
+            self.kernels[name] = (attrs, text)
+
+            if generator is not None:
+                # pyfr/backends/base/makoutil.py, kernel()
+                if any(a in ctx['_extrns'] for a in attrs):
+                    raise ValueError(f'Duplicate argument in {name}')
+                kern = generator(name, int(self._ndim[name]),
+                                 dict(attrs, **ctx['_extrns']), text, fpdtype,
+                                 ixdtype)
+                self.argspecs[name] = kern.argspec()
+                self.sources[name] = kern.render()
+
+        self._ndim = {}
 
         import math
         self.ns = dict(tplargs, pyfr=ns, math=math, _macro=macro,
-                       _alias=alias, _kernel=kernel, _include=self.include)
+                       _alias=alias, _kernel=kernel, _include=self.include,
+                       _ndim=self._ndim)
 
     def include(self, mod):
         if mod in self._seen:
