@@ -16,7 +16,10 @@ kernels -- intcflux / mpicflux / intconu / mpiconu, bcconu / bccflux for
 every boundary type, tflux in all its variants, gradcoru, wavespeed,
 negdivconf, rkvdh2, fieldeval -- are compiled as C and this restatement
 must reproduce them to 2e-13 on random states
-(tests/test_oracle_templates.py).  Beside that it is checked by analytic
+(tests/test_oracle_templates.py); and with those kernels completed by the
+reference's OpenMP generator and driven by the reference's host code
+(oracle/refkernels.py) the whole RHS of the reference is reproduced
+(tests/test_reference_kernels.py).  Beside that it is checked by analytic
 properties (tests/test_oracle_physics.py: the viscous flux against the
 analytic Newtonian stress tensor and Fourier heat flux, the inviscid flux
 against the Euler flux, exact upwinding of HLLC for supersonic states,
