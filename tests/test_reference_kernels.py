@@ -146,3 +146,44 @@ def test_host_fixtures_are_what_the_reference_kernels_produce():
                                   make_refkernel_backend))]
         assert np.abs(rhs[0] - gold['r0_rhs']).max() <= \
             1e-13*np.abs(gold['r0_rhs']).max()
+
+
+@pytest.mark.parametrize('name', ['vortex_p3_rk45_pi_l2',
+                                  'tgv_p2_rk45_cfl_curved'])
+def test_integrator_fixtures_hold_on_reference_kernels(name):
+    """The reference's integrators (RK45 under the PI and CFL controllers)
+    on the reference's own ``rkvdh2`` / ``wavespeed`` / RHS kernels retrace
+    the committed histories (tests/golden/intg_*.npz, recorded on the
+    oracle kernels)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    import make_golden as mg
+
+    from oracle.refkernels import make_refkernel_backend
+
+    rh.install_stubs()
+    rh.set_rank(LocalComm(0, 1).peer(0))
+    import pyfr.backends.base as rbase
+    from pyfr.inifile import Inifile
+    from pyfr.integrators import get_integrator
+    from pyfr.solvers.euler import EulerSystem
+    from pyfr.solvers.navstokes import NavierStokesSystem
+
+    case, n, kw, opts, tlist = mg.INTG_CASES[name]
+    _, box = cases.make(case, n, **kw)
+    cfg = Inifile(mg.intg_cfg_text(name) + LAYOUT)
+    be = make_refkernel_backend(rbase)(cfg)
+    cls = EulerSystem if case == 'vortex' else NavierStokesSystem
+    intg = get_integrator(be, cls, rh.ref_mesh(box.local_mesh()), None, cfg)
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden',
+                                f'intg_{name}.npz'))
+    for i, t in enumerate(tlist):
+        intg.advance_to(t)
+        assert intg.tcurr == float(gold[f'tcurr_t{i}'])
+        u = intg.soln[0]
+        assert np.abs(u - gold[f'u_t{i}']).max() <= \
+            1e-12*np.abs(gold[f'u_t{i}']).max()
+
+    assert (intg.nacptsteps, intg.nrjctsteps) == tuple(gold['counts'][:2])
+    assert intg.dt == pytest.approx(float(gold['dt_final']), rel=1e-9)
