@@ -187,3 +187,67 @@ def test_integrator_fixtures_hold_on_reference_kernels(name):
 
     assert (intg.nacptsteps, intg.nrjctsteps) == tuple(gold['counts'][:2])
     assert intg.dt == pytest.approx(float(gold['dt_final']), rel=1e-9)
+
+
+_direct = r'''
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests', ROOT + '/tests/cudaemu']
+from types import SimpleNamespace
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+from oracle.refkernels import make_refkernel_backend
+rh.install_stubs()
+rh.set_rank(LocalComm(0, 1).peer(0))
+import emu
+import pyfr_b200.backend as bk, pyfr_b200.compiler as comp
+bk.load_runtime = lambda device=0, dry=False: emu.EmuRuntime()
+comp.KernelCompiler.cubin = lambda self, src, name: src.encode()
+import pyfr.backends.base as rbase
+from pyfr.inifile import Inifile
+from pyfr.solvers.euler import EulerSystem
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+for case, n, kw in [('tgv', (3, 2, 2), dict(order=3, warp=0.1)),
+                    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, beta=0.0,
+                                            rsolver='hllc')),
+                    ('vortex', 5, dict(order=3))]:
+    kw2 = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
+    txt += '\n[backend-oracle]\nblocks = 1\nsoasz = 4\ncsubsz = 8\n'
+    _, box = cases.make(case, n, **kw)
+    mesh = rh.ref_mesh(box.local_mesh())
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+
+    outs = []
+    for mk in (lambda cfg: make_refkernel_backend(rbase)(cfg), B200Backend):
+        cfg = Inifile(txt)
+        regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+        s = cls(mk(cfg), mesh, None, regs, cfg, None)
+        s.commit()
+        s.rhs(0.0, 0, 1)
+        outs.append(s.ele_scal_upts(1)[0])
+
+    print('RESULT', case, np.abs(outs[1] - outs[0]).max()/np.abs(outs[0]).max())
+'''
+
+
+def test_b200_backend_against_reference_kernels_directly():
+    """Same unmodified reference host code, two backends: the reference's
+    own generated kernels, and the B200 backend (its generated CUDA run on
+    the CPU execution model, fused launches and all)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-c', _direct % {'root': root}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2500:]
+
+    rows = [l.split() for l in res.stdout.splitlines()
+            if l.startswith('RESULT')]
+    assert len(rows) == 3 and all(float(r[2]) < 1e-12 for r in rows), rows
