@@ -81,6 +81,10 @@ CASES = [
                             rsolver='hllc'), (2, 1, 1)),
     ('tgv', (3, 2, 2), dict(order=2, warp=0.1,
                             pts='gauss-legendre-lobatto'), (1, 1, 1)),
+    # single precision (the generator suffixes every literal with f)
+    ('tgv', (3, 2, 2), dict(order=2, warp=0.1, precision='single'),
+     (1, 1, 1)),
+    ('vortex', 5, dict(order=3, precision='single', rsolver='hllc'), (1, 1)),
 ]
 
 
@@ -92,7 +96,8 @@ def test_oracle_equals_reference_kernels(case, n, kw, parts):
 
     nparts = int(np.prod(parts))
     vparts = box.brick_partition(parts) if nparts > 1 else None
-    _compare(txt, [box.local_mesh(vparts, r) for r in range(nparts)])
+    _compare(txt, [box.local_mesh(vparts, r) for r in range(nparts)],
+             tol=1e-6 if kw.get('precision') == 'single' else 1e-13)
 
 
 @pytest.mark.parametrize('system,n,bcs,kw', [
