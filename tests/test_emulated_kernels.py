@@ -822,3 +822,43 @@ def test_eight_partitions_as_in_the_scaling_run(emulated):
                         **kw)
     for r, s in enumerate(systems):
         assert_parity(s.ele_scal_upts(1)[0], ref[r], ext[r], 1e-12)
+
+
+def test_operator_kernel_on_random_matrices(emulated):
+    """``opmul`` for operators the solvers never hand over: random shapes
+    and sparsity (empty rows and columns, fully dense), alpha / beta
+    variants, ragged last block, and a shared-memory budget small enough to
+    force the input tile to be streamed in several chunks."""
+    from pyfr_b200.backend import B200Backend
+    from pyfr_b200.host.config import Config
+
+    rng = np.random.default_rng(11)
+    cfg = Config('[backend]\nprecision = double\n[backend-b200]\n'
+                 'graphs = false\n')
+    be = B200Backend(cfg)
+    be.smem_budget = 12*1024            # K*LD*8 bytes exceeds this early
+
+    for trial in range(14):
+        M, K = int(rng.integers(1, 40)), int(rng.integers(1, 70))
+        dens = [0.05, 0.3, 1.0][trial % 3]
+        A = rng.standard_normal((M, K))*(rng.random((M, K)) < dens)
+        if trial % 4 == 0 and M > 2 and K > 2:
+            A[rng.integers(M)] = 0
+            A[:, rng.integers(K)] = 0
+        alpha = [1.0, -2.0, 0.5][trial % 3]
+        beta = [0.0, 1.0, -0.5, 0.0][trial % 4]
+        nv, ne = int(rng.integers(1, 6)), int(rng.integers(1, 30))
+
+        b = rng.standard_normal((K, nv, ne))
+        c = rng.standard_normal((M, nv, ne))
+        ma = be.const_matrix(A)
+        mb, mc = be.matrix(b.shape, b, tags={'align'}), \
+            be.matrix(c.shape, c, tags={'align'})
+        be.commit()
+
+        k = be.kernel('mul', ma, mb, out=mc, alpha=alpha, beta=beta)
+        be.run_kernels([k], wait=True)
+
+        want = alpha*np.einsum('mk,kve->mve', A, b) + beta*c
+        assert np.abs(mc.get() - want).max() <= 1e-13*max(
+            1.0, np.abs(want).max()), (trial, M, K, dens, alpha, beta)
