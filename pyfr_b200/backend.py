@@ -70,6 +70,12 @@ class B200Backend(base.BaseBackend):
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
+        # Phases of gradflux whose work items take two adjacent columns
+        # with 16-byte accesses ('p1', 'p3', 'p5'; comma separated)
+        self.gradflux_vec2 = tuple(
+            v.strip() for v in str(cfg.get(sect, 'gradflux-vec2', '')).split(',')
+            if v.strip() and v.strip() != '0'
+        )
         self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
         self.euler_fusion = cfg.getbool(sect, 'euler-fusion', True)
         # Runge-Kutta stage update in the epilogue of the last RHS kernel

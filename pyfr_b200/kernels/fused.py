@@ -320,7 +320,7 @@ class PhaseEmitter:
         return '\n        '.join(out)
 
     def emit(self, tag, classes, srcs, store, inplace=False, outtag=None,
-             rep=None):
+             rep=None, vec=False):
         """``srcs[t]``: name of the (shared) array term ``t`` reads;
         ``store(byte offset expr, val)`` renders a store.  ``rep = (n,
         out stride, in stride)`` applies the same classes ``n`` times with
@@ -335,10 +335,19 @@ class PhaseEmitter:
 
         A work item handles one line for ``self.ncol`` columns ``LD/ncol``
         apart: the index fetches and address additions are shared, the
-        extra columns being reached through immediate offsets."""
+        extra columns being reached through immediate offsets.
+
+        ``vec``: a work item handles two *adjacent* columns with one
+        16-byte access per row (rows are ``LD*isz`` bytes apart and ``LD`` is
+        even, so every access stays aligned): half the loads, stores,
+        index fetches and address additions per value for the same number
+        of shared-memory wavefronts -- for phases that are bound by
+        instruction issue rather than by shared-memory bandwidth."""
         LD, isz, K, out = self.LD, self.isz, self.K, []
-        NC = self.ncol if LD % self.ncol == 0 else 1
+        vec = bool(vec) and LD % 2 == 0 and (LD*isz) % (2*isz) == 0
+        NC = 2 if vec else (self.ncol if LD % self.ncol == 0 else 1)
         W, WB = LD // NC, (LD // NC)*isz
+        CW = 2*isz if vec else isz          # bytes between items' columns
 
         if inplace:
             # A work item overwrites its own inputs after reading them
@@ -391,15 +400,15 @@ class PhaseEmitter:
                           f'    const int rd = item / {nmem*W};',
                           f'    const int ritem = item - rd*{nmem*W};',
                           f'    const int g = ritem / {W};',
-                          f'    const int cbi = (ritem - g*{W})*{isz} + '
+                          f'    const int cbi = (ritem - g*{W})*{CW} + '
                           f'rd*{rep[2]};',
-                          f'    const int cb = (ritem - g*{W})*{isz} + '
+                          f'    const int cb = (ritem - g*{W})*{CW} + '
                           f'rd*{rep[1]};']
                 else:
                     L += [f'for (int item = tid; item < {nmem*W}; '
                           'item += NTHREADS)', '{',
                           f'    const int g = item / {W};',
-                          f'    const int cb = (item - g*{W})*{isz};',
+                          f'    const int cb = (item - g*{W})*{CW};',
                           '    const int cbi = cb;']
 
                 for q in range(npad // 4):
@@ -410,6 +419,9 @@ class PhaseEmitter:
                 at = lambda arr, off: (
                     f'*reinterpret_cast<fpdtype_t *>('
                     f'reinterpret_cast<char *>({arr}) + {off})')
+                at2 = lambda arr, off: (
+                    f'*reinterpret_cast<fpdtype2_t *>('
+                    f'reinterpret_cast<char *>({arr}) + {off})')
 
                 base = 0 if inplace else c.nout
                 regs, off = [], base
@@ -417,6 +429,12 @@ class PhaseEmitter:
                     for j in range(n):
                         L.append(f'    const int i{t}_{j} = {idx(off + j)} '
                                  '+ cbi;')
+                        if vec:
+                            L.append(f'    const fpdtype2_t x{t}_{j} = '
+                                     f'{at2(srcs[t], f"i{t}_{j}")};')
+                            L.append(f'    const fpdtype_t x{t}_{j}_0 = '
+                                     f'x{t}_{j}.x, x{t}_{j}_1 = x{t}_{j}.y;')
+                            continue
                         for k in range(NC):
                             L.append(
                                 f'    const fpdtype_t x{t}_{j}_{k} = '
@@ -436,13 +454,18 @@ class PhaseEmitter:
                     else:
                         dst = f'{idx(i)} + cb'
 
-                    body = []
+                    body, vals = [], []
                     for k in range(NC):
                         pairs = [(c.coefs[t][i, j], f'{regs[t][j]}_{k}')
                                  for t in range(len(c.nins))
                                  for j in range(c.nins[t])]
-                        body.append(store(f'{dst} + {k*WB}',
-                                          _fma_chain(pairs, K), at))
+                        vals.append(_fma_chain(pairs, K))
+                        if not vec:
+                            body.append(store(f'{dst} + {k*WB}', vals[-1],
+                                              at))
+                    if vec:
+                        body.append(store(
+                            dst, f'fpdtype2_t{{{vals[0]}, {vals[1]}}}', at2))
 
                     if key:
                         L.append(f'    if (fm & {1 << key[i]}u)')
@@ -547,9 +570,12 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     K = ConstPool(isz == 8)
     em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 1))
 
+    vecs = set(getattr(be, 'gradflux_vec2', ()) or ())
+
     # Phase 1: G = A1 @ U + M6 @ C
     p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
-                 lambda off, v, at: f'{at("G", off)} = {v};')
+                 lambda off, v, at: f'{at("G", off)} = {v};',
+                 vec='p1' in vecs)
 
     # Phase 3: vect_fpts[d] = M0 @ G[d]
     M0d = np.zeros((nd*nf, nd*nu))
@@ -564,7 +590,8 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
 
     p3 = em.emit('p3', build_classes([M0]), ['G'],
                  lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};',
-                 outtag=outtag, rep=(nd, nf*LD*isz, nu*LD*isz))
+                 outtag=outtag, rep=(nd, nf*LD*isz, nu*LD*isz),
+                 vec='p3' in vecs)
 
     # Phase 5: in-place line transforms of the flux, direction by
     # direction (block d of A5 acts on rows d*nu.. of G), then the sum
@@ -573,7 +600,7 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
     p5lines = em.emit('p5', build_classes([A5d]), ['G'],
                       lambda off, v, at: f'{at("G", off)} = {v};',
-                      inplace=True)
+                      inplace=True, vec='p5' in vecs)
     if LD % 2 == 0:
         gv = 'reinterpret_cast<const fpdtype2_t *>(G)'
         sx = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].x' for d in range(nd))
@@ -609,7 +636,8 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                 lines = build_classes([A5l], rows=range(2*nu, 3*nu))
                 p5a = em.emit('p5l', lines, ['G'],
                               lambda off, v, at: f'{at("G", off)} = {v};',
-                              inplace=True) + '\n        __syncthreads();'
+                              inplace=True, vec='p5' in vecs
+                              ) + '\n        __syncthreads();'
                 extra = lambda off, at: at('G', f'{off} + {2*nu*LD*isz}')
             else:
                 p5a, extra = '', None

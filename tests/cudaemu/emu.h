@@ -26,9 +26,12 @@
 #define __shared__ static      // one CTA runs at a time
 
 struct emu_dim3 { unsigned x, y, z; };
-struct int4 { int x, y, z, w; };
-struct double2 { double x, y; };
-struct float2 { float x, y; };
+// Vector types carry CUDA's alignment requirements; the kernels are built
+// with -fsanitize=alignment (trapping), so a 16-byte access at an address
+// the device would fault on ends the process here too
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) float2 { float x, y; };
 
 static thread_local emu_dim3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;

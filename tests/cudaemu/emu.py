@@ -60,7 +60,8 @@ def translate(src):
     return name, f'#include "{_header()}"\n{src}\n{wrap}'
 
 
-_flags = ['-std=c++17', '-O1', '-fPIC', '-pthread', '-w']
+_flags = ['-std=c++17', '-O1', '-fPIC', '-pthread', '-w',
+          '-fsanitize=alignment', '-fsanitize-undefined-trap-on-error']
 
 
 def _header(tsan=None):

@@ -58,6 +58,12 @@ def _kinds(sysm):
      'gradflux'),
     (dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux'),
     (dict(order=3), {'n-soa': 4}, 'gradflux'),
+    # two adjacent columns per work item (16-byte accesses)
+    (dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
+    (dict(order=3, beta=0.0), {'gradflux-vec2': 'p3'}, 'gradflux'),
+    (dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
+                               'gradflux-planes': 1}, 'gradflux'),
+    (dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
     # the benchmark's kernel variants (p = 4, 512 threads, 220 KB smem)
     (dict(order=4), {}, 'gradflux'),
     (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),
@@ -75,6 +81,32 @@ def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
 
     assert expect in _kinds(sysm)
     assert_parity(out, ref[0], ext[0], 1e-12)
+
+
+def _vec2_cases():
+    from test_gpu_zlate import VEC2_CASES
+    return VEC2_CASES
+
+
+@pytest.mark.parametrize('case,n,kw,opts', _vec2_cases(), ids=str)
+def test_vectorised_gradflux_device_cases(emulated, case, n, kw, opts):
+    """The device parity cases of the gradflux-vec2 variants
+    (tests/test_gpu_zlate.py), here on the execution model; the model also
+    checks that every 16-byte access is 16-byte aligned."""
+    cfg, box = cases.make(case, n, **kw)
+    sysm = _b200(cfg, box, opts=opts)
+    assert 'gradflux' in _kinds(sysm)
+    sysm.rhs(0.0, 0, 1)
+    out = sysm.ele_scal_upts(1)[0]
+
+    _, ref = oracle_rhs(case, n, **kw)
+    if kw.get('precision') == 'single':
+        _, r64 = oracle_rhs(case, n, **{**kw, 'precision': 'double'})
+        floor = rel_err(ref[0].astype(float), r64[0])
+        assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
+    else:
+        _, ext = oracle_rhs(case, n, extended=True, **kw)
+        assert_parity(out, ref[0], ext[0], 1e-12)
 
 
 def test_fp32_kernels(emulated):
@@ -862,3 +894,40 @@ def test_operator_kernel_on_random_matrices(emulated):
         want = alpha*np.einsum('mk,kve->mve', A, b) + beta*c
         assert np.abs(mc.get() - want).max() <= 1e-13*max(
             1.0, np.abs(want).max()), (trial, M, K, dens, alpha, beta)
+
+
+def test_execution_model_traps_misaligned_vector_access():
+    """Negative control for the alignment checking of the execution model:
+    a 16-byte load at an address that is only 8-byte aligned (a device
+    fault) must end the process; the aligned one must not."""
+    import subprocess
+
+    prog = r'''
+import ctypes as ct, sys
+sys.path.insert(0, sys.argv[1])
+import emu
+src = """
+typedef double fpdtype_t;
+typedef double2 fpdtype2_t;
+extern "C" __global__ void probe(const fpdtype_t* __restrict__ a, fpdtype_t* __restrict__ b, int off)
+{
+    const fpdtype2_t v = *reinterpret_cast<const fpdtype2_t *>(a + off);
+    b[0] = v.x + v.y;
+}
+"""
+rt = emu.EmuRuntime()
+a, b = rt.malloc(64), rt.malloc(64)
+m = rt.module_load(src.encode())
+off = ct.c_int(int(sys.argv[2]))
+pa, pb = ct.c_void_p(a), ct.c_void_p(b)
+argv = (ct.c_void_p*3)(ct.addressof(pa), ct.addressof(pb), ct.addressof(off))
+rt.launch(m, 1, 1, 1, 1, 1, 1, 0, 0, argv)
+print('RAN')
+'''
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'cudaemu')
+    run = lambda off: subprocess.run([sys.executable, '-c', prog, here,
+                                      str(off)], capture_output=True,
+                                     text=True, timeout=300)
+    ok, bad = run(2), run(1)
+    assert ok.returncode == 0 and 'RAN' in ok.stdout, ok.stderr[-2000:]
+    assert bad.returncode != 0 and 'RAN' not in bad.stdout

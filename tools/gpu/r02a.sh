@@ -10,6 +10,16 @@ python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python -m pytest tests/test_gpu_zlate.py -m gpu -q 2>&1 | tail -25
 timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zlate.py 2>&1 | tail -4
 timeout 600 python bench.py --kernel-times gpurun_out/r02a_kt64.json > gpurun_out/r02a_bench64.json 2> gpurun_out/r02a_bench64.err; tail -c 3800 gpurun_out/r02a_bench64.json; tail -3 gpurun_out/r02a_bench64.err
+# gradflux-vec2 (16-byte accesses, two adjacent columns per work item): phase 3 is issue-bound, static SASS count
+# of its loop body 58 -> 28 instructions per live output; measure before making it the default
+for v in p3 p1,p3 p1,p3,p5; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-clocks --opt gradflux-vec2=$v --kernel-times gpurun_out/r02a_kt_vec2_$v.json > gpurun_out/r02a_b_vec2_$v.json 2> gpurun_out/r02a_b_vec2_$v.err
+  python - <<PY
+import json
+d = json.load(open('gpurun_out/r02a_kt_vec2_$v.json')); b = json.loads(open('gpurun_out/r02a_b_vec2_$v.json').read())
+print('vec2=$v', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
+PY
+done
 # mixed elements (BASELINE configs[3]): 24^3 cells, p = 3
 timeout 600 python bench.py --case hex+pri+pyr+tet --n 24 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_mixed.json > gpurun_out/r02a_bench_mixed.json 2> gpurun_out/r02a_bench_mixed.err; tail -c 2500 gpurun_out/r02a_bench_mixed.json; tail -3 gpurun_out/r02a_bench_mixed.err
 timeout 600 python bench.py --case hex+pri --n 32 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_hexpri.json > gpurun_out/r02a_bench_hexpri.json 2> gpurun_out/r02a_bench_hexpri.err; tail -c 1500 gpurun_out/r02a_bench_hexpri.json
