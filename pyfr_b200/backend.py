@@ -76,6 +76,15 @@ class B200Backend(base.BaseBackend):
             v.strip() for v in str(cfg.get(sect, 'gradflux-vec2', '')).split(',')
             if v.strip() and v.strip() != '0'
         )
+        # intconu: two consecutive interface points per thread, 128-bit
+        # accesses where a side's addresses are adjacent and aligned
+        self.conu_pairs = cfg.getbool(sect, 'conu-pairs', False)
+        # order of the points of interior / boundary interfaces chosen by
+        # the host mirror: 'reference' (the reference's sort key) or
+        # 'address' (true left-hand address)
+        self.inters_order = cfg.get(sect, 'inters-order', 'reference')
+        if self.inters_order not in ('reference', 'address'):
+            raise ValueError('inters-order must be reference or address')
         self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
         self.euler_fusion = cfg.getbool(sect, 'euler-fusion', True)
         # Runge-Kutta stage update in the epilogue of the last RHS kernel

@@ -100,9 +100,20 @@ class BaseInters:
         return self._view(side, getter, (self.ndims, self.nvars), **kw)
 
     def _memory_order_perm(self, side):
-        # Order interface points by the address of their scal_fpts entry
+        # Order interface points by the address of their scal_fpts entry.
+        # The reference forms that key from a view of shape () -- for the
+        # blocked layout elements 8 apart within a run of ``leaddim``
+        # columns then tie, so five blocks interleave lane by lane (still
+        # whole sectors per warp).  ``inters-order = address`` sorts by the
+        # address in the nvars-wide layout instead: consecutive points are
+        # the consecutive lanes of one flux-point row, which is what lets
+        # ``conu-pairs`` move two points per 16-byte access.  The order of
+        # the points of an interface does not affect any result.
         m, r, c, _ = side_view_maps(side, self.elemap,
                                     'get_scal_fpts_for_inters')
+        if getattr(self._be, 'inters_order', 'reference') == 'address':
+            key = self._be.view(m, r, c, vshape=(self.nvars,)).mapping.get()
+            return np.argsort(key[0], kind='stable')
         return np.argsort(self._be.view(m, r, c, vshape=()).mapping.get()[0])
 
     def _pnorms(self, side):

@@ -182,6 +182,130 @@ __launch_bounds__(128, {getattr(be, 'cflux_minblocks', 4) if viscous else 8})
     return src, name, _names(args)
 
 
+_pair_src = r'''
+// Two consecutive interface points per thread.  Points are sorted by their
+// left-hand address, so the lanes of a block that share a flux-point row
+// follow one another: where a side's two addresses are adjacent and the
+// first is 16-byte aligned the pair moves with one 128-bit access.
+struct pair_t
+{
+    ixdtype_t a0, a1;
+    bool vec;
+};
+
+static __device__ __forceinline__ pair_t
+pair_of(const fpdtype_t *base, const ixdtype_t *__restrict__ map,
+        ixdtype_t i, bool two)
+{
+    pair_t p;
+    p.a0 = map[i];
+    p.a1 = two ? map[i + 1] : p.a0;
+    p.vec = two && p.a1 == p.a0 + 1 &&
+            (reinterpret_cast<unsigned long long>(base + p.a0)
+             & (2*sizeof(fpdtype_t) - 1)) == 0;
+    return p;
+}
+
+static __device__ __forceinline__ void
+ld_pair(const fpdtype_t *__restrict__ b, const pair_t &p, fpdtype_t &x0,
+        fpdtype_t &x1)
+{
+    if (p.vec)
+    {
+        const fpdtype2_t t = *reinterpret_cast<const fpdtype2_t *>(b + p.a0);
+        x0 = t.x; x1 = t.y;
+    }
+    else
+    {
+        x0 = b[p.a0]; x1 = b[p.a1];
+    }
+}
+
+static __device__ __forceinline__ void
+st_pair(fpdtype_t *__restrict__ b, const pair_t &p, bool two, fpdtype_t x0,
+        fpdtype_t x1)
+{
+    if (p.vec)
+    {
+        fpdtype2_t t;
+        t.x = x0; t.y = x1;
+        *reinterpret_cast<fpdtype2_t *>(b + p.a0) = t;
+    }
+    else
+    {
+        b[p.a0] = x0;
+        if (two)
+            b[p.a1] = x1;
+    }
+}
+'''
+
+
+def conu_pairs_source(be, tplargs, both=False):
+    """Interior ``intconu`` with two consecutive points per thread (backend
+    option ``conu-pairs``); same arguments as ``conu_source``, launched
+    over ``ceil(n/2)`` threads."""
+    nv, beta = tplargs['nvars'], tplargs['c']['ldg-beta']
+
+    args = (['ixdtype_t n'] + _view_arg('ulin') + _view_arg('urin') +
+            _view_arg('ulout', const=False) + _view_arg('urout', const=False))
+
+    need_l, need_r = beta != 0.5, beta != -0.5
+    st_l = both or beta != -0.5
+    st_r = both or beta != 0.5
+
+    if beta == -0.5:
+        com = ('l0', 'l1')
+    elif beta == 0.5:
+        com = ('r0', 'r1')
+    else:
+        com = tuple(f'r{k}*{ph.fpconst(0.5 + beta)} + '
+                    f'l{k}*{ph.fpconst(0.5 - beta)}' for k in (0, 1))
+
+    L = []
+    if need_l:
+        L.append('const pair_t pli = pair_of(ulin, ulin_map, i, two);')
+    if need_r:
+        L.append('const pair_t pri = pair_of(urin, urin_map, i, two);')
+    if st_l:
+        L.append('const pair_t plo = pair_of(ulout, ulout_map, i, two);')
+    if st_r:
+        L.append('const pair_t pro = pair_of(urout, urout_map, i, two);')
+
+    B = []
+    if need_l:
+        B.append('fpdtype_t l0, l1; ld_pair(ulin + K_SOA*v, pli, l0, l1);')
+    if need_r:
+        B.append('fpdtype_t r0, r1; ld_pair(urin + K_SOA*v, pri, r0, r1);')
+    B.append(f'const fpdtype_t c0 = {com[0]}, c1 = {com[1]};')
+    if st_l:
+        B.append('st_pair(ulout + K_SOA*v, plo, two, c0, c1);')
+    if st_r:
+        B.append('st_pair(urout + K_SOA*v, pro, two, c0, c1);')
+
+    nl = '\n    '
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, [('NVARS', nv)])}
+{_pair_src}
+extern "C" __global__ void __launch_bounds__(128)
+intconu({', '.join(args)})
+{{
+    const ixdtype_t i = 2*((ixdtype_t) blockIdx.x*blockDim.x + threadIdx.x);
+    if (i >= n)
+        return;
+    const bool two = i + 1 < n;
+
+    {nl.join(L)}
+
+    UNROLL for (int v = 0; v < NVARS; v++)
+    {{
+        {(nl + '    ').join(B)}
+    }}
+}}
+'''
+    return src, 'intconu', _names(args)
+
+
 def conu_source(be, tplargs, mpi, both=False):
     """``both``: also store each side's own trace where the reference
     kernel leaves it untouched (|beta| = 1/2), which makes the preceding

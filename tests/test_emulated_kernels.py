@@ -32,6 +32,10 @@ def _b200(cfg, box, vparts=None, rank=0, comm=None, nregs=2, opts={}):
     from pyfr_b200.backend import B200Backend
 
     cfg.set('backend-b200', 'graphs', os.environ.get('EMU_GRAPHS', 'false'))
+    # EMU_OPTS="conu-pairs=1;inters-order=address" runs the whole file with
+    # those backend options (as EMU_GRAPHS=true does for graph capture)
+    for kv in filter(None, os.environ.get('EMU_OPTS', '').split(';')):
+        cfg.set('backend-b200', *kv.split('=', 1))
     for k, v in opts.items():
         cfg.set('backend-b200', k, v)
 
@@ -64,6 +68,26 @@ def _kinds(sysm):
     (dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
                                'gradflux-planes': 1}, 'gradflux'),
     (dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
+    # intconu over pairs of points (128-bit accesses where both addresses
+    # of a side are adjacent): one-sided, central and left-biased LDG
+    (dict(order=2, warp=0.1), {'conu-pairs': 1}, 'intconu'),
+    (dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {'conu-pairs': 1},
+     'intconu'),
+    (dict(order=2, beta=-0.5, curved=0.5, warp=0.1), {'conu-pairs': 1},
+     'intconu'),
+    (dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0}, 'intconu'),
+    (dict(order=3), {'conu-pairs': 1, 'n-soa': 4}, 'intconu'),
+    # ... with the interface points in true address order (most pairs
+    # then take the 128-bit path)
+    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address'},
+     'intconu'),
+    (dict(order=3, rsolver='hllc', beta=0.0), {'conu-pairs': 1,
+                                               'inters-order': 'address'},
+     'intconu'),
+    (dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1,
+                                          'inters-order': 'address'},
+     'intconu'),
+    (dict(order=4), {'inters-order': 'address'}, 'gradflux'),
     # the benchmark's kernel variants (p = 4, 512 threads, 220 KB smem)
     (dict(order=4), {}, 'gradflux'),
     (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),

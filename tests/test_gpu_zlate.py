@@ -77,6 +77,16 @@ VEC2_CASES = [
      {'gradflux-vec2': 'p1,p3,p5', 'gradflux-planes': 1}),
     ('tgv', (4, 3, 3), dict(order=4, precision='single'),
      {'gradflux-vec2': 'p1,p3,p5'}),
+    # intconu over pairs of points, interface points in address order
+    ('tgv', (4, 3, 3), dict(order=4),
+     {'conu-pairs': 1, 'inters-order': 'address'}),
+    ('tgv', (4, 3, 3), dict(order=3, rsolver='hllc', beta=0.0, warp=0.1),
+     {'conu-pairs': 1, 'inters-order': 'address'}),
+    ('tgv', (3, 3, 3), dict(order=2, beta=-0.5, warp=0.1),
+     {'conu-pairs': 1}),
+    ('tgv', (4, 3, 3), dict(order=4),
+     {'conu-pairs': 1, 'inters-order': 'address',
+      'gradflux-vec2': 'p1,p3,p5'}),
 ]
 
 
@@ -314,10 +324,10 @@ def test_fused_rk_stage_update_matches_oracle(built, case, n, kw, kind):
 
 @pytest.mark.parametrize('case,n,kw,opts', VEC2_CASES, ids=str)
 def test_vectorised_gradflux_phases_match_oracle(built, case, n, kw, opts):
-    """gradflux-vec2 (added after the round's GPU budget was spent; checked
-    on the CPU execution model): same results as the default kernel's
-    oracle parity, including 16-byte alignment of every access, which only
-    the device enforces.  Last in the file on purpose."""
+    """The opt-in variants added after the round's GPU budget was spent
+    (gradflux-vec2, conu-pairs, inters-order = address; checked on the CPU
+    execution model): same parity bar as the default kernels.  Last in the
+    file on purpose."""
     cfg, box = cases.make(case, n, **kw)
     for k, v in opts.items():
         cfg.set('backend-b200', k, v)

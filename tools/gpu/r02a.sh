@@ -20,6 +20,17 @@ d = json.load(open('gpurun_out/r02a_kt_vec2_$v.json')); b = json.loads(open('gpu
 print('vec2=$v', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
 PY
 done
+# interface kernels: points in true address order (-30 % sectors per warp), intconu over pairs (128-bit accesses)
+i=0
+for o in "--opt inters-order=address" "--opt inters-order=address --opt conu-pairs=1" "--opt inters-order=address --opt conu-pairs=1 --opt gradflux-vec2=p3"; do
+  i=$((i+1))
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-clocks $o --kernel-times gpurun_out/r02a_kt_int$i.json > gpurun_out/r02a_b_int$i.json 2> gpurun_out/r02a_b_int$i.err
+  python - <<PY
+import json
+d = json.load(open('gpurun_out/r02a_kt_int$i.json')); b = json.loads(open('gpurun_out/r02a_b_int$i.json').read())
+print('$o', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
+PY
+done
 # mixed elements (BASELINE configs[3]): 24^3 cells, p = 3
 timeout 600 python bench.py --case hex+pri+pyr+tet --n 24 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_mixed.json > gpurun_out/r02a_bench_mixed.json 2> gpurun_out/r02a_bench_mixed.err; tail -c 2500 gpurun_out/r02a_bench_mixed.json; tail -3 gpurun_out/r02a_bench_mixed.err
 timeout 600 python bench.py --case hex+pri --n 32 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_hexpri.json > gpurun_out/r02a_bench_hexpri.json 2> gpurun_out/r02a_bench_hexpri.err; tail -c 1500 gpurun_out/r02a_bench_hexpri.json
