@@ -129,13 +129,29 @@ class BaseElements:
         b, nd, ne = self.basis, self.ndims, self.neles
         mpts, nm = b.mpts, b.nmpts
 
-        x = self.ploc_at_np('mpts').swapaxes(1, 2)        # (nm, ne, nd)
         D = [b.mbasis_deriv_at(mpts, d) for d in range(nd)]
+        xall = self.ploc_at_np('mpts').swapaxes(1, 2)     # (nm, ne, nd)
+
+        smats = np.empty((nd, nm, nd, ne))
+        djac = np.empty((nm, ne))
+
+        # Element chunks: the 3-D form holds ~20 temporaries of the size
+        # of ``x``; whole-mesh arrays would put the set-up of a 64^3 brick
+        # at 20 GB per rank
+        step = max(1, (1 << 22) // (nm*nd))
+        for e0 in range(0, ne, step):
+            sl = slice(e0, min(e0 + step, ne))
+            self._metric_chunk(D, np.ascontiguousarray(xall[:, sl]),
+                               smats[..., sl], djac[:, sl])
+
+        return smats, djac
+
+    def _metric_chunk(self, D, x, smats, djac):
+        nd = self.ndims
+        nm, ne = x.shape[:2]
 
         # dx[d][p, e, i] = d x_i / d xi_d
         dx = [(Dd @ x.reshape(nm, -1)).reshape(nm, ne, nd) for Dd in D]
-
-        smats = np.empty((nd, nm, nd, ne))
 
         if nd == 2:
             a, bb = dx[0][..., 0], dx[0][..., 1]
@@ -143,7 +159,7 @@ class BaseElements:
 
             smats[0, :, 0], smats[0, :, 1] = d, -c
             smats[1, :, 0], smats[1, :, 1] = -bb, a
-            djac = a*d - bb*c
+            djac[:] = a*d - bb*c
         else:
             # T_j = x cross dx/dxi_j, then S_i = (D_j T_k - D_k T_j)/2
             # (component form: np.cross is several times slower on
@@ -163,7 +179,7 @@ class BaseElements:
                 s = 0.5*(DT[k][j] - DT[j][k])
                 smats[i] = s.swapaxes(1, 2)
 
-            djac = np.einsum('pei,pei->pe', dx[0], cross(dx[1], dx[2]))
+            djac[:] = np.einsum('pei,pei->pe', dx[0], cross(dx[1], dx[2]))
 
         return smats, djac
 
