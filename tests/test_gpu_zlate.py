@@ -344,3 +344,74 @@ def test_vectorised_gradflux_phases_match_oracle(built, case, n, kw, opts):
     else:
         _, ext = oracle_rhs(case, n, extended=True, **kw)
         assert_parity(out, ref[0], ext[0], TOL64)
+
+
+VARIANT_REPORT = [
+    ('default', []),
+    ('vec2=p3', ['gradflux-vec2=p3']),
+    ('vec2=p1,p3,p5', ['gradflux-vec2=p1,p3,p5']),
+    ('address', ['inters-order=address']),
+    ('address+pairs', ['inters-order=address', 'conu-pairs=1']),
+    ('address+pairs+vec2=p3', ['inters-order=address', 'conu-pairs=1',
+                               'gradflux-vec2=p3']),
+]
+
+
+def test_zz_opt_in_variant_timing_report(built):
+    """Not a parity test: times the opt-in kernel variants next to the
+    default path through bench.py (32^3 hexes, p = 4, fp64: banks larger
+    than L2) and reports the per-kernel CUDA-event times as a warning in the
+    pytest summary and in gpurun_out/variant_timings.json, so that every
+    device run of the suite leaves the numbers the defaults are chosen
+    from.  Only the default variant has to run; a failing opt-in variant is
+    recorded, its correctness being the business of the parity cases
+    above."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    import warnings
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    report = {}
+
+    with tempfile.TemporaryDirectory() as td:
+        for tag, opts in VARIANT_REPORT:
+            kt = os.path.join(td, 'kt.json')
+            cmd = [sys.executable, os.path.join(root, 'bench.py'), '--n', '32',
+                   '--steps', '10', '--warmup', '3', '--no-cpu', '--no-e2e',
+                   '--no-clocks', '--kernel-times', kt]
+            for o in opts:
+                cmd += ['--opt', o]
+
+            try:
+                res = subprocess.run(cmd, capture_output=True, text=True,
+                                     timeout=300, cwd=root)
+                if res.returncode or not res.stdout.strip():
+                    raise RuntimeError(f'bench.py rc={res.returncode}: '
+                                       + res.stderr.strip()[-200:])
+                line = json.loads(res.stdout.strip().splitlines()[-1])
+                with open(kt) as f:
+                    kern = json.load(f)['kernels']
+                report[tag] = {
+                    'gdof_s': round(line['value'], 2),
+                    'ms_per_rhs': round(line['ms_per_step'], 4),
+                    'kernels_ms': {k.split(':', 1)[-1]: round(v['ms'], 4)
+                                   for k, v in kern.items()}
+                }
+            except Exception as e:
+                report[tag] = {'error': f'{type(e).__name__}: {e}'[:300]}
+
+    try:
+        os.makedirs(os.path.join(root, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(root, 'gpurun_out',
+                               'variant_timings.json'), 'w') as f:
+            json.dump(report, f, indent=1)
+    except OSError:
+        pass
+
+    warnings.warn('opt-in variant timings (TGV NS 32^3 p=4 fp64): '
+                  + json.dumps(report))
+
+    assert 'error' not in report['default'], report['default']
