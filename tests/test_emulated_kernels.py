@@ -329,6 +329,37 @@ def test_bench_script_end_to_end(emulated, monkeypatch, capsys):
                                      'frac', 'traffic'}
 
 
+def test_bench_script_with_opt_in_variants(emulated, monkeypatch, capsys,
+                                           tmp_path):
+    """The invocation the device suite's variant timing report makes
+    (tests/test_gpu_zlate.py): bench.py with --opt switches and
+    --kernel-times."""
+    import json
+    import runpy
+
+    from test_gpu_zlate import VARIANT_REPORT
+
+    monkeypatch.setattr(emu.EmuRuntime, 'elapsed_ms', lambda s, a, b: 1.0)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    kt = str(tmp_path / 'kt.json')
+
+    tag, opts = VARIANT_REPORT[-1]
+    argv = ['bench.py', '--n', '2', '--order', '2', '--steps', '2',
+            '--warmup', '1', '--no-cpu', '--no-e2e', '--no-clocks',
+            '--no-graphs', '--kernel-times', kt]
+    for o in opts:
+        argv += ['--opt', o]
+    monkeypatch.setattr(sys, 'argv', argv)
+    runpy.run_path(os.path.join(root, 'bench.py'), run_name='__main__')
+
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line['value'] > 0 and line['launches_per_step'] == 5
+    with open(kt) as f:
+        kern = json.load(f)['kernels']
+    assert any(k.endswith('gradflux') for k in kern)
+    assert all('ms' in v for v in kern.values())
+
+
 @pytest.mark.parametrize('case,n,kw', [
     ('tgv', (3, 2, 2), dict(order=2, warp=0.1, antialias='surf-flux')),
     ('tgv', (3, 2, 2), dict(order=2, antialias='flux, surf-flux',
