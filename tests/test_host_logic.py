@@ -448,3 +448,45 @@ def test_irregular_partition_reproduces_single_partition():
     for r, o in enumerate(out):
         gidx = box.local_mesh(vparts, r).eidxs['hex']
         assert rel_err(o, ref[0][..., gidx]) < 5e-13
+
+
+@pytest.mark.parametrize('case,n,kw', [
+    ('tgv', (4, 3, 3), dict(order=2, warp=0.1)),
+    ('tgv', (3, 3, 3), dict(order=3, beta=-0.5)),
+    ('tgv', (3, 3, 3), dict(order=2, beta=0.0, rsolver='hllc')),
+], ids=str)
+def test_address_order_of_interface_points(case, n, kw):
+    """inters-order = address: the points of the interior interfaces follow
+    the true left-hand (for beta = -1/2: right-hand) address, i.e. the
+    lanes of a block that share a flux-point row are consecutive; the
+    reference's order (the default) keeps its own key, under which blocks
+    interleave.  Either way the views hold the same set of points."""
+    from pyfr_b200.backend import B200Backend
+
+    maps = {}
+    for order in ('reference', 'address'):
+        cfg, box = cases.make(case, n, **kw)
+        cfg.set('backend-b200', 'inters-order', order)
+        be = B200Backend(cfg, dry=True)
+        sysm = get_system(be, box.local_mesh(), cfg, 2)
+        conu, = [k for g in sysm.rhs_graphs(0, 1) for w, k in g.plan
+                 if w == 'kernel' and getattr(k, 'kind', None) == 'intconu']
+        side = 'urin' if kw.get('beta') == -0.5 else 'ulin'
+        maps[order] = tuple(
+            getattr(conu.info[s], 'view', conu.info[s]).mapping.get()[0]
+            .astype(np.int64) for s in (side, 'ulin', 'urin')
+        )
+
+    ref, adr = maps['reference'], maps['address']
+    assert np.all(np.diff(adr[0]) > 0)
+    assert not np.all(np.diff(ref[0]) > 0) or len(ref[0]) < 64
+
+    # Same interfaces: the (left, right) address pairs agree as sets
+    pr = set(zip(ref[1].tolist(), ref[2].tolist()))
+    pa = set(zip(adr[1].tolist(), adr[2].tolist()))
+    assert pr == pa and len(pr) == len(ref[1])
+
+    with pytest.raises(ValueError):
+        cfg, box = cases.make(case, n, **kw)
+        cfg.set('backend-b200', 'inters-order', 'random')
+        B200Backend(cfg, dry=True)
