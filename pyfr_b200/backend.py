@@ -64,6 +64,9 @@ class B200Backend(base.BaseBackend):
             raise ValueError('n-csub must be a multiple of n-soa')
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
+        # fp64 operators with at least this many distinct coefficients keep
+        # them in __constant__ memory (0: always literals)
+        self.mul_const_table = cfg.getint(sect, 'mul-const-table', 0)
         self.cflux_minblocks = cfg.getint(sect, 'cflux-minblocks', 5)
         self.gradflux_maxctas = cfg.getint(sect, 'gradflux-maxctas', 2)
         self.gradflux_threads = cfg.getint(sect, 'gradflux-threads', 0)

@@ -120,6 +120,20 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
     if (LD*isz) % 16:
         raise ValueError('Row size must be a multiple of 16 bytes')
 
+    # Coefficients: a 64-bit literal costs two uniform-register moves per
+    # use unless it stays in a uniform register for the whole kernel, which
+    # only works for operators with a handful of distinct values (hexes:
+    # 6-13).  Dense operators (tets, pyramids: thousands of distinct
+    # values; 1989 UMOV next to 2768 DFMA for the 90x56 one) can read them
+    # as constant-bank operands of the FMA instead (opt-in until timed).
+    uniq = np.unique(A[A != 0])
+    ctab = (getattr(be, 'mul_const_table', 0) and isz == 8 and
+            getattr(be, 'mul_const_table', 0) <= len(uniq) <= 7000)
+    cidx = {float(v): i for i, v in enumerate(uniq)} if ctab else None
+    coef = ((lambda a: f'KC[{cidx[float(a)]}]') if ctab else ph.fpconst)
+    cdecl = (f'\n__constant__ fpdtype_t KC[{len(uniq)}] = {{'
+             + ', '.join(ph.fpconst(v) for v in uniq) + '};') if ctab else ''
+
     chunks = plan_chunks(K, LD, isz, smem_budget, chunk_hint)
     nchunks = len(chunks)
     crows = chunks[0][1] - chunks[0][0]
@@ -140,9 +154,9 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
         for k, a in terms:
             t = f'sm[{(k - k0)*LD} + col]'
             if expr is None:
-                expr = f'{ph.fpconst(a)}*{t}'
+                expr = f'{coef(a)}*{t}'
             else:
-                expr = f'fma({ph.fpconst(a)}, {t}, {expr})'
+                expr = f'fma({coef(a)}, {t}, {expr})'
 
         return expr
 
@@ -228,7 +242,7 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
 #define CROWS {crows}
 #define TILE (CROWS*LD)
 #define NTHREADS {nthreads}
-{_pipeline_src}
+{_pipeline_src}{cdecl}
 
 // out[{M} x LD] = A[{M} x {K}] @ b[{K} x LD] per element block;
 // {int(np.count_nonzero(A))} non-zeros, {nchunks} chunk(s) of {crows} rows

@@ -601,6 +601,22 @@ def test_mixed_element_types(emulated, pattern, n, kw, nfused):
     assert kinds.count('fluxdiv') + kinds.count('gradflux') == nfused
 
 
+def test_dense_operators_from_constant_table(emulated):
+    """mul-const-table: operators with many distinct coefficients (tets,
+    pyramids) read them from __constant__ memory instead of literals."""
+    import functools
+
+    b200 = functools.partial(_b200, opts={'mul-const-table': 32})
+    (ref, ext, out), sysm = _mixed_outs('hex+pri+pyr+tet', (4, 2, 2),
+                                        dict(order=3), b200)
+    for o, r, e in zip(out, ref, ext):
+        assert_parity(o, r, e, 1e-12)
+
+    muls = [k for g in sysm.rhs_graphs(0, 1) for w, k in g.plan
+            if w == 'kernel' and (k.kind or '').startswith('mul')]
+    assert muls
+
+
 def test_bench_script_mixed_case(emulated, monkeypatch, capsys):
     """bench.py --case hex+pri: the configs[3]-style diagnostic mode."""
     import json

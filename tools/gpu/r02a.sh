@@ -34,6 +34,8 @@ PY
 done
 # mixed elements (BASELINE configs[3]): 24^3 cells, p = 3
 timeout 600 python bench.py --case hex+pri+pyr+tet --n 24 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_mixed.json > gpurun_out/r02a_bench_mixed.json 2> gpurun_out/r02a_bench_mixed.err; tail -c 2500 gpurun_out/r02a_bench_mixed.json; tail -3 gpurun_out/r02a_bench_mixed.err
+# ... with the dense operators' coefficients in __constant__ memory (LDCU pairs instead of two UMOV per DFMA)
+timeout 600 python bench.py --case hex+pri+pyr+tet --n 24 --order 3 --steps 20 --warmup 5 --opt mul-const-table=32 --kernel-times gpurun_out/r02a_kt_mixed_ct.json > gpurun_out/r02a_bench_mixed_ct.json 2> gpurun_out/r02a_bench_mixed_ct.err; tail -c 900 gpurun_out/r02a_bench_mixed_ct.json
 timeout 600 python bench.py --case hex+pri --n 32 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_hexpri.json > gpurun_out/r02a_bench_hexpri.json 2> gpurun_out/r02a_bench_hexpri.err; tail -c 1500 gpurun_out/r02a_bench_hexpri.json
 # RK45 time stepping: separate stage-update kernels vs the fused epilogue (fixed CFL number => same steps)
 for f in "" "--fused-update"; do
