@@ -32,6 +32,15 @@ d = json.load(open('gpurun_out/r02a_kt_int$i.json')); b = json.loads(open('gpuru
 print('$o', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
 PY
 done
+# opmul M3 + negdivconf sits at 87 % of the HBM peak with 160 active threads per SM: more row groups = more loads of `out` in flight
+for rg in 6 8; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-clocks --opt mul-rowgroups=$rg --kernel-times gpurun_out/r02a_kt_rg$rg.json > gpurun_out/r02a_b_rg$rg.json 2> gpurun_out/r02a_b_rg$rg.err
+  python - <<PY
+import json
+d = json.load(open('gpurun_out/r02a_kt_rg$rg.json')); b = json.loads(open('gpurun_out/r02a_b_rg$rg.json').read())
+print('rowgroups=$rg', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
+PY
+done
 # mixed elements (BASELINE configs[3]): 24^3 cells, p = 3
 timeout 600 python bench.py --case hex+pri+pyr+tet --n 24 --order 3 --steps 20 --warmup 5 --kernel-times gpurun_out/r02a_kt_mixed.json > gpurun_out/r02a_bench_mixed.json 2> gpurun_out/r02a_bench_mixed.err; tail -c 2500 gpurun_out/r02a_bench_mixed.json; tail -3 gpurun_out/r02a_bench_mixed.err
 # ... with the dense operators' coefficients in __constant__ memory (LDCU pairs instead of two UMOV per DFMA)
