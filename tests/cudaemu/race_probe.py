@@ -34,16 +34,23 @@ from pyfr_b200 import cases                                  # noqa: E402
 from pyfr_b200.backend import B200Backend                    # noqa: E402
 from pyfr_b200.host.system import get_system                 # noqa: E402
 
-runs = [('tgv', (3, 2, 2), dict(order=2, warp=0.1)),
-        ('tgv', (3, 2, 2), dict(order=2)),
-        ('tgv', 2, dict(order=4)),
-        ('vortex', 5, dict(order=3))]
+runs = [('tgv', (3, 2, 2), dict(order=2, warp=0.1), {}),
+        ('tgv', (3, 2, 2), dict(order=2), {}),
+        ('tgv', 2, dict(order=4), {}),
+        ('vortex', 5, dict(order=3), {}),
+        # opt-in variants: 16-byte accesses over column / point pairs
+        ('tgv', (3, 2, 2), dict(order=2, warp=0.1),
+         {'gradflux-vec2': 'p1,p3,p5', 'conu-pairs': 1,
+          'inters-order': 'address'}),
+        ('tgv', 2, dict(order=4), {'gradflux-vec2': 'p1,p3,p5'})]
 if '--drop-barrier' in sys.argv:
     runs = runs[:1]
 
-for case, n, kw in runs:
+for case, n, kw, opts in runs:
     cfg, box = cases.make(case, n, **kw)
     cfg.set('backend-b200', 'graphs', 'false')
+    for k, v in opts.items():
+        cfg.set('backend-b200', k, v)
     s = get_system(B200Backend(cfg), box.local_mesh(), cfg, 2)
     s.rhs(0.0, 0, 1)
     s.rhs(0.0, 0, 1)
