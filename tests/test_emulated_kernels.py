@@ -133,10 +133,14 @@ def test_vectorised_gradflux_device_cases(emulated, case, n, kw, opts):
         assert_parity(out, ref[0], ext[0], 1e-12)
 
 
-def test_fp32_kernels(emulated):
+@pytest.mark.parametrize('opts', [
+    {}, {'gradflux-vec2': 'p1,p3,p5', 'conu-pairs': 1,
+         'inters-order': 'address'}
+], ids=['default', 'vec2+pairs'])
+def test_fp32_kernels(emulated, opts):
     n, kw = (3, 2, 2), dict(order=2, warp=0.1)
     cfg, box = cases.make('tgv', n, precision='single', **kw)
-    sysm = _b200(cfg, box)
+    sysm = _b200(cfg, box, opts=opts)
     sysm.rhs(0.0, 0, 1)
     out = sysm.ele_scal_upts(1)[0]
 
