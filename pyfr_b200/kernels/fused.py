@@ -344,7 +344,7 @@ class PhaseEmitter:
         of shared-memory wavefronts -- for phases that are bound by
         instruction issue rather than by shared-memory bandwidth."""
         LD, isz, K, out = self.LD, self.isz, self.K, []
-        vec = bool(vec) and LD % 2 == 0 and (LD*isz) % (2*isz) == 0
+        vec = bool(vec) and LD % 2 == 0
         NC = 2 if vec else (self.ncol if LD % self.ncol == 0 else 1)
         W, WB = LD // NC, (LD // NC)*isz
         CW = 2*isz if vec else isz          # bytes between items' columns
