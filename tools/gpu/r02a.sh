@@ -20,6 +20,15 @@ d = json.load(open('gpurun_out/r02a_kt_vec2_$v.json')); b = json.loads(open('gpu
 print('vec2=$v', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
 PY
 done
+# with half as many work items per phase the best CTA size may move
+for t in 384 640; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-clocks --opt gradflux-vec2=p1,p3,p5 --opt gradflux-threads=$t --kernel-times gpurun_out/r02a_kt_vec2_t$t.json > gpurun_out/r02a_b_vec2_t$t.json 2> gpurun_out/r02a_b_vec2_t$t.err
+  python - <<PY
+import json
+d = json.load(open('gpurun_out/r02a_kt_vec2_t$t.json')); b = json.loads(open('gpurun_out/r02a_b_vec2_t$t.json').read())
+print('vec2 threads=$t', round(b['value'],2), round(b['ms_per_step'],3), {k: round(x['ms'],3) for k, x in d['kernels'].items()}, b['compiler'])
+PY
+done
 PYFR_B200_KEEP_SRC=1 ncu --set full --clock-control none --import-source on -k regex:"gradflux" -s 3 -c 1 -o gpurun_out/gradflux_r02a_vec2p3 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-graphs --no-clocks --opt gradflux-vec2=p3 > gpurun_out/ncu_v.log 2>&1; tail -1 gpurun_out/ncu_v.log | cut -c1-200
 # interface kernels: points in true address order (-30 % sectors per warp), intconu over pairs (128-bit accesses)
 i=0
