@@ -175,6 +175,10 @@ def make_backend(base, name='oracle-numpy'):
             A = a.get()
             ext = self.backend.extended_mul
 
+            # Kept so that a test can form the magnitude of the terms an
+            # output is summed from (running-error bound, tests/util.py)
+            self.backend.mul_log.append((A, b, out, alpha, beta))
+
             def run():
                 B, C = _mat3(b), _mat3(out)
 
@@ -319,6 +323,7 @@ def make_backend(base, name='oracle-numpy'):
             self.blocks = cfg.getbool('backend-oracle', 'blocks', False)
             self.extended_mul = cfg.getbool('backend-oracle', 'extended-mul',
                                             False)
+            self.mul_log = []
 
             self.pointwise = PointwiseProvider(self)
             self._providers = [BlasProvider(self), self.pointwise]

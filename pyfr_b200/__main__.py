@@ -99,8 +99,10 @@ def main(argv=None):
             be.commit()
         buf = bufs[len(arr)]
         buf.set(arr[None])
-        comm.allreduce(buf.data, len(arr), 1, {'sum': 0, 'max': 2}[op],
-                       be.stream)
+        # (NCCL dtype code of the buffer's precision: 1 = float64)
+        comm.allreduce(buf.data, len(arr),
+                       1 if be.fpdtype == np.float64 else 0,
+                       {'sum': 0, 'max': 2}[op], be.stream)
         be.wait()
         out = buf.get()[0]
         return out if np.ndim(vals) else float(out[0])

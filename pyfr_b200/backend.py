@@ -21,6 +21,57 @@ from pyfr_b200.compiler import KernelCompiler
 from pyfr_b200.lib import load_runtime
 
 
+class RuntimeScalars:
+    """Run-time scalar kernel arguments (``t`` of time-dependent boundary
+    data, ``dt`` of a stage update) kept in device memory.
+
+    The reference updates such arguments on the executable graph's nodes
+    (``pyfr/backends/cuda/types.py:86-97``, ``cuGraphExecKernelNodeSetParams``).
+    Here a kernel takes a *pointer* to its scalar instead: ``bind`` writes
+    the host mirror, ``flush`` (issued before a graph is launched) uploads
+    the changed range with one small copy on the compute stream, and the
+    captured graph is replayed unchanged -- no re-capture when ``t`` or
+    ``dt`` moves.  The host mirror is pageable memory on purpose: the copy
+    is then staged at call time, so the next ``bind`` cannot race with a
+    copy that has not executed yet."""
+
+    nslots = 4096
+
+    def __init__(self, be):
+        self.be = be
+        self.host = np.zeros(self.nslots, dtype=be.fpdtype)
+        self.dev = None
+        self.nused = 0
+        self.lo, self.hi = self.nslots, 0
+
+    def alloc(self):
+        if self.nused == self.nslots:
+            raise RuntimeError('Out of run-time scalar slots')
+        if self.dev is None:
+            self.dev = types.DevAlloc(self.be.rt, self.host.nbytes)
+        self.nused += 1
+        return self.nused - 1
+
+    def ptr(self, idx):
+        return int(self.dev) + idx*self.host.itemsize
+
+    def set(self, idx, value):
+        # compared in the storage type (a float32 slot holding 0.1f does
+        # not differ from the Python double 0.1 bound again)
+        v = self.host.dtype.type(value)
+        if self.host[idx] != v:
+            self.host[idx] = v
+            self.lo, self.hi = min(self.lo, idx), max(self.hi, idx + 1)
+
+    def flush(self, stream):
+        if self.hi > self.lo and not self.be.rt.dry:
+            isz = self.host.itemsize
+            self.be.rt.memcpy_async(int(self.dev) + self.lo*isz,
+                                    self.host.ctypes.data + self.lo*isz,
+                                    (self.hi - self.lo)*isz, stream)
+        self.lo, self.hi = self.nslots, 0
+
+
 class B200Backend(base.BaseBackend):
     name = 'b200'
     blocks = True
@@ -107,7 +158,11 @@ class B200Backend(base.BaseBackend):
         self.fork_event = rt.new_ptr(rt.event_create)
         self.join_event = rt.new_ptr(rt.event_create)
 
+        self.rtscal = RuntimeScalars(self)
+
         self.comm = comm
+        if hasattr(comm, 'attach'):
+            comm.attach(rt)
         self.pointwise = providers.PointwiseProvider(self)
         self._providers = [providers.OperatorProvider(self),
                            providers.BlasExtProvider(self),
@@ -117,6 +172,7 @@ class B200Backend(base.BaseBackend):
         return types.DevAlloc(self.rt, nbytes)
 
     def run_kernels(self, kernels, wait=False):
+        self.rtscal.flush(self.stream)
         for k in kernels:
             k.run(self.stream)
 

@@ -28,19 +28,40 @@ def _rendezvous(rank, size, payload, addr, port, timeout=300):
         srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
         srv.bind((addr, port))
         srv.listen(size)
+        srv.settimeout(timeout)
 
-        for _ in range(size - 1):
-            conn, _ = srv.accept()
-            conn.sendall(payload)
-            conn.close()
+        # Every other rank announces itself with its rank number; a stray
+        # connection (or a rank connecting twice) is dropped instead of
+        # consuming one of the size - 1 replies
+        seen = set()
+        try:
+            while len(seen) < size - 1:
+                conn, _ = srv.accept()
+                with conn:
+                    conn.settimeout(10)
+                    try:
+                        hello = conn.recv(16)
+                        r = int(hello.decode().strip() or -1)
+                    except (OSError, ValueError):
+                        continue
+                    if not (0 < r < size) or r in seen:
+                        continue
+                    conn.sendall(payload)
+                    seen.add(r)
+        except socket.timeout:
+            raise TimeoutError(f'NCCL id rendezvous: only ranks '
+                               f'{sorted(seen)} of {size - 1} reported '
+                               f'within {timeout} s')
+        finally:
+            srv.close()
 
-        srv.close()
         return payload
 
     deadline = time.time() + timeout
     while True:
         try:
             with socket.create_connection((addr, port), timeout=5) as s:
+                s.sendall(f'{rank:<16d}'.encode())
                 buf = b''
                 while len(buf) < ID_BYTES:
                     chunk = s.recv(ID_BYTES - len(buf))
@@ -57,6 +78,16 @@ def _rendezvous(rank, size, payload, addr, port, timeout=300):
             raise TimeoutError('NCCL id rendezvous timed out')
 
         time.sleep(0.2)
+
+
+def _xchg_words(m):
+    """Words moved for one exchange matrix: the dense ``[nrow][ncol]`` image.
+    An ``align`` tag would pad the rows; such a matrix cannot be sent as one
+    contiguous run."""
+    if m.leaddim != m.ncol:
+        raise ValueError('Exchange matrices must be tightly packed '
+                         f'(leaddim {m.leaddim} != ncol {m.ncol})')
+    return m.nrow*m.ncol
 
 
 class NCCLComm:
@@ -99,7 +130,7 @@ class NCCLComm:
 
         for r in reqs:
             m = r.mat
-            n = m.nrow*m.ncol
+            n = _xchg_words(m)
             fn = rt.nccl_send if r.kind == 'send' else rt.nccl_recv
             fn(self._handle, m.data, n, self._dtype(m), r.peer, stream)
 
@@ -122,3 +153,83 @@ class NCCLComm:
         if self._handle and destroy:
             self.rt.nccl_destroy(self._handle)
         self._handle = None
+
+
+class LoopbackWorld:
+    """Several partitions in ONE process on ONE device.
+
+    Every partition has its own backend (streams, graphs, exchange
+    matrices); what would travel between ranks is copied device-to-device
+    instead.  A send is a ``b200_memcpy_async`` of the packed ``XchgMatrix``
+    into a mailbox buffer, issued on the stream the real exchange would use
+    (and captured into the CUDA graph like it); a receive registers its
+    destination.  ``deliver()`` plays the part of the transport: called
+    between the stages of an RHS evaluation, after every partition has run
+    its graph of that stage, it copies each mailbox into the matching
+    receive buffer.  (It copies *every* registered pair each time; a
+    receive buffer is only read in the stage that follows the one its data
+    was sent in, so re-delivering older mailboxes is harmless.)
+
+    This drives the partition-boundary path -- ``pack``, ``mpiconu``,
+    ``mpicflux`` and the exchange matrices -- on a single GPU, with the
+    semantics of ``pyfr/solvers/base/system.py:185-202`` and the requests
+    of ``pyfr/backends/base/types.py:250-257``."""
+
+    def __init__(self, size):
+        self.size = size
+        self.box, self.recvs = {}, {}
+        self.rt = None
+
+    def peer(self, rank):
+        return LoopbackComm(self, rank)
+
+    def deliver(self):
+        rt = self.rt
+        if rt is None:
+            return
+
+        rt.device_sync()
+        for key, (dst, nb) in self.recvs.items():
+            src = self.box.get(key)
+            if src is not None:
+                if src[1] != nb:
+                    raise ValueError(f'Exchange {key}: sent {src[1]} bytes, '
+                                     f'receiver expects {nb}')
+                rt.memcpy(dst, src[0], nb)
+
+    def run_lockstep(self, systems, t, uin, fout):
+        """One RHS evaluation of all partitions, graph stage by stage."""
+        for s in systems:
+            for ks in s._get_kernels(uin, fout).values():
+                for k in ks:
+                    if k.rtnames:
+                        k.bind(t=t)
+
+        for stage in zip(*[s.rhs_graphs(uin, fout) for s in systems]):
+            for s, g in zip(systems, stage):
+                s.backend.run_graph(g)
+            self.deliver()
+
+
+class LoopbackComm:
+    def __init__(self, world, rank):
+        self.world, self.rank, self.size = world, rank, world.size
+        self.rt = None
+
+    def attach(self, rt):
+        self.rt = self.world.rt = rt
+
+    def exchange(self, reqs, stream):
+        w, rt = self.world, self.rt
+
+        for r in reqs:
+            m = r.mat
+            nb = _xchg_words(m)*m.itemsize
+
+            if r.kind == 'send':
+                key = (self.rank, r.peer, r.tag)
+                if key not in w.box:
+                    w.box[key] = (rt.new_ptr(rt.malloc, max(nb, 1)), nb)
+                rt.memcpy_async(w.box[key][0], m.data, nb, stream)
+            else:
+                w.recvs[r.peer, self.rank, r.tag] = (m.data, nb)

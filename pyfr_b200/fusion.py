@@ -262,7 +262,7 @@ def _rk_tail(be, kerns, fout):
     arguments, extra matrices, rk traffic in bank passes).  The stage
     update must consume the RHS bank ``fout`` as its ``r2``."""
     if not kerns or getattr(kerns[-1], 'kind', None) != 'rkvdh2':
-        return kerns, None, [], [], 0
+        return kerns, None, [], [], 0, None
     if not be.rk_fusion:
         raise kfused.NotFusable('rk fusion disabled')
 
@@ -271,24 +271,21 @@ def _rk_tail(be, kerns, fout):
     if not _same(i['r2'], fout) or r1.traits != fout.traits:
         raise kfused.NotFusable('rkvdh2 does not follow this RHS')
 
+    from pyfr_b200.providers import rt_scalar
+
     regs = [r1] + ([i['rold'], i['rerr']] if tpl['errest'] else [])
     args = [a for m in regs for a in (('p', m.data), ('l', m.blocksz))]
-    args.append(('d' if be.fpdtype == np.float64 else 'f', 0.0))
+    dtarg, dtset = rt_scalar(be)
+    args.append(dtarg)
 
     last = tpl['stage'] == tpl['nstages'] - 1
     passes = 2 + (2 if tpl['errest'] else 0) - (1 if last else 0)
-    return kerns[:-1], tpl, args, regs, passes
+    return kerns[:-1], tpl, args, regs, passes, dtset
 
 
-def _bind_dt(k, nargs):
+def _bind_dt(k, dtset):
     """Gives a fused kernel the ``bind(dt=)`` of the rkvdh2 it absorbed."""
-    idt = nargs - 1
-
-    def bind(dt=0.0):
-        if k._vals[idt].value != dt:
-            k.set_arg(idt, dt)
-
-    k.rtnames, k.bind = ('dt',), bind
+    k.rtnames, k.bind = ('dt',), lambda dt=0.0: dtset(dt)
 
 
 def fuse_tdivtconf_negdivconf(be, kerns, subs):
@@ -299,8 +296,8 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
         return None
 
     allk = kerns
-    kerns, rk, rkargs, rkmats, rkpasses = _rk_tail(be, kerns,
-                                                   kerns[0].info['out'])
+    kerns, rk, rkargs, rkmats, rkpasses, dtset = _rk_tail(
+        be, kerns, kerns[0].info['out'])
     if len(kerns) != 2:
         return None
 
@@ -345,7 +342,7 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     # negdivconf carries the (unused here) run-time argument t
     k.rtnames = ()
     if rk:
-        _bind_dt(k, len(args))
+        _bind_dt(k, dtset)
     return [k]
 
 
@@ -359,8 +356,8 @@ def fuse_fluxdiv(be, kerns, subs):
         return None
 
     allk = kerns
-    kerns, rk, rkargs, rkmats, rkpasses = _rk_tail(be, kerns,
-                                                   kerns[1].info['out'])
+    kerns, rk, rkargs, rkmats, rkpasses, dtset = _rk_tail(
+        be, kerns, kerns[1].info['out'])
     if len(kerns) != 4:
         return None
 
@@ -428,8 +425,10 @@ def fuse_fluxdiv(be, kerns, subs):
 
         if rk:
             # the stage registers of this region's blocks
-            args += [(c, v + b0*rkmats[i // 2].blocksz*isz) if c == 'p' else
-                     (c, v) for i, (c, v) in enumerate(rkargs)]
+            # (the trailing pointer is the run-time scalar dt)
+            args += [(c, v + b0*rkmats[i // 2].blocksz*isz)
+                     if c == 'p' and i < 2*len(rkmats) else (c, v)
+                     for i, (c, v) in enumerate(rkargs)]
 
         kern = B200Kernel(
             be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
@@ -440,7 +439,7 @@ def fuse_fluxdiv(be, kerns, subs):
             info=dict(replaces=allk)
         )
         if rk:
-            _bind_dt(kern, len(args))
+            _bind_dt(kern, dtset)
         out.append(kern)
 
     return out

@@ -143,7 +143,7 @@ def fluxdiv_source(be, ops, tplargs, pts, LD, rk=None):
         regs = ['r1'] + (['rold', 'rerr'] if rk['errest'] else [])
         rkargs = ''.join(f',\n        fpdtype_t* __restrict__ {n}, '
                          f'long long {n}_bsz' for n in regs)
-        rkargs += ',\n        fpdtype_t dt'
+        rkargs += ',\n        const fpdtype_t* __restrict__ dt_p'
     else:
         out_stmt = f'fout[fob + item] = -RJ[p*C_SUB + e]*({psum});'
         rkargs = ''
@@ -181,6 +181,7 @@ fluxdiv(int nblocks, int neles,
         reinterpret_cast<unsigned char *>({tail}) + {em.table_bytes});
 
     const int tid = threadIdx.x;
+    {'const fpdtype_t dt = *dt_p;' if rk else ''}
 
     {em.stage(tail)}
     {geo_stage}

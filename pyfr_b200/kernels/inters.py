@@ -574,7 +574,7 @@ def bc_source(be, tplargs, viscous, kind, has_ploc):
             ('C_GM1', ph.fpconst(c['gamma'] - 1))]
     defs += ph.physics_defines(c, tplargs.get('visc_corr', 'none'), viscous)
 
-    head = _head + _normal_src()
+    head = _head + '    const fpdtype_t t = *t_p;\n' + _normal_src()
     if has_ploc:
         head += r'''
     fpdtype_t ploc[NDIMS];
@@ -588,7 +588,7 @@ def bc_source(be, tplargs, viscous, kind, has_ploc):
     if has_ploc:
         tail_args += ['const fpdtype_t* __restrict__ plocp',
                       'long long ploc_ld']
-    tail_args += ['fpdtype_t t']
+    tail_args += ['const fpdtype_t* __restrict__ t_p']
 
     if kind == 'bcconu':
         args = (['ixdtype_t n'] + _view_arg('ulin')

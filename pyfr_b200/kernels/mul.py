@@ -233,7 +233,7 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
         regs = ['r1'] + (['rold', 'rerr'] if rk['errest'] else [])
         extra_args += ''.join(f', fpdtype_t* __restrict__ {n}, '
                               f'long long {n}_bsz' for n in regs)
-        extra_args += ', fpdtype_t dt'
+        extra_args += ', const fpdtype_t* __restrict__ dt_p'
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz)}
@@ -257,6 +257,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
 
     const int tid = threadIdx.x;
     const int col = tid % {32*wpr}, rg = tid / {32*wpr};
+    {'const fpdtype_t dt = *dt_p;' if rk else ''}
     const bool active = col < LD;
 
     // Work items: (block, chunk) pairs owned by this CTA, in order

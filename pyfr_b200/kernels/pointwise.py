@@ -267,7 +267,7 @@ def fieldeval_source(be, tplargs, npts):
         args += ['const fpdtype_t* __restrict__ wts', 'long long wts_bsz',
                  'int wts_ld']
     args += ['fpdtype_t* __restrict__ out', 'long long out_bsz', 'int out_ld',
-             'fpdtype_t t']
+             'const fpdtype_t* __restrict__ t_p']
 
     gsrc = r'''
         fpdtype_t grad_pri[NVARS][NDIMS];
@@ -336,6 +336,7 @@ fieldeval({', '.join(args)})
     if (blk*C_SUB + e >= neles)
         return;
 
+    const fpdtype_t t = *t_p;
     fpdtype_t acc[NEXPRS];
     UNROLL for (int j = 0; j < NEXPRS; j++)
         acc[j] = {init};

@@ -26,7 +26,7 @@ def rkvdh2_source(be, tplargs):
     if errest:
         args += ['fpdtype_t* __restrict__ rold',
                  'fpdtype_t* __restrict__ rerr']
-    args.append('fpdtype_t dt')
+    args.append('const fpdtype_t* __restrict__ dt_p')
 
     body = ['const fpdtype_t t1 = r1[i], t2 = r2[i];']
     if errest and stage == 0:
@@ -48,6 +48,8 @@ def rkvdh2_source(be, tplargs):
 extern "C" __global__ void __launch_bounds__(256)
 rkvdh2({', '.join(args)})
 {{
+    // run-time scalars live in device memory (backend.RuntimeScalars)
+    const fpdtype_t dt = *dt_p;
     const long long stride = (long long) gridDim.x*blockDim.x;
     for (long long i = (long long) blockIdx.x*blockDim.x + threadIdx.x;
          i < n; i += stride)

@@ -152,14 +152,18 @@ class Runtime:
 
     def nvrtc(self, src, name, opts):
         arr = (c_char_p*len(opts))(*[o.encode() for o in opts])
-        img, n, log = c_void_p(), c_size_t(), c_char_p()
+        img, n, log = c_void_p(), c_size_t(), c_void_p()
 
-        self.nvrtc_compile(src.encode(), name.encode(), arr, len(opts),
-                           byref(img), byref(n), byref(log))
         try:
+            self.nvrtc_compile(src.encode(), name.encode(), arr, len(opts),
+                               byref(img), byref(n),
+                               ct.cast(byref(log), POINTER(c_char_p)))
             return ct.string_at(img.value, n.value)
         finally:
-            self.buffer_free(img)
+            # both buffers are malloc'ed by the library
+            for buf in (img, log):
+                if buf.value:
+                    self.buffer_free(buf)
 
 
 class DryRuntime:

@@ -25,7 +25,10 @@ class DevAlloc:
         self.rt, self.nbytes = rt, nbytes
         self.ptr = rt.new_ptr(rt.malloc, nbytes)
         if not rt.dry:
+            # The fill runs on the legacy stream, which the backend's
+            # non-blocking streams do not synchronise with: wait for it
             rt.memset(self.ptr, 0, nbytes, None)
+            rt.stream_sync(None)
 
     def __int__(self):
         return self.ptr
@@ -238,6 +241,9 @@ class B200Graph(base.Graph):
     def run(self, stream=None):
         be, rt = self.backend, self.backend.rt
         stream = stream or be.stream
+
+        # Run-time scalars (t, dt) reach the kernels through device memory
+        be.rtscal.flush(stream)
 
         if not be.use_graphs:
             self._record(stream)

@@ -7,7 +7,7 @@ import pytest
 from pyfr_b200 import cases
 from pyfr_b200.host.system import get_system
 
-from util import assert_parity, oracle_rhs, rel_err
+from util import assert_parity, oracle_rhs, rel_err, rhs_magnitude
 
 pytestmark = pytest.mark.gpu
 
@@ -46,11 +46,11 @@ def b200_rhs(case, n, opts={}, **kw):
 def test_tgv_rhs_matches_oracle(built, kw, variant):
     n = (5, 4, 3)
     _, ref = oracle_rhs('tgv', n, warp=0.1, **kw)
-    _, ext = oracle_rhs('tgv', n, warp=0.1, extended=True, **kw)
+    esys, ext = oracle_rhs('tgv', n, warp=0.1, extended=True, **kw)
     sysm, out = b200_rhs('tgv', n, VARIANTS[variant], warp=0.1, **kw)
 
     assert out.shape == ref[0].shape
-    assert_parity(out, ref[0], ext[0], TOL64)
+    assert_parity(out, ref[0], ext[0], TOL64, mag=rhs_magnitude(esys[0])[0])
 
     kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
              for w, k in g.plan if w == 'kernel']
@@ -69,10 +69,10 @@ def test_tgv_rhs_matches_oracle(built, kw, variant):
                          ids=str)
 def test_vortex_rhs_matches_oracle(built, kw):
     _, ref = oracle_rhs('vortex', 12, **kw)
-    _, ext = oracle_rhs('vortex', 12, extended=True, **kw)
+    esys, ext = oracle_rhs('vortex', 12, extended=True, **kw)
     _, out = b200_rhs('vortex', 12, {}, **kw)
 
-    assert_parity(out, ref[0], ext[0], TOL64)
+    assert_parity(out, ref[0], ext[0], TOL64, mag=rhs_magnitude(esys[0])[0])
 
 
 def test_matrix_roundtrip_and_layout(built):
@@ -151,8 +151,9 @@ def test_tgv_rhs_affine_mesh(built, kw, opts):
         floor = rel_err(ref[0].astype(float), r64[0])
         assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
     else:
-        _, ext = oracle_rhs('tgv', n, extended=True, **kw)
-        assert_parity(out, ref[0], ext[0], TOL64)
+        esys, ext = oracle_rhs('tgv', n, extended=True, **kw)
+        assert_parity(out, ref[0], ext[0], TOL64,
+                      mag=rhs_magnitude(esys[0])[0])
 
 
 BC_CASES = [
@@ -192,10 +193,10 @@ def test_boundary_conditions_match_oracle(built, system, n, bcs, kw):
         return sysm, sysm.ele_scal_upts(1)[0]
 
     _, ref = run(OracleBackend)
-    _, ext = run(OracleBackend, extended=True)
+    esys, ext = run(OracleBackend, extended=True)
     sysm, out = run(B200Backend)
 
-    assert_parity(out, ref, ext, TOL64)
+    assert_parity(out, ref, ext, TOL64, mag=rhs_magnitude(esys)[0])
 
     kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
              for w, k in g.plan if w == 'kernel']
@@ -232,6 +233,71 @@ def test_full_size_conservation_and_symmetry(built):
     assert abs(mag[1]/mag[2] - 1) < 1e-10
     # no mass sources at t = 0 beyond discretisation error of div u
     assert np.abs(rhs[:, 0]).max() < 1e-4*np.abs(rhs[:, 1]).max()
+
+
+def test_full_size_rhs_matches_c_oracle(built):
+    """BASELINE.json config #2 at full size (64^3 hexes, p=4, fp64, 164 M
+    DoF): one RHS on the device against the C restatement of the path
+    (oracle/crhs, the build *without* -ffast-math) on identical inputs.
+
+    Two fp64 evaluations of this RHS cannot agree to 1e-12 of the field
+    maximum: at M = 0.1 the RHS (max 0.6) is the difference of pressure
+    terms of magnitude 70-180 times operator entries of magnitude 10, so
+    summation order alone moves a point by a few 1e-12 (the NumPy oracle
+    sits 6e-12 from its own extended-precision evaluation at this order;
+    measured below on a small mesh with the same element size ratio).  The
+    assertions are therefore: (i) the field-maximum error is within 4x the
+    oracle's own fp64 floor at this order, (ii) the relative L2 error of
+    every conserved variable is below 1e-11, (iii) the errors have no
+    structure: their mean over the mesh is zero to 1e-3 of their RMS (a
+    systematic defect -- a wrong coefficient, a dropped term -- shows up
+    as a bias long before it shows up in the maximum)."""
+    import gc
+    import os
+
+    from oracle.cbackend import make_cbackend
+    from pyfr_b200 import base
+    from pyfr_b200.backend import B200Backend
+    from util import PARITY_LOG
+
+    # the oracle's own floor at p = 4 (small mesh, same arithmetic)
+    _, r64 = oracle_rhs('tgv', (4, 4, 4), order=4)
+    _, rext = oracle_rhs('tgv', (4, 4, 4), order=4, extended=True)
+    floor = rel_err(r64[0], rext[0])
+
+    n = 64
+    cfg, box = cases.make('tgv', n, order=4)
+    mesh = box.local_mesh()
+    sysm = get_system(B200Backend(cfg), mesh, cfg, 2)
+    sysm.rhs(0.0, 0, 1)
+    sysm.backend.wait()
+    out = sysm.ele_scal_upts(1)[0]
+    del sysm
+    gc.collect()
+
+    CB = make_cbackend(base, fast=False, nthreads=os.cpu_count())
+    cfg, box = cases.make('tgv', n, order=4)
+    csys = get_system(CB(cfg), mesh, cfg, 2)
+    csys.rhs(0.0, 0, 1)
+    ref = csys.ele_scal_upts(1)[0]
+    del csys
+    gc.collect()
+
+    assert out.shape == ref.shape == (125, 5, n**3)
+
+    d = out - ref
+    err = float(np.abs(d).max()/np.abs(ref).max())
+    l2 = [float(np.linalg.norm(d[:, v])/np.linalg.norm(ref[:, v]))
+          for v in range(5)]
+    bias = [float(abs(d[:, v].mean())/max(d[:, v].std(), 1e-300))
+            for v in range(5)]
+    PARITY_LOG.append(dict(test='full-size 64^3 p=4 vs oracle/crhs',
+                           err=err, floor=float(floor), ratio=None,
+                           ratio_oracle=None, l2=l2, bias=bias))
+
+    assert err <= 4*floor, (err, floor)
+    assert max(l2) < 1e-11, l2
+    assert max(bias) < 1e-3, bias
 
 
 @pytest.mark.parametrize('kw', [dict(order=3), dict(order=2, rsolver='hllc'),
