@@ -114,6 +114,12 @@ class B200Backend(base.BaseBackend):
         if self.csubsz % self.soasz:
             raise ValueError('n-csub must be a multiple of n-soa')
 
+        # (options of the table-driven fused kernel select that kernel;
+        # looked up before the getters below record their defaults)
+        table_opts = any(cfg.hasopt(sect, o) for o in (
+            'gradflux-vec2', 'gradflux-planes', 'gradflux-ncol',
+            'gradflux-monojac', 'gradflux-maxctas'))
+
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
         # fp64 operators with at least this many distinct coefficients keep
         # them in __constant__ memory (0: always literals)
@@ -121,6 +127,9 @@ class B200Backend(base.BaseBackend):
         self.cflux_minblocks = cfg.getint(sect, 'cflux-minblocks', 5)
         self.gradflux_maxctas = cfg.getint(sect, 'gradflux-maxctas', 2)
         self.gradflux_threads = cfg.getint(sect, 'gradflux-threads', 0)
+        # sum-factorised fused kernel for tensor-product elements
+        self.gradflux_tensor = (cfg.getbool(sect, 'gradflux-tensor', True)
+                                and not table_opts)
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
@@ -139,6 +148,12 @@ class B200Backend(base.BaseBackend):
         self.inters_order = cfg.get(sect, 'inters-order', 'reference')
         if self.inters_order not in ('reference', 'address'):
             raise ValueError('inters-order must be reference or address')
+        # order in which the interior / boundary interface kernels visit
+        # their points: 'address' (sorted by left-hand address inside the
+        # provider; the views the host built are left untouched) or 'host'
+        self.kernel_order = cfg.get(sect, 'kernel-order', 'address')
+        if self.kernel_order not in ('address', 'host'):
+            raise ValueError('kernel-order must be address or host')
         self.affine_fastpath = cfg.getbool(sect, 'affine-fastpath', True)
         self.euler_fusion = cfg.getbool(sect, 'euler-fusion', True)
         # Runge-Kutta stage update in the epilogue of the last RHS kernel
@@ -150,6 +165,7 @@ class B200Backend(base.BaseBackend):
         self.compiler = KernelCompiler(rt)
         self.nlaunches = 0
         self.view_uses = []
+        self._ordered = {}
         self.dead_rows = cfg.getbool(sect, 'dead-rows', True)
 
         # Compute stream, communication stream and fork/join events

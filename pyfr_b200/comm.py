@@ -219,17 +219,26 @@ class LoopbackComm:
     def attach(self, rt):
         self.rt = self.world.rt = rt
 
+    def register(self, r):
+        """Called when a request is created (``XchgMatrix.sendreq`` /
+        ``recvreq``): mailboxes are allocated here, outside any stream
+        capture."""
+        w, rt = self.world, self.rt
+        m = r.mat
+        nb = _xchg_words(m)*m.itemsize
+
+        if r.kind == 'send':
+            key = (self.rank, r.peer, r.tag)
+            if key not in w.box:
+                w.box[key] = (rt.new_ptr(rt.malloc, max(nb, 1)), nb)
+        else:
+            w.recvs[r.peer, self.rank, r.tag] = (m.data, nb)
+
     def exchange(self, reqs, stream):
         w, rt = self.world, self.rt
 
         for r in reqs:
-            m = r.mat
-            nb = _xchg_words(m)*m.itemsize
-
             if r.kind == 'send':
-                key = (self.rank, r.peer, r.tag)
-                if key not in w.box:
-                    w.box[key] = (rt.new_ptr(rt.malloc, max(nb, 1)), nb)
-                rt.memcpy_async(w.box[key][0], m.data, nb, stream)
-            else:
-                w.recvs[r.peer, self.rank, r.tag] = (m.data, nb)
+                m = r.mat
+                dst, nb = w.box[self.rank, r.peer, r.tag]
+                rt.memcpy_async(dst, m.data, nb, stream)

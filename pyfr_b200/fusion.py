@@ -20,6 +20,7 @@ import numpy as np
 from pyfr_b200.kernels import fused as kfused
 from pyfr_b200.kernels import fused_euler as keuler
 from pyfr_b200.kernels import mul as kmul
+from pyfr_b200.kernels import tensor as ktensor
 
 
 def leaves(k):
@@ -207,10 +208,23 @@ def fuse_gradflux(be, kerns, subs):
 
         affine = ('linear' in ktype and be.affine_fastpath and
                   region_is_affine(ti['verts']))
-        src, name, meta = kfused.gradflux_source(
-            be, ops, ti['tplargs'], pts, LD,
-            rowcls=None if rneed is None else rneed[0], affine=affine
-        )
+        # Tensor-product elements take the sum-factorised kernel; anything
+        # else (or a structure the generator cannot verify) the
+        # table-driven one
+        src = None
+        if be.gradflux_tensor:
+            try:
+                src, name, meta = ktensor.gradflux_tp_source(
+                    be, ops, ti['tplargs'], pts, LD,
+                    rowcls=None if rneed is None else rneed[0], affine=affine
+                )
+            except kfused.NotFusable:
+                src = None
+        if src is None:
+            src, name, meta = kfused.gradflux_source(
+                be, ops, ti['tplargs'], pts, LD,
+                rowcls=None if rneed is None else rneed[0], affine=affine
+            )
         fn = be.pointwise._function(src, name)
         fn.set_smem(meta['smem'])
 
@@ -250,7 +264,7 @@ def fuse_gradflux(be, kerns, subs):
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
             traffic=words*isz, kind='gradflux',
             info=dict(replaces=kerns, dead_rows=rneed is not None,
-                      affine=affine)
+                      affine=affine, tensor=bool(meta.get('tensor')))
         ))
 
     return out

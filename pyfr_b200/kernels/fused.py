@@ -513,145 +513,23 @@ def find_planes(blocks, maxsize=36):
     return comps
 
 
-def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
-                    affine=False):
-    """Source of the fused kernel.
+def geometry_source(be, tplargs, pts, nthreads, affine=False):
+    """Source fragments that give the element kernels their metric terms
+    (shared by ``gradflux_source`` and ``tensor.gradflux_tp_source``).
 
-    ``rowcls``: optional class index (< 16) per flux-point row; the kernel
-    then takes a per-block bit mask ``fmask`` and neither computes nor
-    stores the gradients of rows whose class bit is clear (rows no
-    interface kernel ever reads, see fusion.row_need_classes).
-
-    ``affine``: every element of the region has a constant Jacobian (the
-    caller has checked the vertices); the metric terms are then formed once
-    per block by each thread for the one element it works on and kept in
-    registers, instead of being re-evaluated from shared memory at every
-    point in phases 2 and 4.
-
-    ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
-    ``M6`` (ndims*nupts x nfpts), ``M0`` (nfpts x nupts) and ``A5``
-    (nupts x ndims*nupts); ``tplargs``: the tflux template arguments
-    (``ktype`` is 'linear' or 'curved').  Raises ``NotFusable`` when the
-    operators lack the line structure the kernel relies on."""
-    nd, nv = tplargs['ndims'], tplargs['nvars']
-    A1, M6, M0, A5 = (np.asarray(ops[k], dtype=float)
-                      for k in ('A1', 'M6', 'M0', 'A5'))
-    nu, nf = M0.shape[1], M0.shape[0]
+    Three forms: affine linear elements (one Jacobian per element, formed
+    once per block and kept in registers), other linear elements (Jacobian
+    from per-element monomial coefficients) and curved elements (``smats``
+    and ``rcpdjac`` read from memory).  The fragments refer to the kernel's
+    ``tid``, ``blk``, ``it``, ``bars``, ``G``/``G_WORDS`` and, inside a
+    point loop, ``e`` (element of the block) and ``p`` (solution point);
+    ``geom`` leaves ``s[NDIMS][NDIMS]`` and ``rcpdjac_v`` in scope.
+    Returns a dict of strings plus ``geo_words`` (shared-memory words)."""
+    nd = tplargs['ndims']
+    nu = len(pts) if pts is not None else 0
     isz = np.dtype(be.fpdtype).itemsize
     csub = be.csubsz
-
-    if A1.shape != (nd*nu, nu) or M6.shape != (nd*nu, nf) or \
-       A5.shape != (nu, nd*nu) or LD != nv*csub:
-        raise NotFusable('unexpected operator shapes')
-
     linear = 'linear' in tplargs['ktype']
-    npoints = nu*csub
-
-    # Occupancy plan: as many CTAs per SM as the shared-memory footprint
-    # allows (two when a block is half an SM's worth), sharing a budget of
-    # 512 threads so that each keeps ~128 registers.  Co-resident CTAs run
-    # different phases at any one time, which overlaps the FP64-heavy
-    # pointwise phases of one with the shared-memory/HBM phases of another.
-    smem_fix = ((nu + nf + nd*nu)*LD + (2*tplargs.get('nverts', 0)*nd*csub
-                                        + 2*nu*nd + 16*nd*csub if linear else 0))*isz + 64
-    smem_sm = 228*1024
-    nctas = max(1, min(getattr(be, 'gradflux_maxctas', 2),
-                       smem_sm // (smem_fix + 1024)))
-    if nthreads is None:
-        nthreads = getattr(be, 'gradflux_threads', 0) or 512 // nctas
-    nrounds = -(-npoints // nthreads)
-
-    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
-            ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
-            ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds)]
-    defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
-                               True)
-
-    K = ConstPool(isz == 8)
-    em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 1))
-
-    vecs = set(getattr(be, 'gradflux_vec2', ()) or ())
-
-    # Phase 1: G = A1 @ U + M6 @ C
-    p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
-                 lambda off, v, at: f'{at("G", off)} = {v};',
-                 vec='p1' in vecs)
-
-    # Phase 3: vect_fpts[d] = M0 @ G[d]
-    M0d = np.zeros((nd*nf, nd*nu))
-    for d in range(nd):
-        M0d[d*nf:(d + 1)*nf, d*nu:(d + 1)*nu] = M0
-    if rowcls is not None and max(rowcls) < 16:
-        outtag = lambda r: int(rowcls[r % nf])
-        fm_arg = ',\n         const int* __restrict__ fmask'
-        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + blk);'
-    else:
-        outtag, fm_arg, fm_load = None, '', ''
-
-    p3 = em.emit('p3', build_classes([M0]), ['G'],
-                 lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};',
-                 outtag=outtag, rep=(nd, nf*LD*isz, nu*LD*isz),
-                 vec='p3' in vecs)
-
-    # Phase 5: in-place line transforms of the flux, direction by
-    # direction (block d of A5 acts on rows d*nu.. of G), then the sum
-    A5d = np.zeros((nd*nu, nd*nu))
-    for d in range(nd):
-        A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
-    p5lines = em.emit('p5', build_classes([A5d]), ['G'],
-                      lambda off, v, at: f'{at("G", off)} = {v};',
-                      inplace=True, vec='p5' in vecs)
-    if LD % 2 == 0:
-        gv = 'reinterpret_cast<const fpdtype2_t *>(G)'
-        sx = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].x' for d in range(nd))
-        sy = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].y' for d in range(nd))
-        p5 = f'''{p5lines}
-        __syncthreads();
-
-        for (int item = tid; item < NPTS*LD/2; item += NTHREADS)
-        {{
-            fpdtype2_t t;
-            t.x = {sx};
-            t.y = {sy};
-            reinterpret_cast<fpdtype2_t *>(fout + fob)[item] = t;
-        }}'''
-    else:
-        psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
-        p5 = f'''{p5lines}
-        __syncthreads();
-
-        for (int item = tid; item < NPTS*LD; item += NTHREADS)
-            fout[fob + item] = {psum};'''
-
-    # Preferred form: the last direction by in-place line transforms, the
-    # first two accumulated plane by plane in registers and streamed out
-    if getattr(be, 'gradflux_planes', True):
-        blocks = [A5[:, d*nu:(d + 1)*nu] for d in range(nd)]
-        try:
-            mark = len(em.tables)
-            if nd == 3:
-                A5l = np.zeros_like(A5d)
-                A5l[2*nu:, 2*nu:] = blocks[2]
-                # Rows of the other directions are left untouched
-                lines = build_classes([A5l], rows=range(2*nu, 3*nu))
-                p5a = em.emit('p5l', lines, ['G'],
-                              lambda off, v, at: f'{at("G", off)} = {v};',
-                              inplace=True, vec='p5' in vecs
-                              ) + '\n        __syncthreads();'
-                extra = lambda off, at: at('G', f'{off} + {2*nu*LD*isz}')
-            else:
-                p5a, extra = '', None
-
-            p5b = em.emit_planes(
-                'p5p', blocks[:2], [0, nu], extra,
-                lambda off, v, at: f'{at("(fout + fob)", off)} = {v};'
-            )
-            # Drop the tables of the line-only variant
-            em.tables = [t for t in em.tables[:mark]
-                         if not t[0].startswith('tab_p5_')] + em.tables[mark:]
-            p5 = f'{p5a}\n        {p5b}'
-        except NotFusable:
-            em.tables = em.tables[:mark]
 
     geo_elem = geo_post = ''
     if linear:
@@ -842,6 +720,160 @@ def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             const fpdtype_t rcpdjac_v = __ldg(rcpdjac + blk*rcpdjac_bsz
                                               + p*C_SUB + e);
 '''
+
+    return dict(gsrc=gsrc, gargs=gargs, geo_elem=geo_elem, geo_post=geo_post,
+                geom=geom, geo_words=geo_words, geo_decl=geo_decl,
+                geo_stage=geo_stage, geo_fetch=geo_fetch,
+                geo_bytes=geo_bytes, geo_blk=geo_blk)
+
+
+def gradflux_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
+                    affine=False):
+    """Source of the fused kernel.
+
+    ``rowcls``: optional class index (< 16) per flux-point row; the kernel
+    then takes a per-block bit mask ``fmask`` and neither computes nor
+    stores the gradients of rows whose class bit is clear (rows no
+    interface kernel ever reads, see fusion.row_need_classes).
+
+    ``affine``: every element of the region has a constant Jacobian (the
+    caller has checked the vertices); the metric terms are then formed once
+    per block by each thread for the one element it works on and kept in
+    registers, instead of being re-evaluated from shared memory at every
+    point in phases 2 and 4.
+
+    ``ops``: dict with the operator matrices ``A1`` (ndims*nupts x nupts),
+    ``M6`` (ndims*nupts x nfpts), ``M0`` (nfpts x nupts) and ``A5``
+    (nupts x ndims*nupts); ``tplargs``: the tflux template arguments
+    (``ktype`` is 'linear' or 'curved').  Raises ``NotFusable`` when the
+    operators lack the line structure the kernel relies on."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    A1, M6, M0, A5 = (np.asarray(ops[k], dtype=float)
+                      for k in ('A1', 'M6', 'M0', 'A5'))
+    nu, nf = M0.shape[1], M0.shape[0]
+    isz = np.dtype(be.fpdtype).itemsize
+    csub = be.csubsz
+
+    if A1.shape != (nd*nu, nu) or M6.shape != (nd*nu, nf) or \
+       A5.shape != (nu, nd*nu) or LD != nv*csub:
+        raise NotFusable('unexpected operator shapes')
+
+    linear = 'linear' in tplargs['ktype']
+    npoints = nu*csub
+
+    # Occupancy plan: as many CTAs per SM as the shared-memory footprint
+    # allows (two when a block is half an SM's worth), sharing a budget of
+    # 512 threads so that each keeps ~128 registers.  Co-resident CTAs run
+    # different phases at any one time, which overlaps the FP64-heavy
+    # pointwise phases of one with the shared-memory/HBM phases of another.
+    smem_fix = ((nu + nf + nd*nu)*LD + (2*tplargs.get('nverts', 0)*nd*csub
+                                        + 2*nu*nd + 16*nd*csub if linear else 0))*isz + 64
+    smem_sm = 228*1024
+    nctas = max(1, min(getattr(be, 'gradflux_maxctas', 2),
+                       smem_sm // (smem_fix + 1024)))
+    if nthreads is None:
+        nthreads = getattr(be, 'gradflux_threads', 0) or 512 // nctas
+    nrounds = -(-npoints // nthreads)
+
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
+            ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
+            ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds)]
+    defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
+                               True)
+
+    K = ConstPool(isz == 8)
+    em = PhaseEmitter(LD, isz, K, ncol=getattr(be, 'gradflux_ncol', 1))
+
+    vecs = set(getattr(be, 'gradflux_vec2', ()) or ())
+
+    # Phase 1: G = A1 @ U + M6 @ C
+    p1 = em.emit('p1', build_classes([A1, M6]), ['U', 'C'],
+                 lambda off, v, at: f'{at("G", off)} = {v};',
+                 vec='p1' in vecs)
+
+    # Phase 3: vect_fpts[d] = M0 @ G[d]
+    M0d = np.zeros((nd*nf, nd*nu))
+    for d in range(nd):
+        M0d[d*nf:(d + 1)*nf, d*nu:(d + 1)*nu] = M0
+    if rowcls is not None and max(rowcls) < 16:
+        outtag = lambda r: int(rowcls[r % nf])
+        fm_arg = ',\n         const int* __restrict__ fmask'
+        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + blk);'
+    else:
+        outtag, fm_arg, fm_load = None, '', ''
+
+    p3 = em.emit('p3', build_classes([M0]), ['G'],
+                 lambda off, v, at: f'{at("(vf + vfb)", off)} = {v};',
+                 outtag=outtag, rep=(nd, nf*LD*isz, nu*LD*isz),
+                 vec='p3' in vecs)
+
+    # Phase 5: in-place line transforms of the flux, direction by
+    # direction (block d of A5 acts on rows d*nu.. of G), then the sum
+    A5d = np.zeros((nd*nu, nd*nu))
+    for d in range(nd):
+        A5d[d*nu:(d + 1)*nu, d*nu:(d + 1)*nu] = A5[:, d*nu:(d + 1)*nu]
+    p5lines = em.emit('p5', build_classes([A5d]), ['G'],
+                      lambda off, v, at: f'{at("G", off)} = {v};',
+                      inplace=True, vec='p5' in vecs)
+    if LD % 2 == 0:
+        gv = 'reinterpret_cast<const fpdtype2_t *>(G)'
+        sx = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].x' for d in range(nd))
+        sy = ' + '.join(f'{gv}[{d*nu*LD // 2} + item].y' for d in range(nd))
+        p5 = f'''{p5lines}
+        __syncthreads();
+
+        for (int item = tid; item < NPTS*LD/2; item += NTHREADS)
+        {{
+            fpdtype2_t t;
+            t.x = {sx};
+            t.y = {sy};
+            reinterpret_cast<fpdtype2_t *>(fout + fob)[item] = t;
+        }}'''
+    else:
+        psum = ' + '.join(f'G[{d*nu*LD} + item]' for d in range(nd))
+        p5 = f'''{p5lines}
+        __syncthreads();
+
+        for (int item = tid; item < NPTS*LD; item += NTHREADS)
+            fout[fob + item] = {psum};'''
+
+    # Preferred form: the last direction by in-place line transforms, the
+    # first two accumulated plane by plane in registers and streamed out
+    if getattr(be, 'gradflux_planes', True):
+        blocks = [A5[:, d*nu:(d + 1)*nu] for d in range(nd)]
+        try:
+            mark = len(em.tables)
+            if nd == 3:
+                A5l = np.zeros_like(A5d)
+                A5l[2*nu:, 2*nu:] = blocks[2]
+                # Rows of the other directions are left untouched
+                lines = build_classes([A5l], rows=range(2*nu, 3*nu))
+                p5a = em.emit('p5l', lines, ['G'],
+                              lambda off, v, at: f'{at("G", off)} = {v};',
+                              inplace=True, vec='p5' in vecs
+                              ) + '\n        __syncthreads();'
+                extra = lambda off, at: at('G', f'{off} + {2*nu*LD*isz}')
+            else:
+                p5a, extra = '', None
+
+            p5b = em.emit_planes(
+                'p5p', blocks[:2], [0, nu], extra,
+                lambda off, v, at: f'{at("(fout + fob)", off)} = {v};'
+            )
+            # Drop the tables of the line-only variant
+            em.tables = [t for t in em.tables[:mark]
+                         if not t[0].startswith('tab_p5_')] + em.tables[mark:]
+            p5 = f'{p5a}\n        {p5b}'
+        except NotFusable:
+            em.tables = em.tables[:mark]
+
+    geo = geometry_source(be, tplargs, pts, nthreads, affine)
+    gsrc, gargs, geo_elem, geo_post = (geo[k] for k in (
+        'gsrc', 'gargs', 'geo_elem', 'geo_post'))
+    geom, geo_words, geo_decl, geo_stage = (geo[k] for k in (
+        'geom', 'geo_words', 'geo_decl', 'geo_stage'))
+    geo_fetch, geo_bytes, geo_blk = (geo[k] for k in (
+        'geo_fetch', 'geo_bytes', 'geo_blk'))
 
     # Index tables go to shared memory as far as the per-CTA share of the
     # SM's 228 KB (1 KB of it reserved per resident CTA) allows

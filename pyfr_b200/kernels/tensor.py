@@ -1,0 +1,582 @@
+"""Generator for the fused Navier-Stokes element kernel of tensor-product
+elements (hexahedra, quadrilaterals): ``gradflux`` in sum-factorised form.
+
+Same contract as ``fused.gradflux_source`` -- one launch for the chain
+``tgradpcoru_upts .. tdivtpcorf_upts`` of ``pyfr/solvers/baseadvecdiff/
+system.py:94-205`` -- but written for what the operators of a
+tensor-product element *are* (``pyfr/shapes.py:79-135`` builds them as
+Kronecker products of 1-D matrices): every operator acts along the lines
+of solution points of one direction, with one small 1-D matrix per
+direction.  The generator verifies that structure on the matrices it is
+given (it rebuilds them from the extracted 1-D factors and compares) and
+declines otherwise, so nothing here depends on how the host numbered the
+points.
+
+What this buys over the table-driven kernel (ncu, profiles/r01u: 516 M
+shared-memory wavefronts, 1.31 G warp instructions, 58 instructions per
+flux-point output):
+
+* a thread owns a fixed set of (line, column-group) work items for the
+  whole launch, so every row offset is formed once per kernel and lives in
+  a register: no index tables, no per-block address arithmetic;
+* a work item covers ``16/sizeof(fp)`` adjacent columns with one 16-byte
+  shared-memory access per row (``LDS.128``/``STS.128``/``STG.128``);
+* for affine elements (constant Jacobian) the gradient is never
+  transformed in shared memory: interpolation to the flux points and
+  multiplication by the constant metric commute, so the flux-point pass
+  combines the three interpolated reference gradients in registers and the
+  flux pass transforms its own point -- the separate ``gradcoru`` pass over
+  ``G`` disappears;
+* the last direction of the divergence is fused with the final sum, which
+  streams straight to HBM.
+
+Per element block (hex, p = 4, fp64) the kernel moves 3650 shared-memory
+words per column instead of ~6300.
+"""
+
+import numpy as np
+
+from pyfr_b200.kernels import physics as ph
+from pyfr_b200.kernels.fused import ConstPool, NotFusable, geometry_source
+from pyfr_b200.kernels.mul import _pipeline_src
+
+
+def _components(adj):
+    n = len(adj)
+    seen, comps = np.zeros(n, dtype=bool), []
+
+    for p0 in range(n):
+        if seen[p0]:
+            continue
+
+        comp, todo = [], [p0]
+        seen[p0] = True
+        while todo:
+            p = todo.pop()
+            comp.append(p)
+            for q in np.flatnonzero(adj[p]):
+                if not seen[q]:
+                    seen[q] = True
+                    todo.append(q)
+
+        comps.append(sorted(comp))
+
+    return comps
+
+
+def tp_structure(ops, nd, tol=1e-12):
+    """Line structure of the operators of a tensor-product element.
+
+    ``ops``: ``A1`` (``M4 - M6*M0``, ndims*nupts x nupts), ``M6``
+    (ndims*nupts x nfpts), ``M0`` (nfpts x nupts), ``A5`` (``M1 - M3*M2``,
+    nupts x ndims*nupts).  Returns a dict with, per direction ``d``: the
+    lines (first row and row stride of their ``n1`` solution points, the
+    flux-point rows at their two ends) and the 1-D matrices ``Dg`` (n1 x
+    n1), ``Lg`` (n1 x 2), ``lm``/``lp`` (n1) and ``Dt`` (n1 x n1) such that
+
+        (A1 u + M6 c)[d, line] = Dg[d] u[line] + Lg[d] (c[f-], c[f+])
+        (M0 g)[f-/+ of a line] = lm/lp[d] . g[line]
+        (A5 f)[line]          += Dt[d] f[d, line]
+
+    Raises ``NotFusable`` unless the four matrices are reproduced from
+    these factors to ``tol``."""
+    A1, M6, M0, A5 = (np.asarray(ops[k], dtype=float)
+                      for k in ('A1', 'M6', 'M0', 'A5'))
+    nf, nu = M0.shape
+    n1 = int(round(nu**(1.0/nd)))
+
+    if n1 < 2 or n1**nd != nu or nf != 2*nd*n1**(nd - 1):
+        raise NotFusable('not a tensor-product point set')
+
+    nl = nu // n1
+    scale = lambda A: tol*max(1.0, np.abs(A).max())
+    st = dict(n1=n1, nlines=nl, stride=[], base=[], fm=[], fp=[], Dg=[],
+              Lg=[], lm=[], lp=[], Dt=[])
+    used = np.zeros(nf, dtype=int)
+
+    for d in range(nd):
+        A1d, M6d = A1[d*nu:(d + 1)*nu], M6[d*nu:(d + 1)*nu]
+        A5d = A5[:, d*nu:(d + 1)*nu]
+
+        adj = (A1d != 0) | (A5d != 0)
+        lines = _components(adj | adj.T)
+        if len(lines) != nl or any(len(l) != n1 for l in lines):
+            raise NotFusable('operators do not act along lines')
+
+        strides = {l[i + 1] - l[i] for l in lines for i in range(n1 - 1)}
+        if len(strides) != 1:
+            raise NotFusable('lines are not arithmetic progressions')
+        lines.sort()
+
+        base, fms, fps = [], [], []
+        ref = None
+        for rows in lines:
+            fs = np.flatnonzero(np.any(M6d[rows] != 0, axis=0))
+            if len(fs) != 2:
+                raise NotFusable('a line is not corrected from two points')
+
+            # which end: the interpolated index coordinate of the point
+            pos = [float(M0[f, rows] @ np.arange(n1)) for f in fs]
+            fmn, fpl = (fs[0], fs[1]) if pos[0] < pos[1] else (fs[1], fs[0])
+            used[[fmn, fpl]] += 1
+
+            cur = (A1d[np.ix_(rows, rows)], M6d[np.ix_(rows, [fmn, fpl])],
+                   M0[fmn, rows], M0[fpl, rows], A5d[np.ix_(rows, rows)])
+            if ref is None:
+                ref = cur
+            elif any(np.abs(a - b).max() > scale(b)
+                     for a, b in zip(cur, ref)):
+                raise NotFusable('lines carry different 1-D operators')
+
+            base.append(rows[0])
+            fms.append(int(fmn))
+            fps.append(int(fpl))
+
+        st['stride'].append(int(strides.pop()))
+        st['base'].append(base)
+        st['fm'].append(fms)
+        st['fp'].append(fps)
+        for k, v in zip(('Dg', 'Lg', 'lm', 'lp', 'Dt'), ref):
+            st[k].append(np.array(v))
+
+    if np.any(used != 1):
+        raise NotFusable('flux points are not the ends of the lines')
+
+    # Rebuild the operators from the factors: everything outside the line
+    # structure must vanish
+    B1, B6, B0, B5 = (np.zeros_like(A) for A in (A1, M6, M0, A5))
+    for d in range(nd):
+        for b, fmn, fpl in zip(st['base'][d], st['fm'][d], st['fp'][d]):
+            rows = b + st['stride'][d]*np.arange(n1)
+            B1[np.ix_(d*nu + rows, rows)] = st['Dg'][d]
+            B6[np.ix_(d*nu + rows, [fmn, fpl])] = st['Lg'][d]
+            B0[fmn, rows], B0[fpl, rows] = st['lm'][d], st['lp'][d]
+            B5[np.ix_(rows, d*nu + rows)] = st['Dt'][d]
+
+    for A, B in ((A1, B1), (M6, B6), (M0, B0), (A5, B5)):
+        if np.abs(A - B).max() > scale(A):
+            raise NotFusable('operators have entries outside the lines')
+
+    return st
+
+
+def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
+                       affine=False):
+    """Source of the sum-factorised fused kernel; arguments and return
+    value as ``fused.gradflux_source``."""
+    nd, nv = tplargs['ndims'], tplargs['nvars']
+    st = tp_structure(ops, nd)
+    n1, nl = st['n1'], st['nlines']
+    nu, nf = n1**nd, 2*nd*nl
+    isz = np.dtype(be.fpdtype).itemsize
+    csub = be.csubsz
+
+    if LD != nv*csub:
+        raise NotFusable('unexpected leading dimension')
+
+    # Columns per work item: one 16-byte access
+    NC = 16 // isz
+    if LD % NC or be.soasz % NC:
+        raise NotFusable('columns do not group into 16-byte accesses')
+    NCG = LD // NC
+    comps = 'xyzw'[:NC]
+    vec = {(8, 2): 'double2', (4, 4): 'float4'}[isz, NC]
+
+    linear = 'linear' in tplargs['ktype']
+    affine = bool(affine and linear)
+
+    if nthreads is None:
+        nthreads = getattr(be, 'gradflux_threads', 0) or 512
+    if nthreads % csub or nthreads < NCG:
+        raise NotFusable('thread count does not fit the block layout')
+
+    NLG = nthreads // NCG                      # line groups per round
+    R = -(-nl // NLG)                          # rounds per direction
+    ROWB = LD*isz
+    npoints = nu*csub
+    nrounds = -(-npoints // nthreads)
+
+    defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
+            ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
+            ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds),
+            ('ROWB', ROWB), ('NCG', NCG), ('NLG', NLG), ('NLINES', nl)]
+    defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
+                               True)
+
+    K = ConstPool(isz == 8)
+
+    geo = geometry_source(be, tplargs, pts, nthreads, affine)
+    if affine and not geo['geo_post']:
+        affine = False
+    geom = geo['geom']
+
+    # -- per-thread line descriptors (formed once per launch) ---------------
+    # g_lines[d][line] = {first solution-point row, row of the '-' flux
+    # point, row of the '+' flux point} as byte offsets; the low four bits
+    # of the flux-point entries carry the row's need class
+    if rowcls is not None and max(rowcls) < 16:
+        cls = [int(c) for c in rowcls]
+        fm_arg = ',\n         const int* __restrict__ fmask'
+        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + blk);'
+    else:
+        cls, fm_arg, fm_load = None, '', ''
+
+    tab = []
+    for d in range(nd):
+        for b, fmn, fpl in zip(st['base'][d], st['fm'][d], st['fp'][d]):
+            tab += [b*ROWB, fmn*ROWB | (cls[fmn] if cls else 0),
+                    fpl*ROWB | (cls[fpl] if cls else 0), 0]
+    tabsrc = (f'static __device__ __align__(16) const int g_lines[{len(tab)}]'
+              f' = {{{", ".join(map(str, tab))}}};')
+
+    desc = []
+    for d in range(nd):
+        for r in range(R):
+            desc.append(f'''
+    int lb{d}_{r} = 0, lm{d}_{r} = 0, lp{d}_{r} = 0;
+    const bool on{d}_{r} = lg + {r*NLG} < NLINES && lg < NLG;
+    if (on{d}_{r})
+    {{
+        const int4 q = *reinterpret_cast<const int4 *>(
+            g_lines + {4*d*nl} + 4*(lg + {r*NLG}));
+        lb{d}_{r} = q.x + cb; lm{d}_{r} = q.y; lp{d}_{r} = q.z;
+    }}''')
+    desc = ''.join(desc)
+
+    ld = lambda arr, off: (f'*reinterpret_cast<const fpvec_t *>({arr} + '
+                           f'{off})')
+    stv = lambda arr, off: f'*reinterpret_cast<fpvec_t *>({arr} + {off})'
+
+    def lincomb(dst, terms, indent):
+        """``dst.k = sum coef*src.k`` as FMA chains over the lanes."""
+        out = []
+        for k in comps:
+            e = None
+            for a, x in terms:
+                if a == 0:
+                    continue
+                e = (f'{K(a)}*{x}.{k}' if e is None
+                     else f'fma({K(a)}, {x}.{k}, {e})')
+            out.append(f'{indent}{dst}.{k} = {e or "FP(0.0)"};')
+        return out
+
+    # -- phase 1: G[d] = Dg u + Lg (c-, c+) along the lines of d -------------
+    p1 = []
+    for d in range(nd):
+        sb = st['stride'][d]*ROWB
+        for r in range(R):
+            L = [f'if (on{d}_{r})', '{']
+            for i in range(n1):
+                L.append(f'    const fpvec_t x{i} = '
+                         f'{ld("Ub", f"lb{d}_{r} + {i*sb}")};')
+            L.append(f'    const fpvec_t cm = '
+                     f'{ld("Cb", f"(lm{d}_{r} & ~15) + cb")};')
+            L.append(f'    const fpvec_t cp = '
+                     f'{ld("Cb", f"(lp{d}_{r} & ~15) + cb")};')
+            L.append('    fpvec_t o;')
+            for i in range(n1):
+                terms = [(st['Dg'][d][i, j], f'x{j}') for j in range(n1)]
+                terms += [(st['Lg'][d][i, 0], 'cm'), (st['Lg'][d][i, 1], 'cp')]
+                L += lincomb('o', terms, '    ')
+                L.append(f'    {stv("Gb", f"{d*nu*ROWB + i*sb} + lb{d}_{r}")}'
+                         ' = o;')
+            L.append('}')
+            p1.append('\n        '.join(L))
+    p1 = '\n        '.join(p1)
+
+    # -- phase 3: gradients at the flux points -> HBM -------------------------
+    # Lines of direction a end on the two faces normal to a; all ndims
+    # gradient components are interpolated along the line.  Affine
+    # elements: G still holds the reference gradient and the (constant)
+    # metric is applied to the interpolated values.
+    p3 = []
+    for a in range(nd):
+        sb = st['stride'][a]*ROWB
+        for r in range(R):
+            L = [f'if (on{a}_{r})', '{']
+            if cls:
+                L += [f'    const bool wm = fm & (1u << (lm{a}_{r} & 15)), '
+                      f'wp = fm & (1u << (lp{a}_{r} & 15));']
+            else:
+                L += ['    const bool wm = true, wp = true;']
+            L += ['    if (wm | wp)', '    {']
+            for d in range(nd):
+                L.append(f'        fpvec_t tm{d}, tp{d};')
+                L.append('        {')
+                for i in range(n1):
+                    L.append(f'            const fpvec_t g{i} = '
+                             f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                L += lincomb(f'tm{d}', [(st['lm'][a][i], f'g{i}')
+                                        for i in range(n1)], '            ')
+                L += lincomb(f'tp{d}', [(st['lp'][a][i], f'g{i}')
+                                        for i in range(n1)], '            ')
+                L.append('        }')
+
+            for w, t, lf in (('wm', 'tm', f'lm{a}_{r}'),
+                             ('wp', 'tp', f'lp{a}_{r}')):
+                L += [f'        if ({w})', '        {',
+                      f'            char *vo = vfp + ({lf} & ~15) + cb;']
+                for dp in range(nd):
+                    if affine:
+                        L.append('            { fpvec_t o;')
+                        for ki, k in enumerate(comps):
+                            e = None
+                            for d in range(nd):
+                                e = (f'sP[{ki}][{d}][{dp}]*{t}{d}.{k}'
+                                     if e is None else
+                                     f'fma(sP[{ki}][{d}][{dp}], {t}{d}.{k}, '
+                                     f'{e})')
+                            L.append(f'            o.{k} = rjP[{ki}]*({e});')
+                        L.append(f'            {stv("vo", dp*nf*ROWB)} = o; '
+                                 '}')
+                    else:
+                        L.append(f'            {stv("vo", dp*nf*ROWB)} = '
+                                 f'{t}{dp};')
+                L.append('        }')
+            L += ['    }', '}']
+            p3.append('\n        '.join(L))
+    p3 = '\n        '.join(p3)
+
+    # -- phase 5: divergence --------------------------------------------------
+    # in-place line transforms for all but the last direction ...
+    p5a = []
+    for a in range(nd - 1):
+        sb = st['stride'][a]*ROWB
+        for r in range(R):
+            L = [f'if (on{a}_{r})', '{']
+            for i in range(n1):
+                L.append(f'    const fpvec_t x{i} = '
+                         f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")};')
+            L.append('    fpvec_t o;')
+            for i in range(n1):
+                L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
+                                   for j in range(n1)], '    ')
+                L.append(f'    {stv("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")}'
+                         ' = o;')
+            L.append('}')
+            p5a.append('\n        '.join(L))
+    p5a = '\n        '.join(p5a)
+
+    # ... the last one in registers, summed with the others on the way out
+    a = nd - 1
+    sb = st['stride'][a]*ROWB
+    p5b = []
+    for r in range(R):
+        L = [f'if (on{a}_{r})', '{']
+        for i in range(n1):
+            L.append(f'    const fpvec_t x{i} = '
+                     f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")};')
+        L.append('    fpvec_t o;')
+        for i in range(n1):
+            L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
+                               for j in range(n1)], '    ')
+            for d in range(nd - 1):
+                L.append(f'    {{ const fpvec_t y = '
+                         f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                L.append('      ' + ' '.join(f'o.{k} += y.{k};'
+                                             for k in comps) + ' }')
+            L.append(f'    {stv("fop", f"{i*sb} + lb{a}_{r}")} = o;')
+        L.append('}')
+        p5b.append('\n        '.join(L))
+    p5b = '\n        '.join(p5b)
+
+    # -- metric terms of the work items' columns (affine) ---------------------
+    if affine:
+        metric_p3 = f'''
+        // Constant metric of the {NC} elements this thread's columns belong
+        // to (phase 3) -- QS was filled by the first C_SUB threads
+        fpdtype_t sP[{NC}][NDIMS][NDIMS], rjP[{NC}];
+        UNROLL for (int k = 0; k < {NC}; k++)
+        {{
+            const fpdtype_t *q = QS + (e0 + k)*(NDIMS*NDIMS + 1);
+            UNROLL for (int i = 0; i < NDIMS; i++)
+                UNROLL for (int j = 0; j < NDIMS; j++)
+                    sP[k][i][j] = q[i*NDIMS + j];
+            rjP[k] = q[NDIMS*NDIMS];
+        }}
+'''
+        p2 = ''
+        p4_xform = 'transform_grad(g, s, rcpdjac_v);'
+    else:
+        metric_p3 = ''
+        p2 = f'''
+        // ---- phase 2: physical gradient (in place) ---------------------
+        for (int item = tid; item < NPTS*C_SUB; item += NTHREADS)
+        {{
+            const int e = item % C_SUB, p = item / C_SUB;
+            if (blk*C_SUB + e >= neles)
+                continue;
+{geom}
+            fpdtype_t g[NDIMS][NVARS];
+            UNROLL for (int d = 0; d < NDIMS; d++)
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    g[d][v] = G[(d*NPTS + p)*LD + COFF(e, v, NVARS)];
+
+            transform_grad(g, s, rcpdjac_v);
+
+            UNROLL for (int d = 0; d < NDIMS; d++)
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = g[d][v];
+        }}
+        __syncthreads();
+'''
+        p4_xform = '(void) rcpdjac_v;'
+
+    geo_words = geo['geo_words']
+    smem = ((nu + nf + nd*nu)*LD + geo_words)*isz + 64
+    if smem > 227*1024:
+        raise NotFusable(f'needs {smem} bytes of shared memory')
+
+    src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
+                          be.soasz, be.csubsz, defs)}
+typedef {vec} fpvec_t;
+{_pipeline_src}
+{ph.flux_src}
+{ph.visc_src}
+{ph.geom_src}
+{geo['gsrc']}
+{tabsrc}
+{K.decl()}
+
+#define U_WORDS (NPTS*LD)
+#define C_WORDS (NFPTS*LD)
+#define G_WORDS (NDIMS*NPTS*LD)
+#define V_WORDS (NVERTS*NDIMS*C_SUB)
+
+// tensor-product element, {n1} points per line, {nl} lines per direction;
+// {NC} columns per work item, {NCG} column groups x {NLG} line groups,
+// {R} round(s) per direction{', constant Jacobian' if affine else ''}
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+gradflux(int nblocks, int neles,
+         const fpdtype_t* __restrict__ u, long long u_bsz,
+         const fpdtype_t* ucomm, long long ucomm_bsz,
+         fpdtype_t* vf, long long vf_bsz,
+         fpdtype_t* __restrict__ fout, long long fout_bsz,
+         {geo['gargs']}{fm_arg})
+{{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
+    fpdtype_t *C = U + U_WORDS;
+    fpdtype_t *G = C + C_WORDS;
+    {geo['geo_decl']}
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        G + G_WORDS + {geo_words});
+
+    char *Ub = reinterpret_cast<char *>(U);
+    char *Cb = reinterpret_cast<char *>(C);
+    char *Gb = reinterpret_cast<char *>(G);
+
+    const int tid = threadIdx.x;
+
+    // This thread's work items: column group cg of the lines lg, lg + NLG,
+    // ... of every direction
+    const int cg = tid % NCG, lg = tid / NCG;
+    const int cb = cg*{NC*isz};
+    const int e0 = ((cg*{NC})/(K_SOA*NVARS))*K_SOA + (cg*{NC}) % K_SOA;
+    (void) e0;
+{desc}
+
+    // Stage the reference point set once per CTA
+    {geo['geo_stage']}
+
+    if (tid == 0)
+    {{
+        mbar_init(&bars[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }}
+    __syncthreads();
+
+    auto fetch = [&](long long b, unsigned n)
+    {{
+        mbar_expect_tx(&bars[0], (U_WORDS + C_WORDS)*sizeof(fpdtype_t)
+                                 {geo['geo_bytes']});
+        tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
+        tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
+                    &bars[0]);
+        {geo['geo_fetch']}
+    }};
+
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < nblocks)
+        fetch(blk, 0);
+
+    for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
+    {{
+        const long long nxt = blk + gridDim.x;
+        char *vfp = reinterpret_cast<char *>(vf + blk*vf_bsz);
+        char *fop = reinterpret_cast<char *>(fout + blk*fout_bsz);
+
+        mbar_wait(&bars[0], it & 1);
+        {geo['geo_blk']}
+        {fm_load}
+{geo['geo_elem']}
+
+        // ---- phase 1: corrected transformed gradient ------------------
+        {p1}
+
+        // Keep the solution at this thread's flux-evaluation points
+        fpdtype_t ureg[NROUNDS][NVARS];
+        UNROLL for (int r = 0; r < NROUNDS; r++)
+        {{
+            const int item = tid + r*NTHREADS;
+            if (item < NPTS*C_SUB)
+            {{
+                const int e = item % C_SUB, p = item / C_SUB;
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    ureg[r][v] = U[p*LD + COFF(e, v, NVARS)];
+            }}
+        }}
+        __syncthreads();
+
+        // u and ucomm are consumed: fetch the next block's behind the
+        // remaining phases
+        if (tid == 0 && nxt < nblocks)
+            fetch(nxt, it + 1);
+{p2}
+        // ---- phase 3: gradients at the flux points -> HBM ---------------
+        {{
+{metric_p3}
+        {p3}
+        }}
+        __syncthreads();
+
+        // ---- phase 4: transformed flux (in place over the gradient) -----
+{geo['geo_post']}
+        UNROLL for (int r = 0; r < NROUNDS; r++)
+        {{
+            const int item = tid + r*NTHREADS;
+            const int e = item % C_SUB, p = item / C_SUB;
+            if (item < NPTS*C_SUB && blk*C_SUB + e < neles)
+            {{
+{geom}
+                fpdtype_t g[NDIMS][NVARS];
+                UNROLL for (int d = 0; d < NDIMS; d++)
+                    UNROLL for (int v = 0; v < NVARS; v++)
+                        g[d][v] = G[(d*NPTS + p)*LD + COFF(e, v, NVARS)];
+
+                {p4_xform}
+
+                fpdtype_t ft[NDIMS][NVARS], fo[NDIMS][NVARS], pr, vel[NDIMS];
+                inviscid_flux(ureg[r], ft, pr, vel);
+                viscous_flux_add(ureg[r], g, ft);
+                transform_flux(ft, s, fo);
+
+                UNROLL for (int d = 0; d < NDIMS; d++)
+                    UNROLL for (int v = 0; v < NVARS; v++)
+                        G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = fo[d][v];
+            }}
+        }}
+        __syncthreads();
+
+        // ---- phase 5: divergence along the lines, summed -> HBM ----------
+        {p5a}
+        {'__syncthreads();' if nd > 1 else ''}
+        {p5b}
+        __syncthreads();
+    }}
+}}
+'''
+    meta = dict(nthreads=nthreads, smem=smem, nctas=1,
+                words_per_block=(2*nu + nf + nd*nf)*LD, tensor=True)
+
+    return src, 'gradflux', meta

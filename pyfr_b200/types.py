@@ -121,10 +121,18 @@ class XchgRequest:
 
 class B200XchgMatrix(B200Matrix, base.XchgMatrix):
     def recvreq(self, comm, pid, tag):
-        return XchgRequest('recv', self, pid, tag)
+        return self._req('recv', comm, pid, tag)
 
     def sendreq(self, comm, pid, tag):
-        return XchgRequest('send', self, pid, tag)
+        return self._req('send', comm, pid, tag)
+
+    def _req(self, kind, comm, pid, tag):
+        req = XchgRequest(kind, self, pid, tag)
+        # A communicator may want to know its requests before the first
+        # exchange runs (allocations are not allowed during stream capture)
+        if hasattr(comm, 'register'):
+            comm.register(req)
+        return req
 
 
 class B200Graph(base.Graph):

@@ -32,6 +32,7 @@ struct emu_dim3 { unsigned x, y, z; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 
 static thread_local emu_dim3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;

@@ -16,7 +16,8 @@ import pytest
 from pyfr_b200 import cases
 from pyfr_b200.host.system import get_system
 
-from util import OracleBackend, assert_parity, oracle_rhs, rel_err
+from util import (OracleBackend, assert_parity, oracle_rhs, rel_err,
+                  rhs_magnitude)
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                 'cudaemu'))
@@ -88,6 +89,18 @@ def _kinds(sysm):
                                           'inters-order': 'address'},
      'intconu'),
     (dict(order=4), {'inters-order': 'address'}, 'gradflux'),
+    # the table-driven fused kernel (what non-tensor-product elements and
+    # hexes with gradflux-tensor = 0 take)
+    (dict(order=2, warp=0.1), {'gradflux-tensor': 0}, 'gradflux'),
+    (dict(order=2), {'gradflux-tensor': 0}, 'gradflux'),
+    (dict(order=3, rsolver='hllc', beta=0.0, curved=0.5, warp=0.1),
+     {'gradflux-tensor': 0}, 'gradflux'),
+    (dict(order=4), {'gradflux-tensor': 0}, 'gradflux'),
+    # sum-factorised kernel: curved region + linear region, no dead rows
+    (dict(order=3, rsolver='hllc', beta=0.0, curved=0.5, warp=0.1), {},
+     'gradflux'),
+    (dict(order=2, warp=0.1), {'dead-rows': 0}, 'gradflux'),
+    (dict(order=1), {}, 'gradflux'),
     # the benchmark's kernel variants (p = 4, 512 threads, 220 KB smem)
     (dict(order=4), {}, 'gradflux'),
     (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),
@@ -101,10 +114,19 @@ def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
     out = sysm.ele_scal_upts(1)[0]
 
     _, ref = oracle_rhs('tgv', n, **kw)
-    _, ext = oracle_rhs('tgv', n, extended=True, **kw)
+    esys, ext = oracle_rhs('tgv', n, extended=True, **kw)
 
     assert expect in _kinds(sysm)
-    assert_parity(out, ref[0], ext[0], 1e-12)
+    assert_parity(out, ref[0], ext[0], 1e-12, mag=rhs_magnitude(esys[0])[0])
+
+    # which fused element kernel ran: the sum-factorised one for hexes
+    # unless switched off or the table-driven kernel's own options are set
+    for g in sysm.rhs_graphs(0, 1):
+        for w, k in g.plan:
+            if w == 'kernel' and getattr(k, 'kind', None) == 'gradflux':
+                old = any(o.startswith('gradflux-') and
+                          o != 'gradflux-threads' for o in opts)
+                assert k.info['tensor'] == (not old), opts
 
 
 def _vec2_cases():
