@@ -40,8 +40,19 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=64, help='hexes per direction '
-                    'per GPU')
+    ap.add_argument('--n', type=int, default=64, help='hexes per direction: '
+                    'per GPU (weak scaling) or of the whole mesh (strong)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: N bricks of n^3 (the default, what the '
+                    'driver times); strong: one n^3 mesh split over N ranks '
+                    '(BASELINE configs[2]: --scaling strong --n 128)')
+    ap.add_argument('--partition', default='brick',
+                    choices=['brick', 'reference'],
+                    help='brick: equal bricks; reference: the partition the '
+                    'reference partitioner (pyfr/partitioners/baseline.py) '
+                    'made for this mesh, from tests/golden/parts_hex<n>.npz')
+    ap.add_argument('--no-parity', action='store_true', help='skip the '
+                    'small partitioned-oracle check that precedes the timing')
     ap.add_argument('--case', default='tgv',
                     choices=['tgv', 'hex+pri', 'hex+pri+pyr+tet'],
                     help='tgv: the headline workload; the others time '
@@ -143,11 +154,18 @@ class ClockSampler:
                 'power_w_max': max(pw)}
 
 
-def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1):
+def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1, n=None):
     """The C/OpenMP restatement of the reference's CPU design
     (oracle/crhs, driven through the oracle backend API) on all host
-    cores, on a bounded sample of the workload: the same TGV case on a
-    smaller mesh.  Rebuilt on the machine it runs on (-march=native)."""
+    cores: the same TGV case on an ``n``^3 mesh (default: the bounded
+    sample ``--cpu-n``).  Rebuilt on the machine it runs on
+    (-march=native); threads pinned (OMP_PROC_BIND=close) and the
+    *median* step time reported, because the mean of a few steps on a
+    shared host moved by 1.6x between runs."""
+    # (libgomp reads these when it is loaded, i.e. with the library below)
+    os.environ.setdefault('OMP_PROC_BIND', 'close')
+    os.environ.setdefault('OMP_PLACES', 'cores')
+
     from oracle import cbackend
     from pyfr_b200 import base, cases
     from pyfr_b200.host.system import get_system
@@ -155,7 +173,7 @@ def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1):
     subprocess.run(['make', '-s', '-B', '-C', os.path.join(ROOT, 'oracle')],
                    check=True, capture_output=True)
 
-    n = args.cpu_n
+    n = n or args.cpu_n
     cfg, box = cases.make('tgv', n, order=args.order, rsolver=args.rsolver)
     be = cbackend.make_cbackend(base, fast=True,
                                 nthreads=os.cpu_count())(cfg)
@@ -165,23 +183,26 @@ def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1):
     for _ in range(max(warmup, 1)):
         sysm.rhs(0.0, 0, 1)
 
-    reps, t0 = 0, time.perf_counter()
-    while (reps < steps if steps else
-           (reps < 3 or time.perf_counter() - t0 < min_seconds)):
+    times, t0 = [], time.perf_counter()
+    while (len(times) < steps if steps else
+           (len(times) < 3 or time.perf_counter() - t0 < min_seconds)):
+        t1 = time.perf_counter()
         sysm.rhs(0.0, 0, 1)
-        reps += 1
-    dt = (time.perf_counter() - t0)/reps
+        times.append(time.perf_counter() - t1)
+    dt = statistics.median(times)
 
     return {
         'value': ndof/dt/1e9, 'unit': 'GDoF/s', 'cores': be.nthreads,
-        'kind': 'port',
-        'sample': f'{reps} RHS evaluations of TGV NS hex p={args.order} '
-                  f'fp64 on {n}^3 elements ({ndof} DoF); C11/OpenMP '
-                  'restatement of the reference OpenMP backend design '
-                  '(blocked AoSoA, block-group fusion with thread-local '
-                  'scratch, CSR operator kernels instead of libxsmm; gcc '
-                  '-O3 -march=native -ffast-math), all host threads; the '
-                  'reference backend itself cannot run offline'
+        'kind': 'port', 'mesh': f'{n}^3',
+        'step_s': {'median': dt, 'min': min(times), 'max': max(times)},
+        'sample': f'median of {len(times)} RHS evaluations of TGV NS hex '
+                  f'p={args.order} fp64 on {n}^3 elements ({ndof} DoF); '
+                  'C11/OpenMP restatement of the reference OpenMP backend '
+                  'design (blocked AoSoA, block-group fusion with '
+                  'thread-local scratch, CSR operator kernels instead of '
+                  'libxsmm; gcc -O3 -march=native -ffast-math), all host '
+                  'threads of ONE process, pinned; the reference backend '
+                  'itself cannot run offline'
     }, dt
 
 
@@ -193,27 +214,50 @@ def reference_arm(args):
     if rank != 0:
         return
 
-    # Bound the run: at most ~60 s of timed work whatever --steps says
-    probe, dt = cpu_baseline(args, steps=2, warmup=max(args.warmup, 1))
-    steps = max(1, min(args.steps, int(60.0/dt)))
-    info, dt = cpu_baseline(args, steps=steps, warmup=1)
+    # The mesh of the b200 arm itself when one evaluation stays within a
+    # second or so of CPU time (64^3: ~0.5 s), else the bounded sample;
+    # at most ~60 s of timed work whatever --steps says
+    n = args.n if args.n <= 64 else args.cpu_n
+    steps = max(3, min(args.steps, 60))
+    info, dt = cpu_baseline(args, steps=steps, warmup=max(args.warmup, 1),
+                            n=n)
 
+    cfgd = workload_config(args, n=n, reference=True)
     v = info['value']
     line = {
         'impl': 'reference', 'metric': 'GDoF-RHS/s', 'value': v,
         'unit': 'GDoF/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': args.warmup, 'ms_per_step': dt*1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': args.scaling,
+        'vs_baseline': None,
         'dtype': 'f64' if args.precision == 'double' else 'f32',
         'data': 'synthetic',
-        'config': workload_config(args), 'cpu_baseline': info,
+        'config': cfgd, 'cpu_baseline': info,
         'e2e': {'value': v, 'unit': 'GDoF/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0}
     }
     print(json.dumps(line))
 
 
-def workload_config(args):
+def workload_config(args, n=None, reference=False):
+    n = n or args.n
+    if reference:
+        # One host process whatever --gpus says: the CPU port has no
+        # multi-process driver, so at N > 1 this is a single-host figure
+        per = ' per GPU' if n == args.n and args.scaling == 'weak' else ''
+        return {
+            'workload': f'TGV compressible Navier-Stokes, {n}^3 periodic '
+                        f'hexes{per}, p={args.order}, fp64, {args.rsolver}, '
+                        'LDG beta=0.5 tau=0.1, one RHS evaluation per step',
+            'mesh': f'{n}^3 on one host process (the b200 arm: '
+                    f'{args.n}^3 per GPU)' if args.scaling == 'weak' else
+                    f'{n}^3 on one host process',
+            'l2': 'n/a (CPU)',
+            'parallelism': 'OpenMP threads of one process; not partitioned'
+                           + (f' (single-host figure beside {args.gpus} '
+                              'GPU ranks)' if args.gpus > 1 else '')
+        }
+
     if args.case != 'tgv':
         return {
             'workload': f'compressible Navier-Stokes, {args.n}^3 periodic '
@@ -226,18 +270,85 @@ def workload_config(args):
                            'send/recv halo exchange'
         }
 
+    strong = args.scaling == 'strong'
+    part = ('brick partition' if args.partition == 'brick' else
+            "partitioned by the reference's BaselinePartitioner "
+            '(tests/golden/parts_hex*.npz)')
+    nloc = args.n**3//(args.gpus if strong else 1)
     return {
         'workload': f'TGV compressible Navier-Stokes, {args.n}^3 periodic '
-                    f'hexes per GPU, p={args.order}, '
+                    f'hexes {"in total" if strong else "per GPU"}, '
+                    f'p={args.order}, '
                     f'{"fp64" if args.precision == "double" else "fp32"}, '
                     f'{args.rsolver}, LDG beta=0.5 tau=0.1, one RHS '
                     'evaluation per step',
-        'mesh': f'{args.n}^3 per GPU, brick partition',
+        'mesh': (f'{args.n}^3 over {args.gpus} GPU(s), {part}' if strong
+                 else f'{args.n}^3 per GPU, {part}'),
         'l2': 'inputs larger than L2 (solution bank alone is '
-              f'{args.n**3*(args.order + 1)**3*5*8/1e6:.0f} MB per GPU)',
+              f'{nloc*(args.order + 1)**3*5*8/1e6:.0f} MB per GPU)',
         'parallelism': f'domain decomposition, {args.gpus} rank(s), NCCL '
                        'send/recv halo exchange'
     }
+
+
+def reference_partition(nglob, nparts):
+    """Element -> rank map made by the reference's own partitioner for this
+    box (``pyfr/partitioners/baseline.py``, run offline by
+    ``tests/golden/make_golden.py --partitions``; the dual graph of a
+    periodic box only depends on its size)."""
+    if len(set(nglob)) != 1:
+        raise SystemExit('--partition reference needs a cubic mesh')
+
+    path = os.path.join(ROOT, 'tests', 'golden', f'parts_hex{nglob[0]}.npz')
+    try:
+        with np.load(path) as f:
+            return f[f'vparts{nparts}'].astype(np.int32)
+    except (OSError, KeyError):
+        raise SystemExit(f'No reference partition of a {nglob[0]}^3 box into '
+                         f'{nparts} parts ({path}); use --partition brick')
+
+
+def parity_check(args, be, comm, rank, world):
+    """The RHS of a small partitioned TGV mesh (3^3 hexes per rank, same
+    order, Riemann solver and exchange path as the timed run) on this
+    rank's device against the *partitioned* oracle, before timing.  The
+    oracle is used as the checker only.  Returns ``{err, floor, nranks}``
+    (maximum over ranks, relative to the field maximum; ``floor`` is the
+    oracle's own fp64 distance from its extended-precision evaluation)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from pyfr_b200 import cases
+    from pyfr_b200.host.system import get_system
+    from util import oracle_rhs, rel_err
+
+    parts = bricks(world)
+    n = tuple(3*p for p in parts)
+    kw = dict(order=args.order, rsolver=args.rsolver, warp=0.1)
+
+    cfg, box = cases.make('tgv', n, precision=args.precision, **kw)
+    vparts = box.brick_partition(parts) if world > 1 else None
+    sysm = get_system(be, box.local_mesh(vparts, rank), cfg, 2, comm=comm)
+    for _ in range(2):
+        sysm.rhs(0.0, 0, 1)
+    be.wait()
+    out = sysm.ele_scal_upts(1)[0].astype(float)
+
+    _, ref = oracle_rhs('tgv', n, vparts=vparts, nparts=world, **kw)
+    _, ext = oracle_rhs('tgv', n, vparts=vparts, nparts=world, extended=True,
+                        **kw)
+    err, floor = rel_err(out, ext[rank]), rel_err(ref[rank], ext[rank])
+
+    if world > 1:
+        red = be.matrix((1, 4), tags={'noblock'})
+        code = 1 if be.fpdtype == np.float64 else 0
+        red.set(np.array([[err, floor, 0.0, 0.0]]))
+        comm.allreduce(red.data, 4, code, 2, be.stream)
+        be.wait()
+        err, floor = (float(x) for x in red.get()[0, :2])
+
+    del sysm
+    return {'err': float(err), 'floor': float(floor), 'nranks': world,
+            'mesh': 'x'.join(map(str, n)) + f' hexes, p={args.order}, '
+            f'{"brick partitions, NCCL halo exchange" if world > 1 else "one partition"}'}
 
 
 # -- main benchmark -----------------------------------------------------------
@@ -261,17 +372,19 @@ def main():
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}; launch '
                          'with torch.distributed.run for N > 1')
 
-    # Mesh: `world` bricks of n^3 hexes
+    # Mesh: `world` bricks of n^3 hexes (weak) or one n^3 mesh (strong)
     parts = bricks(world)
+    strong = args.scaling == 'strong'
+    nglob = ((args.n,)*3 if strong else tuple(args.n*p for p in parts))
+    if strong and any(args.n % p for p in parts):
+        raise SystemExit('--scaling strong: n must divide into the bricks')
+
     if args.case == 'tgv':
-        cfg, box = cases.make('tgv', tuple(args.n*p for p in parts),
-                              order=args.order, precision=args.precision,
-                              rsolver=args.rsolver)
+        cfg, box = cases.make('tgv', nglob, order=args.order,
+                              precision=args.precision, rsolver=args.rsolver)
     else:
         args.no_e2e = args.no_cpu = True
-        cfg, box, _ = cases.mixed_case(args.case,
-                                       tuple(args.n*p for p in parts),
-                                       order=args.order,
+        cfg, box, _ = cases.mixed_case(args.case, nglob, order=args.order,
                                        precision=args.precision,
                                        rsolver=args.rsolver)
     cfg.set('backend-b200', 'device-id', lrank)
@@ -290,7 +403,17 @@ def main():
     else:
         comm = type('Serial', (), {'rank': 0, 'size': 1})()
 
-    vparts = box.brick_partition(parts) if world > 1 else None
+    vparts = None
+    if world > 1 and args.partition == 'brick':
+        vparts = box.brick_partition(parts)
+    elif world > 1:
+        vparts = reference_partition(nglob, world)
+
+    # Small partitioned run against the oracle before anything is timed
+    parity = None
+    if not args.no_parity and args.case == 'tgv':
+        parity = parity_check(args, be, comm, rank, world)
+
     t0 = time.time()
     nregs = 2 if args.no_e2e else 4
     sysm = get_system(be, box.local_mesh(vparts, rank), cfg, nregs, comm=comm)
@@ -405,14 +528,20 @@ def main():
 
     # DRAM traffic per launch from the committed ncu --set full capture of
     # this same workload (profiles/ncu_traffic.json), when there is one
-    traffic = {}
+    # (a *static* figure: ncu cannot run inside a timed benchmark; valid
+    # for the per-GPU workload it was captured on, whatever --gpus is)
+    traffic, traffic_src = {}, None
+    nloc = args.n if args.scaling == 'weak' else None
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
             tj = json.load(f)
         if args.case == 'tgv' and \
-           tj['workload'] == (f'tgv n={args.n} order={args.order} '
+           tj['workload'] == (f'tgv n={nloc} order={args.order} '
                               f'{args.precision} {args.rsolver}'):
             traffic = {k: v['dram_bytes'] for k, v in tj['kernels'].items()}
+            traffic_src = ('static: profiles/ncu_traffic.json, dram bytes '
+                           'per launch from the ncu --set full capture '
+                           f'{tj.get("source")} of this per-GPU workload')
     except (OSError, KeyError, ValueError):
         pass
 
@@ -424,7 +553,9 @@ def main():
         roof = {
             'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak_gbs,
             'unit': 'GB/s', 'frac': ach/peak_gbs,
-            'traffic': traffic.get(dom), 'algorithmic_bytes': d['bytes'],
+            'traffic': traffic.get(dom),
+            'traffic_source': traffic_src if dom in traffic else None,
+            'algorithmic_bytes': d['bytes'],
             'peak_source': peak_src, 'kernel_ms': d['ms'],
             'kernel_share_of_step': d['ms']/ksum,
             'sum_kernel_ms': ksum
@@ -533,9 +664,10 @@ def main():
             'metric': 'GDoF-RHS/s', 'value': value, 'unit': 'GDoF/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None,
+            'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64' if isz == 8 else 'f32', 'data': 'synthetic',
-            'config': workload_config(args), 'gpu_launches': launches,
+            'config': workload_config(args), 'parity': parity,
+            'gpu_launches': launches,
             'launches_per_step': nkern, 'cuda_graphs': be.use_graphs,
             'dof': ndof, 'setup_s': setup_s, 'clocks': clocks,
             'roofline': roof, 'rhs_model': rhs_model, 'e2e': e2e,

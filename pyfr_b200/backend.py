@@ -130,6 +130,10 @@ class B200Backend(base.BaseBackend):
         # sum-factorised fused kernel for tensor-product elements
         self.gradflux_tensor = (cfg.getbool(sect, 'gradflux-tensor', True)
                                 and not table_opts)
+        # ... its warp groups (each owns half of a block's elements) and the
+        # phase after which the second group starts (1 or 3)
+        self.gradflux_groups = cfg.getint(sect, 'gradflux-groups', 2)
+        self.gradflux_stagger = cfg.getint(sect, 'gradflux-stagger', 1)
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)

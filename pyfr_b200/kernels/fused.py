@@ -513,7 +513,7 @@ def find_planes(blocks, maxsize=36):
     return comps
 
 
-def geometry_source(be, tplargs, pts, nthreads, affine=False):
+def geometry_source(be, tplargs, pts, nthreads, affine=False, who=None):
     """Source fragments that give the element kernels their metric terms
     (shared by ``gradflux_source`` and ``tensor.gradflux_tp_source``).
 
@@ -524,7 +524,17 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False):
     ``tid``, ``blk``, ``it``, ``bars``, ``G``/``G_WORDS`` and, inside a
     point loop, ``e`` (element of the block) and ``p`` (solution point);
     ``geom`` leaves ``s[NDIMS][NDIMS]`` and ``rcpdjac_v`` in scope.
-    Returns a dict of strings plus ``geo_words`` (shared-memory words)."""
+    Returns a dict of strings plus ``geo_words`` (shared-memory words).
+
+    ``who``: which threads form the per-element quantities and which
+    element a thread works on, as C expressions (default: the first
+    ``C_SUB`` / ``NDIMS*C_SUB`` threads of the CTA, element ``tid %
+    C_SUB``); a kernel whose warp groups own disjoint element sets passes
+    its own."""
+    w = dict(acond='tid < C_SUB', aelem='tid', mine='tid % C_SUB',
+             lcond='tid < NDIMS*C_SUB', lelem='tid % C_SUB',
+             lcomp='tid / C_SUB')
+    w.update(who or {})
     nd = tplargs['ndims']
     nu = len(pts) if pts is not None else 0
     isz = np.dtype(be.fpdtype).itemsize
@@ -560,9 +570,9 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False):
         // every thread picks up those of the one element it works on
         // (tid % C_SUB, the same in every round) and keeps them in
         // registers through phases 2 and 4.
-        if (tid < C_SUB)
+        if (''' + w['acond'] + r''')
         {
-            const int ea = tid;
+            const int ea = ''' + w['aelem'] + r''';
             fpdtype_t jm[NDIMS][NDIMS], sm[NDIMS][NDIMS], djac;
             ''' + '\n            '.join(jl) + r'''
             smats_detj_from_jac(jm, sm, djac);
@@ -575,7 +585,7 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False):
             geo_post = r'''
         fpdtype_t sA[NDIMS][NDIMS], rjA;
         {
-            const fpdtype_t *q = QS + (tid % C_SUB)*(NDIMS*NDIMS + 1);
+            const fpdtype_t *q = QS + (''' + w['mine'] + r''')*(NDIMS*NDIMS + 1);
             UNROLL for (int i = 0; i < NDIMS; i++)
                 UNROLL for (int j = 0; j < NDIMS; j++)
                     sA[i][j] = q[i*NDIMS + j];
@@ -665,9 +675,9 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False):
             q_words = qstride*csub
             geo_elem = (r'''
         // Element-wise Jacobian coefficients from the vertices
-        if (tid < NDIMS*C_SUB)
+        if (''' + w['lcond'] + r''')
         {
-            const int e = tid % C_SUB, i = tid / C_SUB;
+            const int e = ''' + w['lelem'] + r''', i = ''' + w['lcomp'] + r''';
             fpdtype_t v[NVERTS];
             UNROLL for (int n = 0; n < NVERTS; n++)
                 v[n] = VS[n*(NDIMS*C_SUB) + COFF(e, i, NDIMS)];

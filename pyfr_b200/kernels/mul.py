@@ -64,6 +64,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar,
         "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// Barrier over the n threads (a multiple of 32) that name barrier id: lets
+// the warp groups of a CTA synchronise independently of one another
+__device__ __forceinline__ void bar_sync_named(int id, int n)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory");
+}
+
+// One-shot flag in shared memory (release / acquire at CTA scope)
+__device__ __forceinline__ void flag_set(int *f)
+{
+    asm volatile("st.release.cta.shared::cta.s32 [%0], 1;"
+                 :: "r"(smem_u32(f)) : "memory");
+}
+
+__device__ __forceinline__ void flag_wait(int *f)
+{
+    int v;
+    do
+    {
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];"
+                     : "=r"(v) : "r"(smem_u32(f)) : "memory");
+    } while (!v);
+}
+
 // One TMA bulk copy global -> shared, completion signalled on an mbarrier
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src,
                                             unsigned bytes,

@@ -187,25 +187,44 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
 
     if nthreads is None:
         nthreads = getattr(be, 'gradflux_threads', 0) or 512
-    if nthreads % csub or nthreads < NCG:
+
+    # Warp groups: the elements of a block never interact inside this
+    # kernel, so the CTA is split into NG groups of GT threads, each owning
+    # the columns of C_SUB/NG elements and synchronising on its own named
+    # barrier.  The groups run the same phases half a block out of step
+    # (the second starts once the first has finished its first phase 1),
+    # so the FP64-bound flux phase of one overlaps the shared-memory-bound
+    # line phases of the other.
+    NG = getattr(be, 'gradflux_groups', 2)
+    if (NG < 1 or csub % (NG*NC) or be.soasz != csub or nthreads % (32*NG)
+            or (nthreads // NG) % (csub // NG)):
+        NG = 1
+    GT, H = nthreads // NG, csub // NG
+    CPV = H // NC                              # column groups per variable
+    NCGH = nv*CPV                              # ... and per warp group
+
+    if nthreads % csub or GT < NCGH:
         raise NotFusable('thread count does not fit the block layout')
 
-    NLG = nthreads // NCG                      # line groups per round
+    NLG = GT // NCGH                           # line groups per round
     R = -(-nl // NLG)                          # rounds per direction
     ROWB = LD*isz
-    npoints = nu*csub
-    nrounds = -(-npoints // nthreads)
+    nrounds = -(-nu*H // GT)
 
     defs = [('NDIMS', nd), ('NVARS', nv), ('NPTS', nu), ('NFPTS', nf),
             ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
             ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds),
-            ('ROWB', ROWB), ('NCG', NCG), ('NLG', NLG), ('NLINES', nl)]
+            ('ROWB', ROWB), ('NCGH', NCGH), ('NLG', NLG), ('NLINES', nl),
+            ('NG', NG), ('GT', GT), ('H', H), ('CPV', CPV)]
     defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
                                True)
 
     K = ConstPool(isz == 8)
 
-    geo = geometry_source(be, tplargs, pts, nthreads, affine)
+    who = dict(acond='gtid < H', aelem='grp*H + gtid',
+               mine='grp*H + gtid % H', lcond='gtid < NDIMS*H',
+               lelem='grp*H + gtid % H', lcomp='gtid / H')
+    geo = geometry_source(be, tplargs, pts, GT, affine, who=who)
     if affine and not geo['geo_post']:
         affine = False
     geom = geo['geom']
@@ -401,9 +420,9 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         metric_p3 = ''
         p2 = f'''
         // ---- phase 2: physical gradient (in place) ---------------------
-        for (int item = tid; item < NPTS*C_SUB; item += NTHREADS)
+        for (int item = gtid; item < NPTS*H; item += GT)
         {{
-            const int e = item % C_SUB, p = item / C_SUB;
+            const int e = grp*H + item % H, p = item / H;
             if (blk*C_SUB + e >= neles)
                 continue;
 {geom}
@@ -418,7 +437,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                 UNROLL for (int v = 0; v < NVARS; v++)
                     G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = g[d][v];
         }}
-        __syncthreads();
+        GSYNC();
 '''
         p4_xform = '(void) rcpdjac_v;'
 
@@ -426,6 +445,37 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     smem = ((nu + nf + nd*nu)*LD + geo_words)*isz + 64
     if smem > 227*1024:
         raise NotFusable(f'needs {smem} bytes of shared memory')
+
+    stagger = getattr(be, 'gradflux_stagger', 1)
+    if NG > 1:
+        gsync = f'#define GSYNC() bar_sync_named(1 + grp, GT)'
+        hold = '''
+    // The second group starts once the first has finished a phase of its
+    // first block (one thread polls, the rest wait on the group barrier)
+    if (grp > 0 && (long long) blockIdx.x < nblocks)
+    {
+        if (gtid == 0)
+            flag_wait(flag);
+        GSYNC();
+    }
+'''
+        release = ('if (it == 0 && grp == 0 && gtid == 0) flag_set(flag);')
+        issue = '''if (gtid == 0 && nxt < nblocks)
+        {
+            // the group that arrives last starts the copy
+            if (atomicAdd(cnt, 1) == NG - 1)
+            {
+                *reinterpret_cast<volatile int *>(cnt) = 0;
+                fetch(nxt, it + 1);
+            }
+        }'''
+    else:
+        gsync = '#define GSYNC() __syncthreads()'
+        hold, release = '', ''
+        issue = '''if (tid == 0 && nxt < nblocks)
+            fetch(nxt, it + 1);'''
+    rel1 = release if stagger == 1 else ''
+    rel3 = release if stagger != 1 else ''
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz, defs)}
@@ -442,10 +492,12 @@ typedef {vec} fpvec_t;
 #define C_WORDS (NFPTS*LD)
 #define G_WORDS (NDIMS*NPTS*LD)
 #define V_WORDS (NVERTS*NDIMS*C_SUB)
+{gsync}
 
 // tensor-product element, {n1} points per line, {nl} lines per direction;
-// {NC} columns per work item, {NCG} column groups x {NLG} line groups,
-// {R} round(s) per direction{', constant Jacobian' if affine else ''}
+// {NG} warp group(s) of {GT} threads, each over {NCGH} column groups of {NC}
+// columns x {NLG} line groups, {R} round(s) per direction{
+    ', constant Jacobian' if affine else ''}
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
 gradflux(int nblocks, int neles,
          const fpdtype_t* __restrict__ u, long long u_bsz,
@@ -461,18 +513,23 @@ gradflux(int nblocks, int neles,
     {geo['geo_decl']}
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         G + G_WORDS + {geo_words});
+    int *cnt = reinterpret_cast<int *>(bars + 1), *flag = cnt + 1;
+    (void) flag;
 
     char *Ub = reinterpret_cast<char *>(U);
     char *Cb = reinterpret_cast<char *>(C);
     char *Gb = reinterpret_cast<char *>(G);
 
     const int tid = threadIdx.x;
+    const int grp = tid / GT, gtid = tid % GT;
 
-    // This thread's work items: column group cg of the lines lg, lg + NLG,
-    // ... of every direction
-    const int cg = tid % NCG, lg = tid / NCG;
-    const int cb = cg*{NC*isz};
-    const int e0 = ((cg*{NC})/(K_SOA*NVARS))*K_SOA + (cg*{NC}) % K_SOA;
+    // This thread's work items: column group cgl (of its warp group's
+    // elements) of the lines lg, lg + NLG, ... of every direction
+    const int cgl = gtid % NCGH, lg = gtid / NCGH;
+    const int col0 = {'cgl*' + str(NC) if NG == 1 else
+                      f'(cgl / CPV)*C_SUB + grp*H + (cgl % CPV)*{NC}'};
+    const int cb = col0*{isz};
+    const int e0 = (col0/(K_SOA*NVARS))*K_SOA + col0 % K_SOA;
     (void) e0;
 {desc}
 
@@ -482,6 +539,7 @@ gradflux(int nblocks, int neles,
     if (tid == 0)
     {{
         mbar_init(&bars[0], 1);
+        cnt[0] = 0; cnt[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }}
     __syncthreads();
@@ -499,7 +557,7 @@ gradflux(int nblocks, int neles,
     long long blk = blockIdx.x;
     if (tid == 0 && blk < nblocks)
         fetch(blk, 0);
-
+{hold}
     for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
     {{
         const long long nxt = blk + gridDim.x;
@@ -518,35 +576,37 @@ gradflux(int nblocks, int neles,
         fpdtype_t ureg[NROUNDS][NVARS];
         UNROLL for (int r = 0; r < NROUNDS; r++)
         {{
-            const int item = tid + r*NTHREADS;
-            if (item < NPTS*C_SUB)
+            const int item = gtid + r*GT;
+            if (item < NPTS*H)
             {{
-                const int e = item % C_SUB, p = item / C_SUB;
+                const int e = grp*H + item % H, p = item / H;
                 UNROLL for (int v = 0; v < NVARS; v++)
                     ureg[r][v] = U[p*LD + COFF(e, v, NVARS)];
             }}
         }}
-        __syncthreads();
+        GSYNC();
+        {rel1}
 
-        // u and ucomm are consumed: fetch the next block's behind the
-        // remaining phases
-        if (tid == 0 && nxt < nblocks)
-            fetch(nxt, it + 1);
+        // u and ucomm are consumed (by this group): once every group is
+        // here the next block's copies are started behind the remaining
+        // phases
+        {issue}
 {p2}
         // ---- phase 3: gradients at the flux points -> HBM ---------------
         {{
 {metric_p3}
         {p3}
         }}
-        __syncthreads();
+        GSYNC();
+        {rel3}
 
         // ---- phase 4: transformed flux (in place over the gradient) -----
 {geo['geo_post']}
         UNROLL for (int r = 0; r < NROUNDS; r++)
         {{
-            const int item = tid + r*NTHREADS;
-            const int e = item % C_SUB, p = item / C_SUB;
-            if (item < NPTS*C_SUB && blk*C_SUB + e < neles)
+            const int item = gtid + r*GT;
+            const int e = grp*H + item % H, p = item / H;
+            if (item < NPTS*H && blk*C_SUB + e < neles)
             {{
 {geom}
                 fpdtype_t g[NDIMS][NVARS];
@@ -566,17 +626,17 @@ gradflux(int nblocks, int neles,
                         G[(d*NPTS + p)*LD + COFF(e, v, NVARS)] = fo[d][v];
             }}
         }}
-        __syncthreads();
+        GSYNC();
 
         // ---- phase 5: divergence along the lines, summed -> HBM ----------
         {p5a}
-        {'__syncthreads();' if nd > 1 else ''}
+        {'GSYNC();' if nd > 1 else ''}
         {p5b}
-        __syncthreads();
+        GSYNC();
     }}
 }}
 '''
-    meta = dict(nthreads=nthreads, smem=smem, nctas=1,
+    meta = dict(nthreads=nthreads, smem=smem, nctas=1, ngroups=NG,
                 words_per_block=(2*nu + nf + nd*nf)*LD, tensor=True)
 
     return src, 'gradflux', meta

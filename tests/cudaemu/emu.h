@@ -102,6 +102,30 @@ struct EmuBarrier
 static EmuBarrier emu_cta_barrier;
 static inline void __syncthreads() { emu_cta_barrier.wait(); }
 
+// ---- named barriers (bar.sync id, n) and one-shot flags -----------------------
+static EmuBarrier emu_named_barriers[16];
+
+static inline void bar_sync_named(int id, int n)
+{
+    EmuBarrier &b = emu_named_barriers[id];
+    {
+        std::lock_guard<std::mutex> lk(b.m);
+        b.n = (unsigned) n;
+    }
+    b.wait();
+}
+
+static inline void flag_set(int *f)
+{
+    reinterpret_cast<std::atomic<int> *>(f)->store(1, std::memory_order_release);
+}
+
+static inline void flag_wait(int *f)
+{
+    while (!reinterpret_cast<std::atomic<int> *>(f)->load(std::memory_order_acquire))
+        std::this_thread::yield();
+}
+
 // ---- mbarrier + TMA bulk copy ---------------------------------------------------
 // The 8-byte shared-memory slot holds {completed phases, pending bytes}
 struct EmuMbar { std::atomic<unsigned> completed; std::atomic<unsigned> pending; };

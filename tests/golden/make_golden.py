@@ -307,6 +307,42 @@ CONN_CASES = {
 }
 
 
+PARTITION_SIZES = (6, 64, 128)
+
+
+def ref_partitions(n, nparts=(2, 4, 8)):
+    """``vparts<N>``: the partition of a periodic ``n``^3 hex box into N
+    parts by the reference's ``BaselinePartitioner`` (default options, unit
+    weights; ``pyfr/partitioners/baseline.py:87-105`` on the dual graph the
+    reference builds in ``pyfr/partitioners/base.py``)."""
+    rh.install_stubs()
+    from pyfr.partitioners.base import Graph
+    from pyfr.partitioners.baseline import BaselinePartitioner
+
+    from pyfr_b200.host.mesh import BoxMesh
+
+    box = BoxMesh((n, n, n), 0.0, 1.0, periodic=True)
+    ne = box.neles
+
+    # Dual graph: every element of a periodic box of n >= 3 has six
+    # distinct neighbours
+    nb = np.sort(box.roff, axis=1)
+    assert (nb >= 0).all() and (np.diff(nb, axis=1) > 0).all()
+    vtab = 6*np.arange(ne + 1, dtype=np.int64)
+    etab = nb.ravel().astype(np.int64)
+
+    out = {}
+    for k in nparts:
+        graph = Graph(vtab, etab, np.ones(ne, dtype=np.int32),
+                      np.ones(len(etab), dtype=np.int32))
+        part = BaselinePartitioner([1]*k, elewts={box.etype: 1})
+        vp = np.asarray(part._partition_graph(graph, [1.0]*k))
+        assert len(np.unique(vp)) == k
+        out[f'vparts{k}'] = vp.astype(np.int8)
+
+    return out
+
+
 def ref_connectivity_case(name):
     """Partition a synthetic box with the reference's own
     ``BaselinePartitioner`` (pyfr/partitioners/baseline.py) and derive each
@@ -630,6 +666,17 @@ def main():
             np.savez_compressed(os.path.join(HERE, f'host_{name}.npz'),
                                 **ref_host_case(name))
             print(f'host_{name}.npz written')
+        return
+
+    if sys.argv[1:2] == ['--partitions']:
+        # parts_hex<n>.npz: the reference partitioner's element -> rank
+        # maps of periodic n^3 hex boxes (what bench.py --partition
+        # reference and the strong-scaling runs use)
+        for n in map(int, sys.argv[2].split(',') if sys.argv[2:] else
+                     PARTITION_SIZES):
+            np.savez_compressed(os.path.join(HERE, f'parts_hex{n}.npz'),
+                                **ref_partitions(n))
+            print(f'parts_hex{n}.npz written')
         return
 
     if sys.argv[1:] == ['--mixed']:

@@ -196,7 +196,11 @@ def test_boundary_conditions_match_oracle(built, system, n, bcs, kw):
     esys, ext = run(OracleBackend, extended=True)
     sysm, out = run(B200Backend)
 
-    assert_parity(out, ref, ext, TOL64, mag=rhs_magnitude(esys)[0])
+    # (no point-wise running-error criterion here: its magnitude field is
+    # built from the interior trace alone, while a boundary flux is summed
+    # from the *ghost* state's terms -- prescribed inflow values, pow() of
+    # the characteristic boundary -- which can exceed it many times over)
+    assert_parity(out, ref, ext, TOL64)
 
     kinds = [getattr(k, 'kind', None) for g in sysm.rhs_graphs(0, 1)
              for w, k in g.plan if w == 'kernel']
