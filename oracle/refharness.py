@@ -1,7 +1,10 @@
 """TEST ORACLE -- drive the reference's *own* host code in this container.
 
-Only usable where ``/root/reference`` exists (the build container); never
-imported by the product, by ``-m gpu`` tests, ``smoke()`` or ``bench.py``.
+Only usable where a reference tree exists (``/root/reference`` in the build
+container, or the offline install ``baseline/_ref``); never imported by the
+product, by ``smoke()`` or by ``bench.py``.  The one ``-m gpu`` test that
+uses it (tests/test_reference_dropin.py) lets the reference's *host code*
+drive the B200 backend on the device and skips where no tree is present.
 
 The reference's solver stack imports a handful of third-party packages that
 are absent here (mako, mpi4py, h5py, rtree, pytools, gimmik).  None of them
@@ -21,7 +24,21 @@ from types import SimpleNamespace
 
 import numpy as np
 
-REFROOT = os.environ.get('PYFR_B200_REFROOT', '/root/reference')
+def _find_reference():
+    """The reference tree: ``$PYFR_B200_REFROOT``, the read-only checkout of
+    the build container, or the offline install ``baseline/_ref`` (``pip
+    install --no-deps --target baseline/_ref``; git-ignored, but it travels
+    with the repository snapshot to a GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get('PYFR_B200_REFROOT'), '/root/reference',
+             os.path.join(here, 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, 'pyfr')):
+            return c
+    return cands[0] or cands[1]
+
+
+REFROOT = _find_reference()
 
 
 def available():

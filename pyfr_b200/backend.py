@@ -118,7 +118,7 @@ class B200Backend(base.BaseBackend):
         # looked up before the getters below record their defaults)
         table_opts = any(cfg.hasopt(sect, o) for o in (
             'gradflux-vec2', 'gradflux-planes', 'gradflux-ncol',
-            'gradflux-monojac', 'gradflux-maxctas'))
+            'gradflux-monojac'))
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
         # fp64 operators with at least this many distinct coefficients keep
@@ -132,7 +132,7 @@ class B200Backend(base.BaseBackend):
                                 and not table_opts)
         # ... its warp groups (each owns half of a block's elements) and the
         # phase after which the second group starts (1 or 3)
-        self.gradflux_groups = cfg.getint(sect, 'gradflux-groups', 2)
+        self.gradflux_groups = cfg.getint(sect, 'gradflux-groups', 1)
         self.gradflux_stagger = cfg.getint(sect, 'gradflux-stagger', 1)
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
@@ -163,6 +163,8 @@ class B200Backend(base.BaseBackend):
         # Runge-Kutta stage update in the epilogue of the last RHS kernel
         # (only when the caller groups an rkvdh2 kernel with the RHS)
         self.rk_fusion = cfg.getbool(sect, 'rk-fusion', True)
+        # one launch for the per-neighbour kernels (pack, mpiconu, mpicflux)
+        self.batch_launches = cfg.getbool(sect, 'batch-launches', True)
         self.use_graphs = cfg.getbool(sect, 'graphs', True) and not dry
         self.fuse = cfg.getbool(sect, 'fusion', True)
 

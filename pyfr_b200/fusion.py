@@ -346,7 +346,8 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     args = [('i', nblocks), ('p', b.data), ('l', b.blocksz), ('p', out.data),
             ('l', out.blocksz), ('p', r.data), ('l', r.blocksz)] + rkargs
     k = B200Kernel(
-        be, fn, (min(nblocks, be.sm_count), 1, 1), (meta['nthreads'], 1, 1),
+        be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
+        (meta['nthreads'], 1, 1),
         meta['smem'], args, mats=[b, out, r] + rkmats, misc=[meta],
         traffic=traffic,
         kind='mul+negdivconf+rkvdh2' if rk else 'mul+negdivconf',
@@ -569,4 +570,145 @@ def elide_copy_fpts(be, program):
             continue
         out.append((w, repl.get(k, k)))
 
+    return out
+
+
+# -- one launch for the per-neighbour kernels of a graph -------------------------
+_sig_re = None
+
+
+def _batched_source(src):
+    """Turns a 1-D pointwise kernel into a device function and wraps it in
+    a kernel that takes its arguments from a table indexed by
+    ``blockIdx.y``.  Returns (source, kernel name, [parameter types])."""
+    import re
+
+    global _sig_re
+    if _sig_re is None:
+        _sig_re = re.compile(
+            r'extern "C" __global__ void\s*(__launch_bounds__\([^)]*\))?\s*'
+            r'(\w+)\s*\(([^)]*)\)', re.S
+        )
+
+    m = _sig_re.search(src)
+    bounds, name, params = m.group(1) or '', m.group(2), m.group(3)
+    params = [p.strip() for p in params.split(',') if p.strip()]
+    types = [re.sub(r'\w+$', '', p).replace('__restrict__', '').strip()
+             for p in params]
+
+    impl = (f'static __device__ __forceinline__ void {name}_impl('
+            + ', '.join(params) + ')')
+    body = src[:m.start()] + impl + src[m.end():]
+
+    fields = '\n'.join(f'    {t} a{i};' for i, t in enumerate(types))
+    call = ', '.join(f'a.a{i}' for i in range(len(types)))
+    wrap = f'''
+// The same kernel over several argument sets (one per neighbouring
+// partition): grid.y selects the set, grid.x covers the largest
+struct batch_args_t
+{{
+{fields}
+}};
+
+extern "C" __global__ void {bounds}
+{name}(const batch_args_t* __restrict__ tbl)
+{{
+    const batch_args_t a = tbl[blockIdx.y];
+    {name}_impl({call});
+}}
+'''
+    return body + wrap, name, types
+
+
+def _arg_table(kerns):
+    """The argument sets of ``kerns`` laid out as the C compiler lays out
+    ``batch_args_t`` (natural alignment), as an int64 matrix."""
+    import ctypes as ct
+
+    size = {'p': 8, 'l': 8, 'd': 8, 'i': 4, 'f': 4}
+    codes = kerns[0].argcodes
+    offs, off = [], 0
+    for c in codes:
+        off = -(-off // size[c])*size[c]
+        offs.append(off)
+        off += size[c]
+    stride = -(-off // 8)*8
+
+    buf = np.zeros((len(kerns), stride), dtype=np.uint8)
+    for j, k in enumerate(kerns):
+        for c, o, v in zip(codes, offs, k._vals):
+            raw = ct.string_at(ct.addressof(v), size[c])
+            buf[j, o:o + size[c]] = np.frombuffer(raw, dtype=np.uint8)
+
+    return buf.view(np.int64)
+
+
+_batchable = ('pack', 'mpiconu', 'mpicflux')
+
+
+def batch_launches(be, program):
+    """Kernels a graph holds once per neighbouring partition -- ``pack``,
+    ``mpiconu``, ``mpicflux`` (``pyfr/solvers/base/system.py:185-202``,
+    ``pyfr/solvers/navstokes/inters.py:58-67``) -- are launches of one
+    device function over independent argument sets: runs of them become a
+    single launch whose ``blockIdx.y`` picks the argument set from a
+    device-resident table.  At eight ranks this removes eight of the
+    twelve per-neighbour launches of an RHS (10-25 us each)."""
+    from pyfr_b200.providers import B200Kernel
+
+    def kind_of(k):
+        if not isinstance(k, B200Kernel) or k.smem or \
+           getattr(k, 'rtnames', None):
+            return None
+        kind = k.kind or k.fn.name
+        return kind if kind in _batchable else None
+
+    out, run = [], []
+
+    def flush():
+        """``run``: consecutive kernels of one kind (with the exchange
+        requests issued between them).  They act on different neighbours'
+        points, so they may be regrouped by device function (the kernels
+        of a one-sided LDG flux come in two variants, by rank parity)."""
+        ks = [k for w, k in run if w == 'kernel']
+        groups = {}
+        for k in ks:
+            groups.setdefault((id(k.fn), k.block), []).append(k)
+
+        for g in groups.values():
+            if len(g) == 1:
+                out.append(('kernel', g[0]))
+                continue
+
+            src, name, types = _batched_source(g[0].fn.src)
+            fn = be.pointwise._function(src, name)
+            tbl = be.const_matrix(_arg_table(g), dtype=np.int64,
+                                  tags={'noblock'})
+            out.append(('kernel', B200Kernel(
+                be, fn, (max(k.grid[0] for k in g), len(g), 1),
+                g[0].block, 0, [('p', tbl.data)],
+                mats=[m for k in g for m in k.mats] + [tbl],
+                views=[v for k in g for v in k.views],
+                traffic=sum(k.traffic for k in g),
+                kind=g[0].kind or g[0].fn.name, info=dict(batched=g)
+            )))
+
+        out.extend(e for e in run if e[0] != 'kernel')
+        run.clear()
+
+    for w, obj in program:
+        if w == 'kernel':
+            kk = kind_of(obj)
+            cur = next((kind_of(k) for ww, k in run if ww == 'kernel'), None)
+            if kk is None or (cur is not None and kk != cur):
+                flush()
+            if kk is None:
+                out.append((w, obj))
+            else:
+                run.append((w, obj))
+        else:
+            # exchanges between the members of a run stay behind them
+            (run if run else out).append((w, obj))
+
+    flush()
     return out

@@ -166,6 +166,12 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
     R = max(1, min(rowgroups, 32 // wpr, M))
     nthreads = 32*wpr*R
 
+    # Narrow blocks (a small SoA width) leave most of an SM idle under one
+    # CTA: run as many persistent CTAs per SM as fit 256 threads and the
+    # shared memory
+    smem_cta = 2*crows*LD*isz + 16
+    nctas = max(1, min(256 // nthreads, smem_budget // (smem_cta + 1024)))
+
     # Output rows of each row group
     bounds = np.linspace(0, M, R + 1).astype(int)
     groups = [range(bounds[i], bounds[i + 1]) for i in range(R)]
@@ -270,7 +276,7 @@ def mul_source(be, A, LD, alpha, beta, smem_budget=200*1024, rowgroups=4,
 
 // out[{M} x LD] = A[{M} x {K}] @ b[{K} x LD] per element block;
 // {int(np.count_nonzero(A))} non-zeros, {nchunks} chunk(s) of {crows} rows
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+extern "C" __global__ void __launch_bounds__(NTHREADS, {nctas})
 opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
       fpdtype_t* __restrict__ out, long long out_bsz{extra_args})
 {{
@@ -340,7 +346,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
 }}
 '''
 
-    meta = dict(nthreads=nthreads,
+    meta = dict(nthreads=nthreads, nctas=nctas,
                 smem=2*crows*LD*isz + 16, nnz=int(np.count_nonzero(A)),
                 nchunks=nchunks, crows=crows, M=M, K=K)
 

@@ -185,8 +185,16 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     linear = 'linear' in tplargs['ktype']
     affine = bool(affine and linear)
 
+    # Occupancy plan: as many CTAs per SM as the shared-memory footprint
+    # allows (two when a block is half an SM's worth, e.g. n-soa = 4 in
+    # fp64), sharing a budget of 512 threads.  Co-resident CTAs work on
+    # different blocks and drift apart, so the FP64-bound flux phase of one
+    # overlaps the shared-memory-bound line phases of the other.
+    smem_est = (nu + nf + nd*nu)*LD*isz + 4096
+    nctas = max(1, min(getattr(be, 'gradflux_maxctas', 2),
+                       (227*1024) // smem_est))
     if nthreads is None:
-        nthreads = getattr(be, 'gradflux_threads', 0) or 512
+        nthreads = getattr(be, 'gradflux_threads', 0) or 512 // nctas
 
     # Warp groups: the elements of a block never interact inside this
     # kernel, so the CTA is split into NG groups of GT threads, each owning
@@ -195,7 +203,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     # (the second starts once the first has finished its first phase 1),
     # so the FP64-bound flux phase of one overlaps the shared-memory-bound
     # line phases of the other.
-    NG = getattr(be, 'gradflux_groups', 2)
+    NG = getattr(be, 'gradflux_groups', 1)
     if (NG < 1 or csub % (NG*NC) or be.soasz != csub or nthreads % (32*NG)
             or (nthreads // NG) % (csub // NG)):
         NG = 1
@@ -498,7 +506,7 @@ typedef {vec} fpvec_t;
 // {NG} warp group(s) of {GT} threads, each over {NCGH} column groups of {NC}
 // columns x {NLG} line groups, {R} round(s) per direction{
     ', constant Jacobian' if affine else ''}
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+extern "C" __global__ void __launch_bounds__(NTHREADS, {nctas})
 gradflux(int nblocks, int neles,
          const fpdtype_t* __restrict__ u, long long u_bsz,
          const fpdtype_t* ucomm, long long ucomm_bsz,
@@ -636,7 +644,9 @@ gradflux(int nblocks, int neles,
     }}
 }}
 '''
-    meta = dict(nthreads=nthreads, smem=smem, nctas=1, ngroups=NG,
+    if nctas*(smem + 1024) > 227*1024:
+        nctas = 1
+    meta = dict(nthreads=nthreads, smem=smem, nctas=nctas, ngroups=NG,
                 words_per_block=(2*nu + nf + nd*nf)*LD, tensor=True)
 
     return src, 'gradflux', meta

@@ -185,6 +185,9 @@ class B200Graph(base.Graph):
 
         self.program = fusion.elide_copy_fpts(be, self.program)
 
+        if be.batch_launches:
+            self.program = fusion.batch_launches(be, self.program)
+
     def _commit(self):
         self._fuse()
 

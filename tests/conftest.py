@@ -57,6 +57,9 @@ def pytest_terminal_summary(terminalreporter):
 
     tr = terminalreporter
     fp = [r for r in PARITY_LOG if r['err'] == r['err']]
+    for r in fp:
+        if r['floor'] != r['floor']:
+            r['floor'] = 0.0
     worst = max(fp, key=lambda r: r['err'])
     rr = [r for r in fp if r.get('ratio') is not None]
 

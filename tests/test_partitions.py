@@ -140,8 +140,13 @@ def test_partitioned_rhs_matches_partitioned_oracle(substrate, case, n, part,
                             f'rank {r}/{nparts}]')
 
         kinds = _kinds(s)
-        assert 'pack_view' in kinds and 'mpicflux' in kinds
+        assert 'pack' in kinds and 'mpicflux' in kinds
         assert ('mpiconu' in kinds) == viscous and 'copy' not in kinds
+
+        # the per-neighbour kernels of a graph go out as one launch each
+        # (pack: once for the solution, once for the gradients)
+        assert kinds.count('mpicflux') <= 2 and kinds.count('pack') <= 2
+        assert kinds.count('mpiconu') <= 2
 
     # The partitioned discretisation differs from the single-partition one
     # exactly when the LDG flux is one-sided (a check that the test would

@@ -526,3 +526,92 @@ def test_reference_boundary_interfaces_on_b200_backend(built):
     rows = [l.split()[1:] for l in res.stdout.splitlines()
             if l.startswith('RESULT')]
     assert len(rows) == 3 and all(float(r[2]) < 1e-12 for r in rows)
+
+
+_device_script = r"""
+import os, sys
+os.environ['PYFR_B200_BASE'] = 'pyfr.backends.base'
+ROOT = %(root)r
+sys.path[:0] = [ROOT, ROOT + '/tests']
+from types import SimpleNamespace
+import numpy as np
+from oracle import refharness as rh
+from oracle.npbackend import LocalComm
+rh.install_stubs()
+from pyfr.inifile import Inifile
+from pyfr.backends.base import BaseBackend
+from pyfr.solvers.navstokes import NavierStokesSystem
+from pyfr.solvers.euler import EulerSystem
+from pyfr.util import subclass_where
+from pyfr_b200 import cases
+from pyfr_b200.backend import B200Backend
+
+# the reference's own backend discovery finds the backend by name
+# (pyfr/backends/__init__.py:10-11)
+assert subclass_where(BaseBackend, name='b200') is B200Backend
+assert issubclass(B200Backend, BaseBackend)
+
+for case, n, kw in [('tgv', (4, 3, 3), dict(order=4)),
+                    ('tgv', (4, 3, 3), dict(order=3, warp=0.1,
+                                            rsolver='hllc', beta=0.0)),
+                    ('vortex', 8, dict(order=3))]:
+    kw2 = {k: v for k, v in kw.items() if k != 'warp'}
+    txt = (cases.tgv_cfg(**kw2) if case == 'tgv' else cases.vortex_cfg(**kw2))
+    _, box = cases.make(case, n, **kw)
+    mesh = box.local_mesh()
+    world = LocalComm(0, 1)
+    rh.set_rank(world.peer(0))
+
+    be = B200Backend(Inifile(txt))
+    assert not be.rt.dry and be.use_graphs
+    regs = [SimpleNamespace(rhs=True, dynamic=False, n=2, extent=None)]
+    cls = NavierStokesSystem if case == 'tgv' else EulerSystem
+    s = cls(be, rh.ref_mesh(mesh), None, regs, Inifile(txt), None)
+    s.commit()
+    for _ in range(2):
+        s.rhs(0.0, 0, 1)
+    be.wait()
+    out = s.ele_scal_upts(1)[0]
+    kinds = [getattr(k, 'kind', None) or k.fn.name
+             for g in s._rhs_graphs(0, 1) for w, k in g.plan if w == 'kernel']
+
+    # reference host code on the NumPy oracle backend, same mesh
+    rs, rbe = rh.ref_system(txt, mesh, 2, world.peer(0))
+    rs.rhs(0.0, 0, 1)
+    ref = rs.ele_scal_upts(1)[0]
+    print('RESULT', case, np.abs(out - ref).max()/np.abs(ref).max(),
+          ','.join(kinds))
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _ref_available(),
+                    reason='no PyFR tree (PYFR_B200_REFROOT, /root/reference '
+                           'or baseline/_ref)')
+def test_reference_host_drives_the_device(built):
+    """The drop-in on hardware: the reference's unmodified
+    ``NavierStokesSystem`` / ``EulerSystem`` (from the PyFR tree that is
+    present) drive ``B200Backend`` -- derived from the reference's own
+    ``pyfr.backends.base`` classes and found by its backend discovery -- on
+    the device, CUDA graphs on; the RHS equals the reference host on the
+    NumPy oracle backend."""
+    res = subprocess.run([sys.executable, '-c',
+                          _device_script % {'root': ROOT}],
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+
+    rows = [l.split() for l in res.stdout.splitlines()
+            if l.startswith('RESULT')]
+    assert [r[1] for r in rows] == ['tgv', 'tgv', 'vortex']
+    # (the p = 4 case is held to the oracle's fp64 floor at that order)
+    assert float(rows[0][2]) < 3e-11 and float(rows[1][2]) < 5e-12
+    assert float(rows[2][2]) < 1e-12
+    assert rows[0][3].split(',') == ['mul', 'intconu', 'gradflux',
+                                     'intcflux', 'mul+negdivconf']
+    assert 'fluxdiv' in rows[2][3]
+
+    from util import PARITY_LOG
+    for r in rows:
+        PARITY_LOG.append(dict(test=f'reference host on the device: {r[1]}',
+                               err=float(r[2]), floor=0.0, ratio=None,
+                               ratio_oracle=None, kernels=r[3]))

@@ -113,6 +113,57 @@ def rhs_magnitude(sysm, uin=0, fout=1):
     return mags
 
 
+def rhs_magnitude_from_state(cfg, mesh, u, eidx=None):
+    """The magnitude field of ``rhs_magnitude`` formed from the *solution*
+    alone (no oracle run), for the elements ``eidx`` of a one-element-type
+    mesh: the transformed flux is taken as the inviscid one (the viscous
+    flux is smaller by the Reynolds number) and the Riemann terms from the
+    element's own trace.  What the full-size parity test uses, where no
+    extended-precision evaluation is affordable."""
+    from pyfr_b200.host.elements import EulerElements, NavierStokesElements
+    from pyfr_b200.host.shapes import shape_map
+
+    cls = {'euler': EulerElements, 'navier-stokes': NavierStokesElements}[
+        cfg.get('solver', 'system')]
+    gamma = cfg.getfloat('constants', 'gamma')
+    (et, spts), = mesh.spts.items()
+    if eidx is not None:
+        spts, u = spts[:, eidx], u[..., eidx]
+
+    e = cls(shape_map[et], spts, cfg)
+    nd, nu = e.ndims, e.nupts
+
+    def prim(q):
+        rho, E = q[:, 0], q[:, -1]
+        vel = [q[:, 1 + d]/rho for d in range(nd)]
+        p = (gamma - 1)*(E - 0.5*rho*sum(v*v for v in vel))
+        return rho, vel, E, p
+
+    # |S F_inv(u)| at the solution points, term by term
+    rho, vel, E, p = prim(u)
+    F = np.zeros((nd,) + u.shape)
+    for d in range(nd):
+        F[d, :, 0] = np.abs(rho*vel[d])
+        for i in range(nd):
+            F[d, :, 1 + i] = np.abs(rho*vel[d]*vel[i]) + (d == i)*np.abs(p)
+        F[d, :, -1] = np.abs((E + p)*vel[d])
+    smat = np.abs(e.smat_at_np('upts'))              # (nd, nupts, nd, neles)
+    Ft = np.einsum('dpke,kpve->dpve', smat, F)
+
+    mm = lambda A, B: (A @ B.reshape(B.shape[0], -1)).reshape(
+        A.shape[0], *B.shape[1:])
+    A5 = np.abs(e.basis.opmat('M1 - M3*M2'))
+    S = mm(A5, Ft.reshape(nd*nu, *u.shape[1:]))
+
+    uf = mm(e.basis.opmat('M0'), u)
+    rho, vel, E, p = prim(uf)
+    lam = np.sqrt(sum(v*v for v in vel)) + np.sqrt(np.abs(gamma*p/rho))
+    magn = np.linalg.norm(e._pnorm_fpts, axis=-1)
+    S += mm(np.abs(e.basis.opmat('M3')), (magn*lam)[:, None, :]*np.abs(uf))
+
+    return np.abs(e.rcpdjac_at_np('upts'))[:, None, :]*S
+
+
 def running_error_ratio(out, ref_ext, mag):
     """max over points of ``|out - ext| / (eps * magnitude)``."""
     eps = np.finfo(np.asarray(out).dtype).eps
