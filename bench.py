@@ -40,7 +40,10 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=64, help='hexes per direction: '
+    # (--mesh-n: the spelling to use under torchrun, whose own parser
+    # claims --n as an abbreviation of --nnodes)
+    ap.add_argument('--n', '--mesh-n', type=int, default=64,
+                    help='hexes per direction: '
                     'per GPU (weak scaling) or of the whole mesh (strong)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: N bricks of n^3 (the default, what the '
@@ -53,6 +56,10 @@ def parse():
                     'made for this mesh, from tests/golden/parts_hex<n>.npz')
     ap.add_argument('--no-parity', action='store_true', help='skip the '
                     'small partitioned-oracle check that precedes the timing')
+    ap.add_argument('--timestep', action='store_true', help='also time whole '
+                    'time steps (RK4 over axnpby; RK45 with separate and '
+                    'with fused stage updates) and report them as '
+                    '"time_step"')
     ap.add_argument('--case', default='tgv',
                     choices=['tgv', 'hex+pri', 'hex+pri+pyr+tet'],
                     help='tgv: the headline workload; the others time '
@@ -154,7 +161,8 @@ class ClockSampler:
                 'power_w_max': max(pw)}
 
 
-def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1, n=None):
+def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1, n=None,
+                 budget_s=None):
     """The C/OpenMP restatement of the reference's CPU design
     (oracle/crhs, driven through the oracle backend API) on all host
     cores: the same TGV case on an ``n``^3 mesh (default: the bounded
@@ -180,8 +188,15 @@ def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1, n=None):
     sysm = get_system(be, box.local_mesh(), cfg, 2)
     ndof = sum(sysm.ele_ndofs)
 
+    t0 = time.perf_counter()
     for _ in range(max(warmup, 1)):
         sysm.rhs(0.0, 0, 1)
+
+    # (exactly ``steps`` timed evaluations unless that would exceed the
+    # time budget, judged by the warm-up)
+    if steps and budget_s:
+        est = (time.perf_counter() - t0)/max(warmup, 1)
+        steps = max(1, min(steps, int(budget_s/max(est, 1e-9))))
 
     times, t0 = [], time.perf_counter()
     while (len(times) < steps if steps else
@@ -193,7 +208,7 @@ def cpu_baseline(args, min_seconds=10.0, steps=None, warmup=1, n=None):
 
     return {
         'value': ndof/dt/1e9, 'unit': 'GDoF/s', 'cores': be.nthreads,
-        'kind': 'port', 'mesh': f'{n}^3',
+        'kind': 'port', 'mesh': f'{n}^3', 'nsteps': len(times),
         'step_s': {'median': dt, 'min': min(times), 'max': max(times)},
         'sample': f'median of {len(times)} RHS evaluations of TGV NS hex '
                   f'p={args.order} fp64 on {n}^3 elements ({ndof} DoF); '
@@ -218,9 +233,9 @@ def reference_arm(args):
     # second or so of CPU time (64^3: ~0.5 s), else the bounded sample;
     # at most ~60 s of timed work whatever --steps says
     n = args.n if args.n <= 64 else args.cpu_n
-    steps = max(3, min(args.steps, 60))
-    info, dt = cpu_baseline(args, steps=steps, warmup=max(args.warmup, 1),
-                            n=n)
+    info, dt = cpu_baseline(args, steps=args.steps,
+                            warmup=max(args.warmup, 1), n=n, budget_s=90.0)
+    steps = info.pop('nsteps')
 
     cfgd = workload_config(args, n=n, reference=True)
     v = info['value']
@@ -388,6 +403,14 @@ def main():
                                        precision=args.precision,
                                        rsolver=args.rsolver)
     cfg.set('backend-b200', 'device-id', lrank)
+
+    # 64-bit view indices where a rank's largest buffer (the gradients at
+    # the flux points) outgrows 32-bit element offsets: 128^3 on one or two
+    # ranks (reference: [backend] memory-model = large)
+    nele_loc = int(np.prod(nglob))//world
+    n1 = args.order + 1
+    if args.case == 'tgv' and 3*6*n1**2*5*nele_loc*1.05 >= 2**31:
+        cfg.set('backend', 'memory-model', 'large')
     if args.no_graphs:
         cfg.set('backend-b200', 'graphs', 'false')
     for kv in args.opt:
@@ -416,6 +439,8 @@ def main():
 
     t0 = time.time()
     nregs = 2 if args.no_e2e else 4
+    if args.timestep:
+        nregs = max(nregs, 3)
     sysm = get_system(be, box.local_mesh(vparts, rank), cfg, nregs, comm=comm)
     setup_s = time.time() - t0
     ndof_local = sum(sysm.ele_ndofs)
@@ -654,10 +679,33 @@ def main():
                 raise
             e2e_error = f'{type(exc).__name__}: {exc}'
 
+    # ---- whole time steps (the callers of the RHS) ----------
+    tstep = None
+    if args.timestep:
+        from pyfr_b200.host.integrator import RK4Stepper, RK45Stepper
+
+        tstep, dt = {}, 1e-5
+        for name, mk, nst in [
+                ('rk4', lambda: RK4Stepper(sysm), 4),
+                ('rk45', lambda: RK45Stepper(sysm), 5),
+                ('rk45_fused_update', lambda: RK45Stepper(sysm, fused=True),
+                 5)]:
+            st = mk()
+            for _ in range(3):
+                st.step(dt)
+            nsteps = max(3, args.steps//4)
+            tms = timed(lambda: st.step(dt), nsteps)/nsteps
+            tstep[name] = {
+                'ms_per_step': tms, 'rhs_per_step': nst,
+                'gdof_rhs_per_s': ndof*nst/(tms*1e-3)/1e9,
+                'overhead_vs_rhs_only': tms/(nst*ms_per_step) - 1
+            }
+
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_baseline(args)
+        cpu.pop('nsteps', None)
 
     if rank == 0:
         line = {
@@ -669,8 +717,10 @@ def main():
             'config': workload_config(args), 'parity': parity,
             'gpu_launches': launches,
             'launches_per_step': nkern, 'cuda_graphs': be.use_graphs,
+            'index_bits': 64 if be.ixdtype == np.int64 else 32,
             'dof': ndof, 'setup_s': setup_s, 'clocks': clocks,
-            'roofline': roof, 'rhs_model': rhs_model, 'e2e': e2e,
+            'roofline': roof, 'rhs_model': rhs_model, 'time_step': tstep,
+            'e2e': e2e,
             **({'e2e_error': e2e_error} if e2e_error else {}),
             'cpu_baseline': cpu,
             'compiler': be.compiler.stats

@@ -109,7 +109,10 @@ class B200Backend(base.BaseBackend):
         # hold a whole block's gradients in shared memory at p = 4
         isz = np.dtype(self.fpdtype).itemsize
         self.alignb = 256
-        self.soasz = cfg.getint(sect, 'n-soa', 64 // isz)
+        if cfg.hasopt(sect, 'n-soa'):
+            self.soasz = cfg.getint(sect, 'n-soa')
+        else:
+            self.soasz = self._auto_soasz(cfg, isz)
         self.csubsz = cfg.getint(sect, 'n-csub', self.soasz)
         if self.csubsz % self.soasz:
             raise ValueError('n-csub must be a multiple of n-soa')
@@ -121,6 +124,8 @@ class B200Backend(base.BaseBackend):
             'gradflux-monojac'))
 
         self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
+        # dense operators (tets, pyramids) take the small-GEMM kernel
+        self.dense_mul = cfg.getbool(sect, 'dense-mul', True)
         # fp64 operators with at least this many distinct coefficients keep
         # them in __constant__ memory (0: always literals)
         self.mul_const_table = cfg.getint(sect, 'mul-const-table', 0)
@@ -134,6 +139,10 @@ class B200Backend(base.BaseBackend):
         # phase after which the second group starts (1 or 3)
         self.gradflux_groups = cfg.getint(sect, 'gradflux-groups', 1)
         self.gradflux_stagger = cfg.getint(sect, 'gradflux-stagger', 1)
+        # fetch the constant metric of a flux-point work item after its
+        # interpolation (fewer live registers, three fetches per block)
+        self.gradflux_metric_late = cfg.getbool(sect, 'gradflux-metric-late',
+                                                False)
         self.gradflux_planes = cfg.getbool(sect, 'gradflux-planes', False)
         self.gradflux_monojac = cfg.getbool(sect, 'gradflux-monojac', True)
         self.gradflux_ncol = cfg.getint(sect, 'gradflux-ncol', 1)
@@ -189,6 +198,27 @@ class B200Backend(base.BaseBackend):
         self._providers = [providers.OperatorProvider(self),
                            providers.BlasExtProvider(self),
                            providers.PackingProvider(self), self.pointwise]
+
+    @staticmethod
+    def _auto_soasz(cfg, isz, smem=212*1024):
+        """SoA width: 64 bytes' worth of scalars, halved (down to one
+        16-byte access) until the fused element kernel of a hexahedron of
+        the configured order keeps a whole block -- solution, common
+        solution and the ndims gradient components of nvars = 5 fields --
+        in shared memory.  fp64 p <= 4 and fp32 p <= 3 keep the full width;
+        fp32 p = 6 (BASELINE configs[4]) runs at a width of 4, where the
+        fused kernel is 2.2x faster than the eleven-launch chain of the
+        full width (profiles/r02e)."""
+        soasz = 64 // isz
+        try:
+            n1 = cfg.getint('solver', 'order') + 1
+        except Exception:
+            return soasz
+
+        rows = 4*n1**3 + 6*n1**2
+        while soasz*isz > 16 and rows*5*soasz*isz > smem:
+            soasz //= 2
+        return soasz
 
     def _malloc_impl(self, nbytes):
         return types.DevAlloc(self.rt, nbytes)

@@ -19,6 +19,7 @@ import numpy as np
 
 from pyfr_b200.kernels import fused as kfused
 from pyfr_b200.kernels import fused_euler as keuler
+from pyfr_b200.kernels import dense as kdense
 from pyfr_b200.kernels import mul as kmul
 from pyfr_b200.kernels import tensor as ktensor
 
@@ -332,10 +333,19 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     nblocks = -(-b.ncol // LD)
     r = ineg['rcpdjac']
 
-    src, name, meta = kmul.mul_source(
-        be, im['A'], LD, im['alpha'], im['beta'], smem_budget=be.smem_budget,
-        rowgroups=be.mul_rowgroups, negdiv_nvars=nv, rk=rk
-    )
+    isz = b.itemsize
+    if be.dense_mul and not rk and kdense.is_dense(im['A'], LD, isz):
+        src, name, meta = kdense.dense_mul_source(
+            be, im['A'], LD, im['alpha'], im['beta'], negdiv_nvars=nv
+        )
+        ngrid = min(-(-nblocks // meta['nb']), be.sm_count)
+    else:
+        src, name, meta = kmul.mul_source(
+            be, im['A'], LD, im['alpha'], im['beta'],
+            smem_budget=be.smem_budget, rowgroups=be.mul_rowgroups,
+            negdiv_nvars=nv, rk=rk
+        )
+        ngrid = min(nblocks, be.sm_count*meta['nctas'])
     fn = be.pointwise._function(src, name)
     fn.set_smem(meta['smem'])
 
@@ -346,8 +356,7 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     args = [('i', nblocks), ('p', b.data), ('l', b.blocksz), ('p', out.data),
             ('l', out.blocksz), ('p', r.data), ('l', r.blocksz)] + rkargs
     k = B200Kernel(
-        be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
-        (meta['nthreads'], 1, 1),
+        be, fn, (ngrid, 1, 1), (meta['nthreads'], 1, 1),
         meta['smem'], args, mats=[b, out, r] + rkmats, misc=[meta],
         traffic=traffic,
         kind='mul+negdivconf+rkvdh2' if rk else 'mul+negdivconf',

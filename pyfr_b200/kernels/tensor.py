@@ -316,6 +316,19 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     # gradient components are interpolated along the line.  Affine
     # elements: G still holds the reference gradient and the (constant)
     # metric is applied to the interpolated values.
+    metric_load = f'''
+        // Constant metric of the {NC} elements this item's columns belong to
+        // (QS was filled by the first threads of the block)
+        fpdtype_t sP[{NC}][NDIMS][NDIMS], rjP[{NC}];
+        UNROLL for (int k = 0; k < {NC}; k++)
+        {{
+            const fpdtype_t *q = QS + (e0 + k)*(NDIMS*NDIMS + 1);
+            UNROLL for (int i = 0; i < NDIMS; i++)
+                UNROLL for (int j = 0; j < NDIMS; j++)
+                    sP[k][i][j] = q[i*NDIMS + j];
+            rjP[k] = q[NDIMS*NDIMS];
+        }}'''
+    late = getattr(be, 'gradflux_metric_late', False)
     p3 = []
     for a in range(nd):
         sb = st['stride'][a]*ROWB
@@ -339,6 +352,10 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                                         for i in range(n1)], '            ')
                 L.append('        }')
 
+            if affine and late:
+                # (the metric is fetched after the interpolation, so that
+                # its registers do not limit the loads in flight above)
+                L.append(metric_load)
             for w, t, lf in (('wm', 'tm', f'lm{a}_{r}'),
                              ('wp', 'tp', f'lp{a}_{r}')):
                 L += [f'        if ({w})', '        {',
@@ -409,23 +426,11 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
 
     # -- metric terms of the work items' columns (affine) ---------------------
     if affine:
-        metric_p3 = f'''
-        // Constant metric of the {NC} elements this thread's columns belong
-        // to (phase 3) -- QS was filled by the first C_SUB threads
-        fpdtype_t sP[{NC}][NDIMS][NDIMS], rjP[{NC}];
-        UNROLL for (int k = 0; k < {NC}; k++)
-        {{
-            const fpdtype_t *q = QS + (e0 + k)*(NDIMS*NDIMS + 1);
-            UNROLL for (int i = 0; i < NDIMS; i++)
-                UNROLL for (int j = 0; j < NDIMS; j++)
-                    sP[k][i][j] = q[i*NDIMS + j];
-            rjP[k] = q[NDIMS*NDIMS];
-        }}
-'''
+        metric_p3 = '' if late else metric_load
         p2 = ''
         p4_xform = 'transform_grad(g, s, rcpdjac_v);'
     else:
-        metric_p3 = ''
+        metric_p3 = '' if late else metric_load
         p2 = f'''
         // ---- phase 2: physical gradient (in place) ---------------------
         for (int item = gtid; item < NPTS*H; item += GT)

@@ -55,6 +55,17 @@ def pytest_terminal_summary(terminalreporter):
     if not PARITY_LOG:
         return
 
+    out = os.path.join(ROOT, 'gpurun_out')
+    try:
+        os.makedirs(out, exist_ok=True)
+        name = 'parity_errors.json'
+        if os.environ.get('PYFR_B200_PARITY_TAG'):
+            name = f'parity_errors_{os.environ["PYFR_B200_PARITY_TAG"]}.json'
+        with open(os.path.join(out, name), 'w') as f:
+            json.dump(PARITY_LOG, f, indent=1)
+    except OSError:
+        pass
+
     tr = terminalreporter
     fp = [r for r in PARITY_LOG if r['err'] == r['err']]
     for r in fp:
@@ -69,22 +80,12 @@ def pytest_terminal_summary(terminalreporter):
                   f'{worst["test"]}')
     if rr:
         w = max(rr, key=lambda r: r['ratio'])
+        own = (f' (oracle fp64 itself {w["ratio_oracle"]:.1f})'
+               if w.get('ratio_oracle') is not None else '')
         tr.write_line(f'point-wise running-error ratio (limit '
                       f'{RUNNING_ERROR_C:g} eps): {len(rr)} comparisons, '
-                      f'largest {w["ratio"]:.1f} (oracle fp64 itself '
-                      f'{w["ratio_oracle"]:.1f}) in {w["test"]}')
+                      f'largest {w["ratio"]:.1f}{own} in {w["test"]}')
     for r in sorted(fp, key=lambda r: -r['err'])[:6]:
         tr.write_line(f'  err {r["err"]:.2e} floor {r["floor"]:.2e} '
                       + (f'ratio {r["ratio"]:.1f} ' if r.get('ratio')
                          is not None else '') + r['test'].split('::')[-1])
-
-    out = os.path.join(ROOT, 'gpurun_out')
-    try:
-        os.makedirs(out, exist_ok=True)
-        name = 'parity_errors.json'
-        if os.environ.get('PYFR_B200_PARITY_TAG'):
-            name = f'parity_errors_{os.environ["PYFR_B200_PARITY_TAG"]}.json'
-        with open(os.path.join(out, name), 'w') as f:
-            json.dump(PARITY_LOG, f, indent=1)
-    except OSError:
-        pass

@@ -45,7 +45,7 @@ def _check(stdout, ngpus):
 def test_reference_arm_single(built):
     res = subprocess.run(
         [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl',
-         'reference', '--steps', '2', '--warmup', '1', '--cpu-n', '4'],
+         'reference', '--steps', '2', '--warmup', '1', '--n', '4'],
         capture_output=True, text=True, timeout=600, cwd=ROOT
     )
     assert res.returncode == 0, res.stderr[-2000:]
@@ -60,7 +60,7 @@ def test_reference_arm_under_torchrun(built):
          '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
          '--master-port', str(_free_port()), os.path.join(ROOT, 'bench.py'),
          '--impl', 'reference', '--gpus', '2', '--steps', '2', '--warmup',
-         '1', '--cpu-n', '4'],
+         '1', '--mesh-n', '4'],
         capture_output=True, text=True, timeout=900, cwd=ROOT,
         env=dict(os.environ, OMP_NUM_THREADS='2')
     )
