@@ -19,9 +19,10 @@ Here:
   columns = 5 warps);
 * a warp owns 32 columns and one group of output rows; per input row it
   reads one value from shared memory and issues one FMA per output row of
-  its group, the coefficient coming straight from the constant bank
-  (``DFMA R, R, c[bank][imm], R``: no literal moves, uniform across the
-  warp) -- 20-30 FMAs per shared-memory load;
+  its group, the coefficients coming from constant memory through uniform
+  registers (one 16-byte uniform load per two FMAs, no literal moves) --
+  20-30 FMAs per shared-memory load -- in a *rolled* loop over the input
+  rows, so the code is a few hundred instructions whatever the operator;
 * the input tiles arrive by TMA bulk copy (one per block and chunk of input
   rows), double buffered on mbarriers, persistent CTAs.
 
@@ -67,9 +68,6 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
     # Row groups: enough warps to fill the SM, at most ~32 accumulators
     R = max(rowgroups, -(-M // 32))
     R = max(1, min(R, M, 32 // NWC))
-    bounds = np.linspace(0, M, R + 1).astype(int)
-    groups = [range(bounds[i], bounds[i + 1]) for i in range(R)]
-    maxrows = max(len(g) for g in groups)
     nthreads = 32*NWC*R
 
     # Chunks of input rows: two tiles of NB blocks within the budget.  A
@@ -85,15 +83,29 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
     BST = KC*LD + pad                         # block stride in the tile
     TILE = NB*BST
 
-    cdecl = (f'__constant__ fpdtype_t KA[{M*K}] = {{'
-             + ', '.join(ph.fpconst(v) for v in A.ravel()) + '};')
+    # Coefficients in constant memory, transposed and padded: KA[k][m],
+    # m padded to R equal row groups of RP rows, so that the RP coefficients
+    # a warp needs for one input row are contiguous (two per 16-byte
+    # uniform load) and the inner loops have fixed trip counts.  The loop
+    # over the input rows stays *rolled*: fully unrolled, the thousands of
+    # FMAs of a dense operator run once per tile and the kernel is bound by
+    # instruction fetch (profiles/r02f: the unrolled form reached 22 % of
+    # the FP64 peak, like the sparse generator it replaced).
+    RP = -(-M // R)
+    RP += RP % 2
+    MP = R*RP
+    AT = np.zeros((K, MP))
+    AT[:, :M] = A.T
+    cdecl = (f'__align__(16) __constant__ fpdtype_t KA[{K*MP}] = {{'
+             + ', '.join(ph.fpconst(v) for v in AT.ravel()) + '};')
+    maxrows = RP
 
     def store(m, val):
-        ix = f'ob + {m*LD}'
+        ix = f'ob + ({m})*LD'
         if negdiv_nvars:
             old = f'out[{ix}] + ' if beta == 1 else (
                 f'{ph.fpconst(beta)}*out[{ix}] + ' if beta else '')
-            return (f'out[{ix}] = -__ldg(rcpdjac + rjb + {m}*C_SUB)*'
+            return (f'out[{ix}] = -__ldg(rcpdjac + rjb + ({m})*C_SUB)*'
                     f'({old}{val});')
         if beta == 0:
             return f'out[{ix}] = {val};'
@@ -102,40 +114,34 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
         else:
             return f'out[{ix}] = fma({ph.fpconst(beta)}, out[{ix}], {val});'
 
-    cases = []
-    for ci, (k0, k1) in enumerate(chunks):
-        first, last = ci == 0, ci == len(chunks) - 1
-        body = []
-        for rg, rows in enumerate(groups):
-            L = []
-            for k in range(k0, k1):
-                L.append(f'{{ const fpdtype_t x = sm[{(k - k0)*LD}];')
-                for j, m in enumerate(rows):
-                    if A[m, k] == 0:
-                        continue
-                    if first and k == k0:
-                        L.append(f'  acc[{j}] = KA[{m*K + k}]*x;')
-                    else:
-                        L.append(f'  acc[{j}] = fma(KA[{m*K + k}], x, '
-                                 f'acc[{j}]);')
-                L.append('}')
-            if first:
-                # rows whose first-column coefficient vanishes
-                z = [f'acc[{j}] = FP(0.0);' for j, m in enumerate(rows)
-                     if A[m, k0] == 0]
-                L = z + L
-            if last:
-                L.append('if (live)')
-                L.append('{')
-                L += ['    ' + store(m, f'acc[{j}]')
-                      for j, m in enumerate(rows)]
-                L.append('}')
-            body.append(f'            case {rg}:\n                '
-                        + '\n                '.join(L)
-                        + '\n                break;')
-        cases.append(f'        case {ci}:\n            switch (rg)\n'
-                     '            {\n' + '\n'.join(body)
-                     + '\n            }\n            break;')
+    body = f'''
+        const int kbeg = chunk*KC;
+        const int kend = (kbeg + KC < {K}) ? kbeg + KC : {K};
+
+        if (chunk == 0)
+        {{
+            UNROLL for (int i = 0; i < RP; i++)
+                acc[i] = FP(0.0);
+        }}
+
+        #pragma unroll 2
+        for (int k = kbeg; k < kend; k++)
+        {{
+            const fpdtype_t x = sm[(k - kbeg)*LD];
+            const fpdtype_t *ka = KA + k*{MP} + m0;
+            UNROLL for (int i = 0; i < RP; i++)
+                acc[i] = fma(ka[i], x, acc[i]);
+        }}
+
+        if (chunk == NCHUNKS - 1 && live)
+        {{
+            UNROLL for (int i = 0; i < RP; i++)
+                if (m0 + i < {M})
+                {{
+                    {store('m0 + i', 'acc[i]')}
+                }}
+        }}
+'''
 
     extra_args = extra_pre = ''
     if negdiv_nvars:
@@ -155,6 +161,7 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
 #define BST {BST}
 #define TILE {TILE}
 #define NTHREADS {nthreads}
+#define RP {RP}
 {_pipeline_src}
 {cdecl}
 
@@ -172,6 +179,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
 
     const int tid = threadIdx.x;
     const int warp = tid / 32, wc = warp % {NWC}, rg = warp / {NWC};
+    const int m0 = rg*RP;
 
     // This thread's column: block jb of the tile, column cc of the block
     const int col = wc*32 + tid % 32;
@@ -226,11 +234,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
         const long long ob = blk*out_bsz + cc;
 {extra_pre}
 
-        switch (chunk)
-        {{
-{chr(10).join(cases)}
-        }}
-
+{body}
         __syncthreads();
     }}
 }}

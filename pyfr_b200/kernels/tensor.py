@@ -430,7 +430,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         p2 = ''
         p4_xform = 'transform_grad(g, s, rcpdjac_v);'
     else:
-        metric_p3 = '' if late else metric_load
+        metric_p3 = ''
         p2 = f'''
         // ---- phase 2: physical gradient (in place) ---------------------
         for (int item = gtid; item < NPTS*H; item += GT)

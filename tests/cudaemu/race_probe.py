@@ -18,8 +18,10 @@ if '--drop-barrier' in sys.argv:
     def _bad(src):
         if 'gradflux(' in src:
             i = src.index('// ---- phase 5')
-            j = src.rindex('__syncthreads();', 0, i)
-            src = src[:j] + src[j + 16:]
+            # (the sum-factorised kernel synchronises through GSYNC())
+            bar = 'GSYNC();' if 'GSYNC();' in src[:i] else '__syncthreads();'
+            j = src.rindex(bar, 0, i)
+            src = src[:j] + src[j + len(bar):]
         return _orig(src)
 
     emu.translate = _bad
@@ -42,7 +44,13 @@ runs = [('tgv', (3, 2, 2), dict(order=2, warp=0.1), {}),
         ('tgv', (3, 2, 2), dict(order=2, warp=0.1),
          {'gradflux-vec2': 'p1,p3,p5', 'conu-pairs': 1,
           'inters-order': 'address'}),
-        ('tgv', 2, dict(order=4), {'gradflux-vec2': 'p1,p3,p5'})]
+        ('tgv', 2, dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}),
+        # the table-driven fused kernel, warp groups, narrow blocks with
+        # two CTAs per SM, fp32 (four columns per access)
+        ('tgv', (3, 2, 2), dict(order=2, warp=0.1), {'gradflux-tensor': 0}),
+        ('tgv', 2, dict(order=4), {'gradflux-groups': 2}),
+        ('tgv', (3, 2, 2), dict(order=3), {'n-soa': 4}),
+        ('tgv', 2, dict(order=2, precision='single'), {})]
 if '--drop-barrier' in sys.argv:
     runs = runs[:1]
 
