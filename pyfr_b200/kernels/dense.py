@@ -91,9 +91,11 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
     # FMAs of a dense operator run once per tile and the kernel is bound by
     # instruction fetch (profiles/r02f: the unrolled form reached 22 % of
     # the FP64 peak, like the sparse generator it replaced).
-    RP = -(-M // R)
-    RP += RP % 2
+    VW = 16 // isz                            # coefficients per load
+    RP = -(-(-(-M // R)) // VW)*VW
     MP = R*RP
+    vt = {2: 'double2', 4: 'float4'}[VW]
+    lanes = 'xyzw'[:VW]
     AT = np.zeros((K, MP))
     AT[:, :M] = A.T
     cdecl = (f'__align__(16) __constant__ fpdtype_t KA[{K*MP}] = {{'
@@ -128,9 +130,14 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
         for (int k = kbeg; k < kend; k++)
         {{
             const fpdtype_t x = sm[(k - kbeg)*LD];
-            const fpdtype_t *ka = KA + k*{MP} + m0;
-            UNROLL for (int i = 0; i < RP; i++)
-                acc[i] = fma(ka[i], x, acc[i]);
+            const {vt} *ka = reinterpret_cast<const {vt} *>(
+                KA + k*{MP} + m0);
+            UNROLL for (int i = 0; i < RP/{VW}; i++)
+            {{
+                const {vt} c = ka[i];
+                {' '.join(f'acc[{VW}*i + {j}] = fma(c.{l}, x, acc[{VW}*i + {j}]);'
+                          for j, l in enumerate(lanes))}
+            }}
         }}
 
         if (chunk == NCHUNKS - 1 && live)
@@ -178,7 +185,12 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
         reinterpret_cast<unsigned long long *>(tiles + 2*TILE);
 
     const int tid = threadIdx.x;
-    const int warp = tid / 32, wc = warp % {NWC}, rg = warp / {NWC};
+    // (taken through a warp broadcast so that the compiler knows the row
+    // group is uniform: the coefficient loads then go through the uniform
+    // datapath, LDCU + FMA with a uniform-register operand, instead of one
+    // per-thread constant load per FMA -- measured 3x slower, r02g)
+    const int warp = __shfl_sync(0xffffffffu, tid / 32, 0);
+    const int wc = warp % {NWC}, rg = warp / {NWC};
     const int m0 = rg*RP;
 
     // This thread's column: block jb of the tile, column cc of the block

@@ -47,6 +47,8 @@ using std::fmin;
 using std::fmax;
 
 template <class T> static inline T __ldg(const T *p) { return *p; }
+// (a warp broadcast of a value every lane already holds)
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 
 // ---- atomics / bit casts -------------------------------------------------------
 static std::mutex emu_atomic_mutex;

@@ -255,19 +255,30 @@ def test_full_size_rhs_matches_c_oracle(built):
     here.  The scale-free statement is the point-wise one: every point lies
     within a modest multiple of ``eps`` times the magnitude of its own terms
     (tests/util.py: rhs_magnitude; both oracles sit at 3-4.4 for every n).
-    Two fp64 evaluations may therefore differ by up to twice that; the
-    assertion is the limit ``RUNNING_ERROR_C`` of the small-mesh tests, on
-    every point of a quarter of the mesh (every fourth element block).  The
-    field-maximum error, the relative L2 error per variable and the bias of
-    the differences are recorded."""
+    Two fp64 evaluations may therefore differ by up to twice that.  At
+    this size a second effect shows: the metric terms are differences of
+    vertex coordinates, exact only to ``eps |x|/h`` (32 eps at the corners
+    of this box), and every term of the RHS is linear in them.  Which
+    rounding one gets depends on how the Jacobian is formed -- the C oracle
+    and the device kernels form it differently -- so against the C oracle
+    the criterion allows for it (tests/util.py: geometry_conditioning),
+    while two *independent device kernels* (the sum-factorised affine
+    kernel and the table-driven general-geometry kernel under the host's
+    interface order), which form the Jacobian alike, must meet the plain
+    limit ``RUNNING_ERROR_C``.  Measured (r02g): 58.9 eps against the C
+    oracle without the allowance, 58.2 for the general kernel against it,
+    5.3 between the two kernels.  Checked on every point of a quarter of
+    the mesh (every fourth element block); the field-maximum error, the
+    relative L2 error per variable and the bias of the differences are
+    recorded."""
     import gc
     import os
 
     from oracle.cbackend import make_cbackend
     from pyfr_b200 import base
     from pyfr_b200.backend import B200Backend
-    from util import (PARITY_LOG, RUNNING_ERROR_C, rhs_magnitude_from_state,
-                      running_error_ratio)
+    from util import (PARITY_LOG, RUNNING_ERROR_C, geometry_conditioning,
+                      rhs_magnitude_from_state, running_error_ratio)
 
     n = 64
     cfg, box = cases.make('tgv', n, order=4)
@@ -294,7 +305,9 @@ def test_full_size_rhs_matches_c_oracle(built):
     # point-wise criterion on every fourth block of eight elements
     eidx = np.flatnonzero((np.arange(n**3)//8) % 4 == 0)
     mag = rhs_magnitude_from_state(cfg, mesh, u0, eidx)
-    ratio = running_error_ratio(out[..., eidx], ref[..., eidx], mag)
+    ratio_raw = running_error_ratio(out[..., eidx], ref[..., eidx], mag)
+    geo = geometry_conditioning(mesh, eidx)
+    ratio = running_error_ratio(out[..., eidx], ref[..., eidx], mag*geo)
 
     d = out - ref
     err = float(np.abs(d).max()/np.abs(ref).max())
@@ -305,6 +318,7 @@ def test_full_size_rhs_matches_c_oracle(built):
     rec = dict(test='full-size 64^3 p=4 vs oracle/crhs',
                err=err, floor=float('nan'), ratio=ratio,
                ratio_oracle=None, l2_momentum_energy=l2,
+               ratio_without_geometry_allowance=ratio_raw,
                bias=bias, npoints_checked=int(mag.size))
     PARITY_LOG.append(rec)
 
@@ -333,6 +347,7 @@ def test_full_size_rhs_matches_c_oracle(built):
         out2[..., eidx], ref[..., eidx], mag)
     rec['ratio_vs_general_kernel'] = running_error_ratio(
         out[..., eidx], out2[..., eidx], mag)
+    assert rec['ratio_vs_general_kernel'] <= RUNNING_ERROR_C
 
     assert ratio <= RUNNING_ERROR_C, ratio
     # (a loose global sanity bound on top: 64^3 sits at ~2.5e-10)

@@ -164,6 +164,23 @@ def rhs_magnitude_from_state(cfg, mesh, u, eidx=None):
     return np.abs(e.rcpdjac_at_np('upts'))[:, None, :]*S
 
 
+def geometry_conditioning(mesh, eidx=None):
+    """``1 + |x|/h`` per element: how much of an element's metric terms is
+    decided by the rounding of its own vertex coordinates.  A linear
+    element's Jacobian is a difference of vertex coordinates (``pyfr/
+    solvers/baseadvec/kernels/smats.mako``); with coordinates of magnitude
+    ``|x|`` and an element of size ``h`` its relative accuracy is ``eps
+    |x|/h`` whatever the evaluation order, and every term of the RHS is
+    linear in it.  Negligible on the small test meshes (|x|/h <= 2), 32 at
+    the corners of the 64^3 box."""
+    (et, spts), = mesh.spts.items()
+    if eidx is not None:
+        spts = spts[:, eidx]
+    xmax = np.abs(spts).max(axis=(0, 2))
+    h = (spts.max(axis=0) - spts.min(axis=0)).min(axis=-1)
+    return 1 + xmax/h
+
+
 def running_error_ratio(out, ref_ext, mag):
     """max over points of ``|out - ext| / (eps * magnitude)``."""
     eps = np.finfo(np.asarray(out).dtype).eps
