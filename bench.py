@@ -595,8 +595,9 @@ def main():
     balg = (5*nu*5 + 5*nf*5 + 3*3*nf*5)*isz/(nu*5)
     rhs_model = {
         'bytes_per_dof_3pass': balg,
-        'achieved_gbs_3pass': value*balg,
-        'frac_of_hbm_3pass': value*balg/peak_gbs,
+        # (per GPU: the whole-job value over the ranks)
+        'achieved_gbs_3pass': value*balg/world,
+        'frac_of_hbm_3pass': value*balg/world/peak_gbs,
         'peak_source': peak_src
     } if args.case == 'tgv' else None
 
