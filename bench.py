@@ -705,6 +705,24 @@ def main():
                 'overhead_vs_rhs_only': tms/(nst*ms_per_step) - 1
             }
 
+            if name == 'rk45_fused_update':
+                # per-kernel event times of one fused stage (graphs of a
+                # key that carries a post-RHS kernel)
+                key = next(k for k in sysm._graphs if len(k) == 3)
+                ks = [k for g in sysm._graphs[key] for w, k in g.plan
+                      if w == 'kernel']
+                ea, eb = (rt.new_ptr(rt.event_create) for _ in range(2))
+                kms = {}
+                for j, k in enumerate(ks):
+                    rt.event_record(ea, be.stream)
+                    for _ in range(3):
+                        k.run(be.stream)
+                    rt.event_record(eb, be.stream)
+                    rt.device_sync()
+                    kms[f'{j}:{getattr(k, "kind", None) or k.fn.name}'] = \
+                        rt.elapsed_ms(ea, eb)/3
+                tstep[name]['stage_kernels_ms'] = kms
+
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

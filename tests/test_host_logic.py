@@ -490,3 +490,147 @@ def test_address_order_of_interface_points(case, n, kw):
         cfg, box = cases.make(case, n, **kw)
         cfg.set('backend-b200', 'inters-order', 'random')
         B200Backend(cfg, dry=True)
+
+
+# -- round 2: kernel-private point order, batched launches, generators ---------
+def _dry_system(case, n, opts={}, vparts=None, rank=0, nparts=1, **kw):
+    from pyfr_b200.backend import B200Backend
+
+    cfg, box = cases.make(case, n, **kw)
+    for k, v in opts.items():
+        cfg.set('backend-b200', k, v)
+    be = B200Backend(cfg, dry=True)
+    comm = type('C', (), dict(rank=rank, size=nparts))()
+    if vparts is not None and callable(vparts):
+        vparts = vparts(box)
+    return be, get_system(be, box.local_mesh(vparts, rank), cfg, 2, comm=comm)
+
+
+def _plan_kernels(sysm):
+    return [k for g in sysm.rhs_graphs(0, 1) for w, k in g.plan
+            if w == 'kernel']
+
+
+def test_interface_kernels_order_their_points_privately():
+    """``kernel-order = address`` (the default): the interface kernels visit
+    their points sorted by left-hand address through *copies* of the index
+    arrays; the views the host built are the same objects with the same
+    contents as under ``kernel-order = host``, so the reference's host code
+    sees no difference."""
+    maps = {}
+    for order in ('host', 'address'):
+        be, sysm = _dry_system('tgv', (4, 3, 3), {'kernel-order': order},
+                               order=2, warp=0.1)
+        conu, = [k for k in _plan_kernels(sysm) if k.kind == 'intconu']
+        v = conu.info['ulin']
+        host = getattr(v, 'orig', getattr(v, 'view', v))
+        maps[order] = (host.mapping.get()[0].copy(),
+                       v.mapping.get()[0].copy(),
+                       conu.info['urin'].mapping.get()[0].copy())
+
+    (h0, k0, r0), (h1, k1, r1) = maps['host'], maps['address']
+    assert np.array_equal(h0, h1)                    # host views untouched
+    assert np.array_equal(h0, k0)                    # 'host': used as is
+    assert not np.all(np.diff(h0) > 0)
+    assert np.all(np.diff(k1) > 0)                   # sorted for the kernel
+    # the same interfaces: (left, right) pairs agree as sets
+    assert set(zip(k0.tolist(), r0.tolist())) == \
+        set(zip(k1.tolist(), r1.tolist()))
+
+
+def test_per_neighbour_kernels_are_batched():
+    """Eight bricks: three neighbours per rank; ``pack``, ``mpiconu`` and
+    ``mpicflux`` go out as at most two launches per kind (one per LDG
+    orientation) instead of one per neighbour."""
+    brick = lambda box: box.brick_partition((2, 2, 2))
+    kinds = {}
+    for batch in (0, 1):
+        be, sysm = _dry_system('tgv', (4, 4, 4), {'batch-launches': batch},
+                               vparts=brick, rank=3, nparts=8, order=2)
+        ks = _plan_kernels(sysm)
+        kinds[batch] = [k.kind or k.fn.name for k in ks]
+        if batch:
+            b = [k for k in ks if k.info and 'batched' in k.info]
+            assert b and all(k.grid[1] == len(k.info['batched']) for k in b)
+            npack = sum(len(k.info['batched']) for k in b
+                        if k.kind == 'pack')
+
+    # (solution: three neighbours; gradients: only to the neighbours this
+    # rank is the sending side of)
+    assert 4 <= kinds[0].count('pack') == npack <= 6
+    assert kinds[0].count('mpicflux') == 3
+    assert kinds[1].count('pack') == 2 and kinds[1].count('mpicflux') <= 2
+    assert kinds[1].count('mpiconu') <= 2 < kinds[0].count('mpiconu')
+
+
+def test_tensor_structure_is_verified_not_assumed():
+    """``tp_structure`` accepts the operators of hexes and quads (and
+    reproduces them from its 1-D factors) and declines everything else."""
+    from pyfr_b200.host.shapes import shape_map
+    from pyfr_b200.kernels.fused import NotFusable
+    from pyfr_b200.kernels.tensor import tp_structure
+
+    def ops(etype, order):
+        cfg, _ = cases.make('tgv' if etype in ('hex', 'pri', 'tet', 'pyr')
+                            else 'vortex', 2, order=order)
+        if etype not in ('hex', 'quad'):
+            cfg, _, _ = cases.mixed_case(
+                'hex+pri+pyr+tet' if etype != 'tri' else 'quad+tri',
+                (4, 4, 4) if etype != 'tri' else (4, 4), order=order)
+        nverts = {'hex': 8, 'quad': 4, 'pri': 6, 'tet': 4, 'pyr': 5,
+                  'tri': 3}[etype]
+        b = shape_map[etype](nverts, cfg)
+        return dict(A1=b.opmat('M4 - M6*M0'), M6=b.opmat('M6'),
+                    M0=b.opmat('M0'), A5=b.opmat('M1 - M3*M2')), b.ndims
+
+    for etype, order in (('hex', 1), ('hex', 2), ('hex', 4), ('quad', 3)):
+        o, nd = ops(etype, order)
+        st = tp_structure(o, nd)
+        assert st['n1'] == order + 1 and st['nlines'] == (order + 1)**(nd - 1)
+        assert all(s == (order + 1)**d for d, s in enumerate(st['stride']))
+
+    for etype in ('pri', 'tet', 'pyr', 'tri'):
+        o, nd = ops(etype, 3 if etype != 'pri' else 2)
+        with pytest.raises(NotFusable):
+            tp_structure(o, nd)
+
+    # a perturbed hex operator (one entry outside the line structure)
+    o, nd = ops('hex', 2)
+    o['A5'] = o['A5'].copy()
+    o['A5'][0, -1] += 1e-6
+    with pytest.raises(NotFusable):
+        tp_structure(o, nd)
+
+
+def test_soa_width_follows_the_order():
+    from pyfr_b200.backend import B200Backend
+
+    want = {(4, 'double'): 8, (5, 'double'): 4, (6, 'single'): 4,
+            (4, 'single'): 16, (2, 'double'): 8}
+    for (order, prec), soa in want.items():
+        cfg, _ = cases.make('tgv', 2, order=order, precision=prec)
+        assert B200Backend(cfg, dry=True).soasz == soa
+
+    cfg, _ = cases.make('tgv', 2, order=6, precision='single')
+    cfg.set('backend-b200', 'n-soa', 16)
+    assert B200Backend(cfg, dry=True).soasz == 16
+
+
+def test_dense_kernel_takes_the_dense_operators_only():
+    from pyfr_b200.kernels.dense import is_dense
+
+    cfg, box, _ = cases.mixed_case('hex+pri+pyr+tet', (4, 4, 4), order=3)
+    from pyfr_b200.backend import B200Backend
+
+    be = B200Backend(cfg, dry=True)
+    sysm = get_system(be, box.local_mesh(), cfg, 2)
+    seen = {}
+    for k in _plan_kernels(sysm):
+        m = k.misc[0] if k.misc and isinstance(k.misc[0], dict) else {}
+        if 'M' in m:
+            seen[m['M'], m['K']] = bool(m.get('dense'))
+
+    # pyramid / tet operators are dense, the hexahedron's are not
+    assert seen[90, 56] and seen[30, 90] and seen[60, 20]
+    assert not seen[96, 64] and not seen[64, 96]
+    assert not is_dense(np.eye(200), 40, 8)
