@@ -19,10 +19,11 @@ Here:
   columns = 5 warps);
 * a warp owns 32 columns and one group of output rows; per input row it
   reads one value from shared memory and issues one FMA per output row of
-  its group, the coefficients coming from constant memory through uniform
-  registers (one 16-byte uniform load per two FMAs, no literal moves) --
-  20-30 FMAs per shared-memory load -- in a *rolled* loop over the input
-  rows, so the code is a few hundred instructions whatever the operator;
+  its group, the coefficients coming from a copy of the operator in shared
+  memory, read at warp-uniform addresses (one broadcast wavefront per two
+  coefficients) -- 20-30 FMAs per data load -- in a *rolled* loop over the
+  input rows, so the code is a few hundred instructions whatever the
+  operator;
 * the input tiles arrive by TMA bulk copy (one per block and chunk of input
   rows), double buffered on mbarriers, persistent CTAs.
 
@@ -98,7 +99,7 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
     lanes = 'xyzw'[:VW]
     AT = np.zeros((K, MP))
     AT[:, :M] = A.T
-    cdecl = (f'__align__(16) __constant__ fpdtype_t KA[{K*MP}] = {{'
+    cdecl = (f'static __device__ __align__(16) const fpdtype_t KA[{K*MP}] = {{'
              + ', '.join(ph.fpconst(v) for v in AT.ravel()) + '};')
     maxrows = RP
 
@@ -131,7 +132,7 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
         {{
             const fpdtype_t x = sm[(k - kbeg)*LD];
             const {vt} *ka = reinterpret_cast<const {vt} *>(
-                KA + k*{MP} + m0);
+                KAs + k*{MP} + m0);
             UNROLL for (int i = 0; i < RP/{VW}; i++)
             {{
                 const {vt} c = ka[i];
@@ -157,7 +158,9 @@ def dense_mul_source(be, A, LD, alpha, beta, negdiv_nvars=None,
         extra_pre = (f'        const long long rjb = blk*rcpdjac_bsz + '
                      f'(cc/(K_SOA*{negdiv_nvars}))*K_SOA + cc % K_SOA;')
 
-    smem = 2*TILE*isz + 16
+    # the operator itself, staged in shared memory once per CTA
+    KAW = -(-K*MP*isz // 16)*16 // isz
+    smem = (2*TILE + KAW)*isz + 16
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz)}
@@ -181,8 +184,16 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *tiles = reinterpret_cast<fpdtype_t *>(smem_raw);
+    fpdtype_t *KAs = tiles + 2*TILE;
     unsigned long long *full =
-        reinterpret_cast<unsigned long long *>(tiles + 2*TILE);
+        reinterpret_cast<unsigned long long *>(KAs + {KAW});
+
+    // The coefficients are read at warp-uniform addresses: from shared
+    // memory that is one broadcast wavefront per 16 bytes.  (From constant
+    // memory the {K*MP*isz//1024} KB operator cycles through the 2 KB first-level
+    // constant cache once per tile: measured 15 % of the FP64 peak, r02j.)
+    for (int i = threadIdx.x; i < {K*MP}; i += NTHREADS)
+        KAs[i] = KA[i];
 
     const int tid = threadIdx.x;
     // (taken through a warp broadcast so that the compiler knows the row

@@ -52,8 +52,8 @@ def translate(src):
     src = src.replace('asm volatile("fence.mbarrier_init.release.cluster;" '
                       '::: "memory");', '')
     src = re.sub(r'extern __shared__[^;]*;', '', src)
-    src = src.replace('static __device__ __align__(16) const int',
-                      'alignas(16) static const int')
+    src = re.sub(r'static __device__ __align__\((\d+)\) const (\w+)',
+                 r'alignas(\1) static const \2', src)
     src = src.replace('#define UNROLL _Pragma("unroll")', '#define UNROLL')
 
     name, wrap = _wrapper(src)

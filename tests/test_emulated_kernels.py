@@ -155,12 +155,16 @@ def test_vectorised_gradflux_device_cases(emulated, case, n, kw, opts):
         assert_parity(out, ref[0], ext[0], 1e-12)
 
 
-@pytest.mark.parametrize('opts', [
-    {}, {'gradflux-vec2': 'p1,p3,p5', 'conu-pairs': 1,
-         'inters-order': 'address'}
-], ids=['default', 'vec2+pairs'])
-def test_fp32_kernels(emulated, opts):
-    n, kw = (3, 2, 2), dict(order=2, warp=0.1)
+@pytest.mark.parametrize('opts,order', [
+    ({}, 2), ({'gradflux-vec2': 'p1,p3,p5', 'conu-pairs': 1,
+               'inters-order': 'address'}, 2),
+    # BASELINE configs[4] proxy: p = 6, SoA width 4 chosen automatically,
+    # the sum-factorised fused kernel (four columns per access)
+    ({}, 6)
+], ids=['default', 'vec2+pairs', 'p6'])
+def test_fp32_kernels(emulated, opts, order):
+    n, kw = (3, 2, 2) if order == 2 else (2, 2, 2), dict(order=order,
+                                                         warp=0.1)
     cfg, box = cases.make('tgv', n, precision='single', **kw)
     sysm = _b200(cfg, box, opts=opts)
     sysm.rhs(0.0, 0, 1)
@@ -172,6 +176,8 @@ def test_fp32_kernels(emulated, opts):
 
     assert out.dtype == np.float32
     assert rel_err(out.astype(float), r64[0]) <= max(4*floor, 1e-5)
+    if order == 6:
+        assert sysm.backend.soasz == 4 and 'gradflux' in _kinds(sysm)
 
 
 @pytest.mark.parametrize('kw,opts,expect', [

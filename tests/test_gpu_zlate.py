@@ -346,14 +346,17 @@ def test_vectorised_gradflux_phases_match_oracle(built, case, n, kw, opts):
         assert_parity(out, ref[0], ext[0], TOL64)
 
 
+# (round 2: the defaults are the sum-factorised fused kernel and the
+# provider-private address order; the report times what they replaced and
+# the measured alternatives of DESIGN.md section 3 beside them)
 VARIANT_REPORT = [
     ('default', []),
-    ('vec2=p3', ['gradflux-vec2=p3']),
-    ('vec2=p1,p3,p5', ['gradflux-vec2=p1,p3,p5']),
-    ('address', ['inters-order=address']),
-    ('address+pairs', ['inters-order=address', 'conu-pairs=1']),
-    ('address+pairs+vec2=p3', ['inters-order=address', 'conu-pairs=1',
-                               'gradflux-vec2=p3']),
+    ('table-driven gradflux', ['gradflux-tensor=0']),
+    ('host order of interface points', ['kernel-order=host']),
+    ('round-1 path', ['gradflux-tensor=0', 'kernel-order=host']),
+    ('general geometry', ['affine-fastpath=0']),
+    ('two warp groups', ['gradflux-groups=2']),
+    ('n-soa=4, two CTAs per SM', ['n-soa=4']),
 ]
 
 
@@ -387,7 +390,7 @@ def test_zz_opt_in_variant_timing_report(built):
             kt = os.path.join(td, 'kt.json')
             cmd = [sys.executable, os.path.join(root, 'bench.py'), '--n', '32',
                    '--steps', '10', '--warmup', '3', '--no-cpu', '--no-e2e',
-                   '--no-clocks', '--kernel-times', kt]
+                   '--no-clocks', '--no-parity', '--kernel-times', kt]
             for o in opts:
                 cmd += ['--opt', o]
 
