@@ -123,9 +123,16 @@ class B200Backend(base.BaseBackend):
             'gradflux-vec2', 'gradflux-planes', 'gradflux-ncol',
             'gradflux-monojac'))
 
-        self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 4)
+        # row groups (= threads) of the sparse operator kernel; 0: four for a
+        # pure stream (out = A b), eight where the kernel also reads `out`
+        # (beta != 0, negdivconf / stage-update epilogues: more loads in
+        # flight -- 0.796 -> 0.641 ms for M3 + negdivconf, while M0 loses
+        # 10 % at eight; r02k)
+        self.mul_rowgroups = cfg.getint(sect, 'mul-rowgroups', 0)
         # dense operators (tets, pyramids) take the small-GEMM kernel
         self.dense_mul = cfg.getbool(sect, 'dense-mul', True)
+        # ... on the FP64 tensor cores (mma.sync m8n8k4) in double precision
+        self.dense_mma = cfg.getbool(sect, 'dense-mma', True)
         # fp64 operators with at least this many distinct coefficients keep
         # them in __constant__ memory (0: always literals)
         self.mul_const_table = cfg.getint(sect, 'mul-const-table', 0)

@@ -335,14 +335,15 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
 
     isz = b.itemsize
     if be.dense_mul and not rk and kdense.is_dense(im['A'], LD, isz):
-        src, name, meta = kdense.dense_mul_source(
-            be, im['A'], LD, im['alpha'], im['beta'], negdiv_nvars=nv
-        )
+        gen = (kdense.dense_mma_source if be.dense_mma and isz == 8
+               else kdense.dense_mul_source)
+        src, name, meta = gen(be, im['A'], LD, im['alpha'], im['beta'],
+                              negdiv_nvars=nv)
         ngrid = min(-(-nblocks // meta['nb']), be.sm_count)
     else:
         src, name, meta = kmul.mul_source(
             be, im['A'], LD, im['alpha'], im['beta'],
-            smem_budget=be.smem_budget, rowgroups=be.mul_rowgroups,
+            smem_budget=be.smem_budget, rowgroups=be.mul_rowgroups or 8,
             negdiv_nvars=nv, rk=rk
         )
         ngrid = min(nblocks, be.sm_count*meta['nctas'])

@@ -88,6 +88,19 @@ __device__ __forceinline__ void flag_wait(int *f)
     } while (!v);
 }
 
+// FP64 tensor-core product of an 8x4 by a 4x8 fragment, accumulated into
+// this lane's two entries of the 8x8 result (lane = 4*g + t: a = A[g][t],
+// b = B[t][g], c0/c1 = C[g][2t], C[g][2t + 1])
+__device__ __forceinline__ void mma_m8n8k4(fpdtype_t &c0, fpdtype_t &c1,
+                                           fpdtype_t a, fpdtype_t b)
+{
+#if PYFR_B200_FP64
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 "
+                 "{%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
+}
+
 // One TMA bulk copy global -> shared, completion signalled on an mbarrier
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src,
                                             unsigned bytes,

@@ -21,6 +21,7 @@ def prologue(fpdtype, ixdtype, soasz, csubsz, defines=()):
         f'typedef {fp} fpdtype_t;',
         f'typedef {ix} ixdtype_t;',
         f'typedef {fp}2 fpdtype2_t;',
+        f'#define PYFR_B200_FP64 {int(fp == "double")}',
         f'#define K_SOA {soasz}',
         f'#define C_SUB {csubsz}',
         *[f'#define {k} {v}' for k, v in defines],

@@ -128,6 +128,29 @@ static inline void flag_wait(int *f)
         std::this_thread::yield();
 }
 
+// ---- warp-level matrix product (mma.sync m8n8k4, FP64) --------------------------
+// Every thread of the CTA must take part the same number of times (the
+// kernels that use it have uniform control flow): fragments are parked in
+// a CTA-wide scratch array between two barriers.
+static double emu_mma_a[1024], emu_mma_b[1024];
+
+template <class T>
+static inline void mma_m8n8k4(T &c0, T &c1, T a, T b)
+{
+    const unsigned tid = threadIdx.x, w0 = tid & ~31u, lane = tid & 31u;
+    emu_mma_a[tid] = a;
+    emu_mma_b[tid] = b;
+    emu_cta_barrier.wait();
+    const unsigned g = lane >> 2, t = lane & 3u;
+    for (unsigned k = 0; k < 4; k++)
+    {
+        // A[g][k] sits in lane 4g + k, B[k][n] in lane 4n + k
+        c0 += (T) (emu_mma_a[w0 + 4*g + k]*emu_mma_b[w0 + 4*(2*t) + k]);
+        c1 += (T) (emu_mma_a[w0 + 4*g + k]*emu_mma_b[w0 + 4*(2*t + 1) + k]);
+    }
+    emu_cta_barrier.wait();
+}
+
 // ---- mbarrier + TMA bulk copy ---------------------------------------------------
 // The 8-byte shared-memory slot holds {completed phases, pending bytes}
 struct EmuMbar { std::atomic<unsigned> completed; std::atomic<unsigned> pending; };

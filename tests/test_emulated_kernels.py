@@ -342,12 +342,18 @@ def test_bench_script_end_to_end(emulated, monkeypatch, capsys):
     monkeypatch.setattr(emu.EmuRuntime, 'elapsed_ms', lambda s, a, b: 1.0)
     monkeypatch.setattr(sys, 'argv', [
         'bench.py', '--n', '2', '--order', '2', '--steps', '3', '--warmup',
-        '1', '--no-cpu', '--no-clocks', '--no-graphs'
+        '1', '--no-cpu', '--no-clocks', '--no-graphs', '--timestep'
     ])
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runpy.run_path(os.path.join(root, 'bench.py'), run_name='__main__')
 
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+
+    # the partitioned-oracle check that precedes the timing, and the whole
+    # time steps timed after it
+    assert line['parity']['nranks'] == 1 and line['parity']['err'] < 1e-11
+    assert set(line['time_step']) == {'rk4', 'rk45', 'rk45_fused_update'}
+    assert 'stage_kernels_ms' in line['time_step']['rk45_fused_update']
 
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup',
                 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
