@@ -339,7 +339,7 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
                else kdense.dense_mul_source)
         src, name, meta = gen(be, im['A'], LD, im['alpha'], im['beta'],
                               negdiv_nvars=nv)
-        ngrid = min(-(-nblocks // meta['nb']), be.sm_count)
+        ngrid = min(-(-nblocks // meta['nb']), be.sm_count*meta['nctas'])
     else:
         src, name, meta = kmul.mul_source(
             be, im['A'], LD, im['alpha'], im['beta'],

@@ -347,6 +347,8 @@ def dense_mma_source(be, A, LD, alpha, beta, negdiv_nvars=None,
                       'long long rcpdjac_bsz')
 
     smem = (2*TILE + MP*KP)*isz + 16
+    # two CTAs per SM where the tiles are small (few row groups)
+    nctas = 2 if (2*(smem + 1024) <= 227*1024 and 2*nthreads <= 768) else 1
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz)}
@@ -367,7 +369,7 @@ def dense_mma_source(be, A, LD, alpha, beta, negdiv_nvars=None,
 // out[{M} x LD] = A[{M} x {K}] @ b[{K} x LD] per element block on the FP64
 // tensor cores; tiles of {NB} blocks = {TC} columns = {NWC} warps x {R} row
 // group(s) of {MW} rows, {nchunks} chunk(s) of {KC} input rows
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1)
+extern "C" __global__ void __launch_bounds__(NTHREADS, {nctas})
 opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
       fpdtype_t* __restrict__ out, long long out_bsz{extra_args})
 {{
@@ -497,7 +499,7 @@ opmul(int nblocks, const fpdtype_t* __restrict__ b, long long b_bsz,
     }}
 }}
 '''
-    meta = dict(nthreads=nthreads, nctas=1, smem=smem,
+    meta = dict(nthreads=nthreads, nctas=nctas, smem=smem,
                 nnz=int(np.count_nonzero(A)), nchunks=nchunks, crows=KC,
                 M=M, K=K, dense=True, mma=True, nb=NB)
 

@@ -31,6 +31,13 @@ def prologue(fpdtype, ixdtype, soasz, csubsz, defines=()):
         ' + (e) % K_SOA)',
         '#define FP(x) ((fpdtype_t) (x))',
         '#define UNROLL _Pragma("unroll")',
+        '// optimisation barrier: the value is re-formed where it is used',
+        '#define OPAQUE(x) asm volatile("" : "+r"(x))',
+        '#ifdef __CUDACC__',
+        '#define OPAQUE64(x) asm volatile("" : "+l"(x))',
+        '#else',
+        '#define OPAQUE64(x) asm volatile("" : "+r"(x))',
+        '#endif',
         ''
     ]
 

@@ -244,31 +244,56 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     if rowcls is not None and max(rowcls) < 16:
         cls = [int(c) for c in rowcls]
         fm_arg = ',\n         const int* __restrict__ fmask'
-        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + blk);'
+        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + bq);'
     else:
         cls, fm_arg, fm_load = None, '', ''
 
+    # Packed: {first solution-point row | row of the '-' flux point << 16,
+    # row of the '+' flux point | need classes of the two << 16, 24}.  A
+    # thread keeps two words per work item for the whole launch; row
+    # offsets and write masks are re-formed from them inside each phase
+    # (a few integer operations) behind an optimisation barrier.  Without
+    # it the compiler hoists the nine offsets and six class masks of a
+    # thread out of the block loop and, at 128 registers, spills them:
+    # their reloads sat on the critical path of every work item (ncu
+    # r02c: 6.5 % of the kernel's stall samples on those ``LDL``).
     tab = []
     for d in range(nd):
         for b, fmn, fpl in zip(st['base'][d], st['fm'][d], st['fp'][d]):
-            tab += [b*ROWB, fmn*ROWB | (cls[fmn] if cls else 0),
-                    fpl*ROWB | (cls[fpl] if cls else 0), 0]
-    tabsrc = (f'static __device__ __align__(16) const int g_lines[{len(tab)}]'
-              f' = {{{", ".join(map(str, tab))}}};')
+            tab += [b | fmn << 16,
+                    fpl | ((cls[fmn] | cls[fpl] << 8) << 16 if cls else 0)]
+    tabsrc = (f'static __device__ __align__(8) const unsigned '
+              f'g_lines[{len(tab)}] = {{{", ".join(map(str, tab))}}};')
 
     desc = []
     for d in range(nd):
         for r in range(R):
             desc.append(f'''
-    int lb{d}_{r} = 0, lm{d}_{r} = 0, lp{d}_{r} = 0;
+    unsigned dx{d}_{r} = 0, dy{d}_{r} = 0;
     const bool on{d}_{r} = lg + {r*NLG} < NLINES && lg < NLG;
     if (on{d}_{r})
     {{
-        const int4 q = *reinterpret_cast<const int4 *>(
-            g_lines + {4*d*nl} + 4*(lg + {r*NLG}));
-        lb{d}_{r} = q.x + cb; lm{d}_{r} = q.y; lp{d}_{r} = q.z;
+        dx{d}_{r} = g_lines[{2*d*nl} + 2*(lg + {r*NLG})];
+        dy{d}_{r} = g_lines[{2*d*nl} + 2*(lg + {r*NLG}) + 1];
     }}''')
     desc = ''.join(desc)
+
+    def unpack(d, r, ends=False, masks=False):
+        """Row offsets (bytes, this item's columns included) of work item
+        ``(d, r)``: ``lb`` first solution point, ``lm``/``lp`` its flux
+        points; ``wm``/``wp`` whether those rows are needed."""
+        L = [f'    unsigned qx = dx{d}_{r}, qy = dy{d}_{r};',
+             '    OPAQUE(qx); OPAQUE(qy);',
+             '    const int lb = (int) (qx & 0xffffu)*ROWB + cb;']
+        if ends:
+            L += ['    const int lm = (int) (qx >> 16)*ROWB + cb, '
+                  'lp = (int) (qy & 0xffffu)*ROWB + cb;']
+        if masks and cls:
+            L += ['    const bool wm = (fm >> ((qy >> 16) & 0xffu)) & 1u, '
+                  'wp = (fm >> (qy >> 24)) & 1u;']
+        elif masks:
+            L += ['    const bool wm = true, wp = true;']
+        return L
 
     ld = lambda arr, off: (f'*reinterpret_cast<const fpvec_t *>({arr} + '
                            f'{off})')
@@ -292,20 +317,18 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     for d in range(nd):
         sb = st['stride'][d]*ROWB
         for r in range(R):
-            L = [f'if (on{d}_{r})', '{']
+            L = [f'if (on{d}_{r})', '{'] + unpack(d, r, ends=True)
             for i in range(n1):
                 L.append(f'    const fpvec_t x{i} = '
-                         f'{ld("Ub", f"lb{d}_{r} + {i*sb}")};')
-            L.append(f'    const fpvec_t cm = '
-                     f'{ld("Cb", f"(lm{d}_{r} & ~15) + cb")};')
-            L.append(f'    const fpvec_t cp = '
-                     f'{ld("Cb", f"(lp{d}_{r} & ~15) + cb")};')
+                         f'{ld("Ub", f"lb + {i*sb}")};')
+            L.append(f'    const fpvec_t cm = {ld("Cb", "lm")};')
+            L.append(f'    const fpvec_t cp = {ld("Cb", "lp")};')
             L.append('    fpvec_t o;')
             for i in range(n1):
                 terms = [(st['Dg'][d][i, j], f'x{j}') for j in range(n1)]
                 terms += [(st['Lg'][d][i, 0], 'cm'), (st['Lg'][d][i, 1], 'cp')]
                 L += lincomb('o', terms, '    ')
-                L.append(f'    {stv("Gb", f"{d*nu*ROWB + i*sb} + lb{d}_{r}")}'
+                L.append(f'    {stv("Gb", f"{d*nu*ROWB + i*sb} + lb")}'
                          ' = o;')
             L.append('}')
             p1.append('\n        '.join(L))
@@ -333,19 +356,15 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     for a in range(nd):
         sb = st['stride'][a]*ROWB
         for r in range(R):
-            L = [f'if (on{a}_{r})', '{']
-            if cls:
-                L += [f'    const bool wm = fm & (1u << (lm{a}_{r} & 15)), '
-                      f'wp = fm & (1u << (lp{a}_{r} & 15));']
-            else:
-                L += ['    const bool wm = true, wp = true;']
+            L = ([f'if (on{a}_{r})', '{'] +
+                 unpack(a, r, ends=True, masks=True))
             L += ['    if (wm | wp)', '    {']
             for d in range(nd):
                 L.append(f'        fpvec_t tm{d}, tp{d};')
                 L.append('        {')
                 for i in range(n1):
                     L.append(f'            const fpvec_t g{i} = '
-                             f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                             f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
                 L += lincomb(f'tm{d}', [(st['lm'][a][i], f'g{i}')
                                         for i in range(n1)], '            ')
                 L += lincomb(f'tp{d}', [(st['lp'][a][i], f'g{i}')
@@ -356,10 +375,9 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                 # (the metric is fetched after the interpolation, so that
                 # its registers do not limit the loads in flight above)
                 L.append(metric_load)
-            for w, t, lf in (('wm', 'tm', f'lm{a}_{r}'),
-                             ('wp', 'tp', f'lp{a}_{r}')):
+            for w, t, lf in (('wm', 'tm', 'lm'), ('wp', 'tp', 'lp')):
                 L += [f'        if ({w})', '        {',
-                      f'            char *vo = vfp + ({lf} & ~15) + cb;']
+                      f'            char *vo = vfp + {lf};']
                 for dp in range(nd):
                     if affine:
                         L.append('            { fpvec_t o;')
@@ -387,15 +405,15 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     for a in range(nd - 1):
         sb = st['stride'][a]*ROWB
         for r in range(R):
-            L = [f'if (on{a}_{r})', '{']
+            L = [f'if (on{a}_{r})', '{'] + unpack(a, r)
             for i in range(n1):
                 L.append(f'    const fpvec_t x{i} = '
-                         f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                         f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb")};')
             L.append('    fpvec_t o;')
             for i in range(n1):
                 L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
                                    for j in range(n1)], '    ')
-                L.append(f'    {stv("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")}'
+                L.append(f'    {stv("Gb", f"{a*nu*ROWB + i*sb} + lb")}'
                          ' = o;')
             L.append('}')
             p5a.append('\n        '.join(L))
@@ -406,20 +424,20 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     sb = st['stride'][a]*ROWB
     p5b = []
     for r in range(R):
-        L = [f'if (on{a}_{r})', '{']
+        L = [f'if (on{a}_{r})', '{'] + unpack(a, r)
         for i in range(n1):
             L.append(f'    const fpvec_t x{i} = '
-                     f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                     f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb")};')
         L.append('    fpvec_t o;')
         for i in range(n1):
             L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
                                for j in range(n1)], '    ')
             for d in range(nd - 1):
                 L.append(f'    {{ const fpvec_t y = '
-                         f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb{a}_{r}")};')
+                         f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
                 L.append('      ' + ' '.join(f'o.{k} += y.{k};'
                                              for k in comps) + ' }')
-            L.append(f'    {stv("fop", f"{i*sb} + lb{a}_{r}")} = o;')
+            L.append(f'    {stv("fop", f"{i*sb} + lb")} = o;')
         L.append('}')
         p5b.append('\n        '.join(L))
     p5b = '\n        '.join(p5b)
@@ -436,7 +454,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         for (int item = gtid; item < NPTS*H; item += GT)
         {{
             const int e = grp*H + item % H, p = item / H;
-            if (blk*C_SUB + e >= neles)
+            if (bq*C_SUB + e >= neles)
                 continue;
 {geom}
             fpdtype_t g[NDIMS][NVARS];
@@ -573,9 +591,13 @@ gradflux(int nblocks, int neles,
 {hold}
     for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
     {{
-        const long long nxt = blk + gridDim.x;
-        char *vfp = reinterpret_cast<char *>(vf + blk*vf_bsz);
-        char *fop = reinterpret_cast<char *>(fout + blk*fout_bsz);
+        // (block pointers are formed from the block number every time:
+        // kept as induction variables they cost a dozen registers)
+        long long bq = blk;
+        OPAQUE64(bq);
+        const long long nxt = bq + gridDim.x;
+        char *vfp = reinterpret_cast<char *>(vf + bq*vf_bsz);
+        char *fop = reinterpret_cast<char *>(fout + bq*fout_bsz);
 
         mbar_wait(&bars[0], it & 1);
         {geo['geo_blk']}
@@ -619,7 +641,7 @@ gradflux(int nblocks, int neles,
         {{
             const int item = gtid + r*GT;
             const int e = grp*H + item % H, p = item / H;
-            if (item < NPTS*H && blk*C_SUB + e < neles)
+            if (item < NPTS*H && bq*C_SUB + e < neles)
             {{
 {geom}
                 fpdtype_t g[NDIMS][NVARS];
