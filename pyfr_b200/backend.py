@@ -146,6 +146,9 @@ class B200Backend(base.BaseBackend):
         # phase after which the second group starts (1 or 3)
         self.gradflux_groups = cfg.getint(sect, 'gradflux-groups', 1)
         self.gradflux_stagger = cfg.getint(sect, 'gradflux-stagger', 1)
+        # loads of the next work item written ahead of the arithmetic of
+        # the current one in the line phases (tensor-product kernel)
+        self.gradflux_swp = cfg.getbool(sect, 'gradflux-swp', True)
         # fetch the constant metric of a flux-point work item after its
         # interpolation (fewer live registers, three fetches per block)
         self.gradflux_metric_late = cfg.getbool(sect, 'gradflux-metric-late',
@@ -189,6 +192,15 @@ class B200Backend(base.BaseBackend):
         self.view_uses = []
         self._ordered = {}
         self.dead_rows = cfg.getbool(sect, 'dead-rows', True)
+        # interior common solution (|ldg-beta| = 1/2) gathered by the
+        # element kernel: no intconu launch (fusion.conu_fold_plan)
+        self.conu_fold = cfg.getbool(sect, 'conu-fold', True)
+        # element kernel on half blocks, two CTAs per SM, where a whole
+        # block fills the shared memory (tensor-product kernel)
+        # (measured a loss with per-thread copies in place of the bulk
+        # copy: 0.275 -> 0.281 ms at 32^3, r02n; off)
+        self.gradflux_split = cfg.getbool(sect, 'gradflux-split', False)
+        self.last_committed = None
 
         # Compute stream, communication stream and fork/join events
         self.stream = rt.new_ptr(rt.stream_create)

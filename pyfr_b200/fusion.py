@@ -133,6 +133,100 @@ def region_is_affine(verts, tol=1e-12):
     return True
 
 
+
+def conu_fold_plan(be, C):
+    """Can the interior ``intconu`` that stores the common solution into
+    ``C`` (the first ``nfpts`` rows of an element type's ``vect_fpts``,
+    ``pyfr/solvers/baseadvecdiff/elements.py:42-46``) be folded into the
+    element kernel that consumes it?
+
+    With |ldg-beta| = 1/2 the common solution at an interior flux point is
+    the trace of one of the two sides (``navstokes/kernels/intconu.mako``):
+    nothing is computed, a value is moved.  The element kernel can fetch it
+    from where ``disu`` left it -- the neighbour's (or its own) entry of
+    ``scal_fpts`` -- while it stages its block, which saves the ``intconu``
+    launch and its read and write of the flux-point array.  The rewrite
+    reaches back into the graph committed just before the present one
+    (``disu``, ``intconu``, packs; the reference's ``g1`` of
+    ``baseadvecdiff/system.py:64-92``), which must not have run yet.
+
+    Returns ``None`` or a dict with the graph, the kernel to drop, the
+    trace matrix and the per-block gather indices (``-1``: the common value
+    has been stored into ``C`` by a boundary or partition-boundary
+    kernel)."""
+    if not getattr(be, 'conu_fold', True):
+        return None
+
+    g = be.last_committed() if getattr(be, 'last_committed', None) else None
+    if g is None or getattr(g, 'started', False):
+        return None
+
+    # On a partitioned mesh intconu is what the exchange of the traces
+    # (issued by the same graph) overlaps with: it stays
+    if any(w == 'xchg' for w, o in g.program):
+        return None
+
+    ks = [k for w, k in g.program
+          if w == 'kernel' and getattr(k, 'kind', None) == 'intconu']
+    if len(ks) != 1 or not ks[0].info.get('both'):
+        return None
+
+    k = ks[0]
+    i = k.info
+    beta = i['tplargs']['c']['ldg-beta']
+    if abs(beta) != 0.5:
+        return None
+
+    VF = _root(C)
+    nf, LD, isz = C.nrow, C.leaddim, C.itemsize
+    csub, soa, nv = be.csubsz, be.soasz, i['tplargs']['nvars']
+    views = [i[n] for n in ('ulin', 'urin', 'ulout', 'urout')]
+
+    if any(v.nvrow != 1 or v.nvcol != nv or len(v._mats) != 1
+           for v in views):
+        return None
+
+    S = views[0]._mats[0]
+    if (_root(S) is not S or views[1]._mats[0] is not S or S.nrow != nf or
+        S.leaddim != LD or S.nblocks != VF.nblocks or
+        any(_root(v._mats[0]) is not VF or _rows_of(v._mats[0])[1] != 0
+            for v in views[2:])):
+        return None
+
+    nblocks = VF.nblocks
+    if S.blocksz*nblocks >= 2**31:
+        return None
+
+    src = (views[1] if beta > 0 else views[0]).mapping.get()[0]
+    src = src.astype(np.int64) - S.offset // isz
+    if len(src) and (src.min() < 0 or src.max() >= S.blocksz*nblocks):
+        return None
+
+    gidx = np.full((nblocks, nf*csub), -1, dtype=np.int32)
+    for v in views[2:]:
+        d = v.mapping.get()[0].astype(np.int64) - VF.offset // isz
+        blk, rem = np.divmod(d, VF.blocksz)
+        row, col = np.divmod(rem, LD)
+        e = (col // (soa*nv))*soa + col % soa
+
+        if len(d) and (d.min() < 0 or blk.max() >= nblocks or
+                       row.max() >= nf or np.any(col % (soa*nv) >= soa) or
+                       np.any(gidx[blk, row*csub + e] != -1)):
+            return None
+
+        gidx[blk, row*csub + e] = src
+
+    return dict(graph=g, kernel=k, sfp=S, gidx=gidx)
+
+
+def apply_conu_fold(plan):
+    """Drops the folded ``intconu`` from the graph that held it."""
+    g, k = plan['graph'], plan['kernel']
+    g.program = [(w, o) for w, o in g.program if o is not k]
+    g._plan()
+    g.folded = getattr(g, 'folded', []) + [k]
+
+
 def fuse_gradflux(be, kerns, subs):
     """tgradpcoru .. tdivtpcorf of one element type -> ``gradflux``."""
     from pyfr_b200.providers import B200Kernel
@@ -189,6 +283,11 @@ def fuse_gradflux(be, kerns, subs):
     ops = dict(A1=i0['A'], M6=i1['A'], M0=M0, A5=i5['A'])
     out = []
 
+    # The common solution gathered by the element kernel itself (all
+    # regions of the element type or none)
+    fold = conu_fold_plan(be, C) if be.gradflux_tensor else None
+    fold_gidx = None
+
     # Dead-store elimination on vect_fpts
     rneed = row_need_classes(be, VF, nf, VF.nblocks) if be.dead_rows else None
 
@@ -217,11 +316,20 @@ def fuse_gradflux(be, kerns, subs):
             try:
                 src, name, meta = ktensor.gradflux_tp_source(
                     be, ops, ti['tplargs'], pts, LD,
-                    rowcls=None if rneed is None else rneed[0], affine=affine
+                    rowcls=None if rneed is None else rneed[0], affine=affine,
+                    gather=fold is not None
                 )
             except kfused.NotFusable:
                 src = None
         if src is None:
+            if fold is not None:
+                # (the table-driven kernel has no gather form: start over
+                # without the fold)
+                be.conu_fold, keep = False, be.conu_fold
+                try:
+                    return fuse_gradflux(be, kerns, subs)
+                finally:
+                    be.conu_fold = keep
             src, name, meta = kfused.gradflux_source(
                 be, ops, ti['tplargs'], pts, LD,
                 rowcls=None if rneed is None else rneed[0], affine=affine
@@ -247,6 +355,17 @@ def fuse_gradflux(be, kerns, subs):
             geo = [s, r]
 
         words = meta['words_per_block']*nblocks
+        if fold is not None:
+            if fold_gidx is None:
+                fold_gidx = be.const_matrix(fold['gidx'].reshape(1, -1),
+                                            dtype=np.int32, tags={'noblock'})
+            ngp = meta['gather_points']
+            gargs = [('p', fold_gidx.data + b0*ngp*4),
+                     ('p', fold['sfp'].data)]
+            # (+ the index table, one 32-bit word per point)
+            words += nblocks*ngp*4 // isz
+        else:
+            gargs = []
         if rneed is not None:
             fm = be.const_matrix(rneed[1][None, b0:b0 + nblocks],
                                  dtype=np.int32, tags={'noblock'})
@@ -259,14 +378,25 @@ def fuse_gradflux(be, kerns, subs):
                        int((cls == c).sum()) for c in range(cls.max() + 1))
             words -= nd*(nf*nblocks - live)*LD
 
+        args += gargs
+        if fold is not None:
+            geo = geo + [fold_gidx, fold['sfp']]
+
+        # (a kernel working on half blocks walks twice as many)
+        ngrid = min(nblocks*meta.get('split', 1), be.sm_count*meta['nctas'])
         out.append(B200Kernel(
-            be, fn, (min(nblocks, be.sm_count*meta['nctas']), 1, 1),
+            be, fn, (ngrid, 1, 1),
             (meta['nthreads'], 1, 1), meta['smem'], args,
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
             traffic=words*isz, kind='gradflux',
             info=dict(replaces=kerns, dead_rows=rneed is not None,
-                      affine=affine, tensor=bool(meta.get('tensor')))
+                      affine=affine, tensor=bool(meta.get('tensor')),
+                      gather=fold is not None, split=meta.get('split', 1),
+                      gidx=fold_gidx)
         ))
+
+    if fold is not None:
+        apply_conu_fold(fold)
 
     return out
 
@@ -503,19 +633,38 @@ def elide_copy_fpts(be, program):
     conus = [k for k in kerns if getattr(k, 'kind', None) in
              ('intconu', 'mpiconu')]
 
-    if len(copies) != 1 or not conus:
+    if not copies or not conus:
         return program
 
-    cp = copies[0]
-    dst, src = cp.info['dst'], cp.info['src']
-
-    if any(kerns.index(k) < kerns.index(cp) for k in conus):
+    # One copy per element type (mixed meshes: several); the interface
+    # views span all of them
+    pairs = [(cp.info['dst'], cp.info['src']) for cp in copies]
+    base_d = {int(d.basedata) for d, s in pairs}
+    base_s = {int(s.basedata) for d, s in pairs}
+    if len(base_d) != 1 or len(base_s) != 1:
         return program
 
-    def where(view, mat):
-        # (block, offset in block) of every view point inside ``mat``
-        m = view.mapping.get()[0].astype(np.int64) - mat.offset//mat.itemsize
-        return m // mat.blocksz, m % mat.blocksz
+    if any(kerns.index(k) < kerns.index(cp) for k in conus for cp in copies):
+        return program
+
+    def span(m):
+        lo = m.offset // m.itemsize
+        return lo, lo + (m.nblocks - 1)*m.blocksz + m.nrow*m.leaddim
+
+    dspan = [span(d) for d, s in pairs]
+    sspan = [span(s) for d, s in pairs]
+
+    def locate(mp, spans, mats):
+        """(matrix number, block, offset in block) of view points"""
+        mp = mp.astype(np.int64)
+        which = np.full(len(mp), -1)
+        blk, off = np.zeros_like(mp), np.zeros_like(mp)
+        for j, ((lo, hi), m) in enumerate(zip(spans, mats)):
+            sel = (mp >= lo) & (mp < hi)
+            which[sel] = j
+            blk[sel] = (mp[sel] - lo) // m.blocksz
+            off[sel] = (mp[sel] - lo) % m.blocksz
+        return which, blk, off
 
     # Coverage: interior kernels touch 2n points, partition-boundary ones n
     npts = 0
@@ -529,12 +678,16 @@ def elide_copy_fpts(be, program):
             vin, vout = getattr(vin, 'view', vin), getattr(vout, 'view', vout)
 
             # The trace and the common solution must be addressed alike
-            if (int(vout.basedata) != int(dst.basedata) or
-                int(vin.basedata) != int(src.basedata)):
+            if (int(vout.basedata) not in base_d or
+                int(vin.basedata) not in base_s):
                 return program
 
-            (bi, oi), (bo, oo) = where(vin, src), where(vout, dst)
-            if not (np.array_equal(bi, bo) and np.array_equal(oi, oo)):
+            wi, bi, oi = locate(vin.mapping.get()[0], sspan,
+                                [s for d, s in pairs])
+            wo, bo, oo = locate(vout.mapping.get()[0], dspan,
+                                [d for d, s in pairs])
+            if not (np.all(wi >= 0) and np.array_equal(wi, wo) and
+                    np.array_equal(bi, bo) and np.array_equal(oi, oo)):
                 return program
 
             npts += vin.n
@@ -543,26 +696,34 @@ def elide_copy_fpts(be, program):
     # write their output for every beta (navstokes/kernels/mpiconu.mako)
     # but run in a later graph, after the halo has arrived: count the
     # points of every other view the backend has bound for *writing* into
-    # the common-solution buffer
+    # the common-solution buffers
     here = {id(getattr(v, 'view', v)) for k in conus
             for v in (k.info['ulout'], k.info['urout']) if v is not None}
-    lo = dst.offset // dst.itemsize
-    hi = lo + (dst.nblocks - 1)*dst.blocksz + dst.nrow*dst.leaddim
     seen = set()
     for v, mode in be.view_uses:
         if mode != 'w' or id(v) in here or id(v) in seen or \
-           int(v.basedata) != int(dst.basedata):
+           int(v.basedata) not in base_d:
             continue
         seen.add(id(v))
 
-        m = v.mapping.get()[0]
-        if v.n and (m.min() < lo or m.max() >= hi):
-            return program
+        if v.n:
+            w, _, _ = locate(v.mapping.get()[0], dspan, [d for d, s in pairs])
+            # (views into other buffers of the same allocation -- the
+            # common fluxes in scal_fpts -- are not ours to count)
+            if np.all(w < 0):
+                continue
+            if np.any(w < 0):
+                return program
 
         npts += v.n
 
-    nele = src.ioshape[-1] if hasattr(src, 'ioshape') else None
-    if nele is None or npts != src.nrow*nele:
+    total = 0
+    for d, s in pairs:
+        nele = s.ioshape[-1] if hasattr(s, 'ioshape') else None
+        if nele is None:
+            return program
+        total += s.nrow*nele
+    if npts != total:
         return program
 
     # Regenerate intconu with both-side stores
@@ -576,7 +737,7 @@ def elide_copy_fpts(be, program):
 
     out = []
     for w, k in program:
-        if k is cp:
+        if any(k is cp for cp in copies):
             continue
         out.append((w, repl.get(k, k)))
 

@@ -576,16 +576,22 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False, who=None):
             fpdtype_t jm[NDIMS][NDIMS], sm[NDIMS][NDIMS], djac;
             ''' + '\n            '.join(jl) + r'''
             smats_detj_from_jac(jm, sm, djac);
+            // (second copy: the metric scaled by 1/|J|, as the
+            // flux-point gradients use it)
+            const fpdtype_t rj = FP(1.0)/djac;
             UNROLL for (int i = 0; i < NDIMS; i++)
                 UNROLL for (int j = 0; j < NDIMS; j++)
-                    QS[ea*(NDIMS*NDIMS + 1) + i*NDIMS + j] = sm[i][j];
-            QS[ea*(NDIMS*NDIMS + 1) + NDIMS*NDIMS] = FP(1.0)/djac;
+                {
+                    QS[ea*QSTRIDE + i*NDIMS + j] = sm[i][j];
+                    QS[ea*QSTRIDE + NDIMS*NDIMS + 1 + i*NDIMS + j] = rj*sm[i][j];
+                }
+            QS[ea*QSTRIDE + NDIMS*NDIMS] = rj;
         }
 ''')
             geo_post = r'''
         fpdtype_t sA[NDIMS][NDIMS], rjA;
         {
-            const fpdtype_t *q = QS + (''' + w['mine'] + r''')*(NDIMS*NDIMS + 1);
+            const fpdtype_t *q = QS + (''' + w['mine'] + r''')*QSTRIDE;
             UNROLL for (int i = 0; i < NDIMS; i++)
                 UNROLL for (int j = 0; j < NDIMS; j++)
                     sA[i][j] = q[i*NDIMS + j];
@@ -596,7 +602,8 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False, who=None):
             const fpdtype_t (&s)[NDIMS][NDIMS] = sA;
             const fpdtype_t rcpdjac_v = rjA;
 '''
-            npt_words, q_words = 2, (nd*nd + 1)*csub
+            npt_words, q_words = 2, 2*(nd*nd + 1)*csub
+            gsrc = f'#define QSTRIDE {2*(nd*nd + 1)}\n' + gsrc
         elif mj is not None:
             # Per element: Q[q][i] = sum_n W[d][k][n] V[n][i] for every
             # (d, monomial k) with a non-zero coefficient; per point: the

@@ -114,6 +114,33 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src,
 }
 '''
 
+# (kept apart from ``_pipeline_src`` so that only the kernels that use it
+# carry it)
+_cpasync_src = r'''
+// Per-thread asynchronous copy global -> shared of N = 4, 8 or 16 bytes
+// (LDGSTS): gathers land in shared memory without passing through registers
+template <int N>
+__device__ __forceinline__ void cp_async(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
+                 :: "r"(smem_u32(dst)), "l"(src), "n"(N) : "memory");
+}
+
+// ... 16 bytes, not kept in the first-level cache
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// ... all of this thread's copies have landed (visible to the CTA after
+// the next barrier)
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+'''
+
 
 def plan_chunks(K, LD, itemsize, smem_budget, hint=None):
     """Split the K input rows into equal chunks whose double-buffered tile

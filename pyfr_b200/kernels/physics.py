@@ -80,9 +80,13 @@ inviscid_flux(const fpdtype_t s[NVARS], fpdtype_t f[NDIMS][NVARS],
 
 visc_src = r'''
 // ---- viscous flux, added into fout[d][v] -----------------------------------
+// The flux is linear in the gradient: ``sc`` scales it through the
+// viscosity, so a caller holding the gradient without its 1/|J| factor
+// passes that factor here instead of multiplying NDIMS*NVARS values by it.
 __device__ __forceinline__ void
-viscous_flux_add(const fpdtype_t u[NVARS], const fpdtype_t g[NDIMS][NVARS],
-                 fpdtype_t fout[NDIMS][NVARS])
+viscous_flux_add_sc(const fpdtype_t u[NVARS],
+                    const fpdtype_t g[NDIMS][NVARS],
+                    fpdtype_t fout[NDIMS][NVARS], const fpdtype_t sc)
 {
     const fpdtype_t rho = u[0], E = u[NVARS - 1];
     const fpdtype_t rcprho = FP(1.0)/rho;
@@ -102,9 +106,9 @@ viscous_flux_add(const fpdtype_t u[NVARS], const fpdtype_t g[NDIMS][NVARS],
         q2 += vel[i]*vel[i];
     const fpdtype_t cpT = C_GAMMA*(rcprho*E - FP(0.5)*q2);
     const fpdtype_t Trat = C_RCPCPTREF*cpT;
-    const fpdtype_t mu_c = C_MU_SUTH*Trat*sqrt(Trat)/(cpT + C_CPTS);
+    const fpdtype_t mu_c = sc*(C_MU_SUTH*Trat*sqrt(Trat)/(cpT + C_CPTS));
 #else
-    const fpdtype_t mu_c = C_MU;
+    const fpdtype_t mu_c = sc*C_MU;
 #endif
 
     fpdtype_t div = 0;
@@ -138,6 +142,13 @@ viscous_flux_add(const fpdtype_t u[NVARS], const fpdtype_t g[NDIMS][NVARS],
 
         fout[d][NVARS - 1] += ef + -mu_c*C_GAMMA_PR*T_x[d];
     }
+}
+
+__device__ __forceinline__ void
+viscous_flux_add(const fpdtype_t u[NVARS], const fpdtype_t g[NDIMS][NVARS],
+                 fpdtype_t fout[NDIMS][NVARS])
+{
+    viscous_flux_add_sc(u, g, fout, FP(1.0));
 }
 '''
 

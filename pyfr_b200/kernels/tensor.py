@@ -161,18 +161,67 @@ def tp_structure(ops, nd, tol=1e-12):
 
 
 def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
-                       affine=False):
+                       affine=False, gather=False):
     """Source of the sum-factorised fused kernel; arguments and return
-    value as ``fused.gradflux_source``."""
+    value as ``fused.gradflux_source``.
+
+    ``gather``: the kernel forms the common solution at its flux points
+    itself (``fusion.fold_conu``: the interior ``intconu`` launch and its
+    pass over the flux-point array disappear).  Instead of one bulk copy of
+    the block's ``ucomm`` tile every thread copies a few points, each from
+    the address a per-block index table names -- the trace of whichever
+    side of the interface a one-sided LDG flux takes (``sfp`` + index), or
+    the block's own ``ucomm`` entry where another kernel (boundary,
+    partition boundary) has stored the common value (index < 0) -- with
+    per-thread asynchronous copies straight into shared memory.
+
+    Half blocks (``gradflux-split``, automatic): where a whole element
+    block fills an SM's shared memory (hexahedra, p = 4, fp64: 208 KB) the
+    kernel works on half blocks instead -- the columns of ``C_SUB/2``
+    elements, two co-resident CTAs of half the threads per SM -- so that
+    the FP64-bound flux phase of one CTA overlaps the shared-memory-bound
+    line phases of the other (measured with ``n-soa = 4``, where the
+    *storage* has half-width blocks: -13 %, r02m; that setting slows every
+    other kernel down).  The storage layout stays as it is: a half block's
+    rows are 16-byte runs of the full rows, fetched with per-thread
+    asynchronous copies instead of one bulk copy, and stored with the same
+    16-byte stores as before."""
     nd, nv = tplargs['ndims'], tplargs['nvars']
     st = tp_structure(ops, nd)
     n1, nl = st['n1'], st['nlines']
     nu, nf = n1**nd, 2*nd*nl
     isz = np.dtype(be.fpdtype).itemsize
-    csub = be.csubsz
+    gcsub, GLD = be.csubsz, LD                 # storage layout
 
-    if LD != nv*csub:
+    if LD != nv*gcsub:
         raise NotFusable('unexpected leading dimension')
+    if gather and be.soasz != gcsub:
+        raise NotFusable('gather form needs one SoA group per block')
+
+    # Half blocks?
+    linear = 'linear' in tplargs['ktype']
+    geo_est = 4096
+    fits = lambda ld: (227*1024) // ((nu + nf + nd*nu)*ld*isz + geo_est)
+    SPLIT = 1
+    if (getattr(be, 'gradflux_split', True) and linear and
+        be.soasz == gcsub and gcsub % 2 == 0 and (gcsub // 2)*isz >= 16 and
+        getattr(be, 'gradflux_groups', 1) == 1 and
+        not getattr(be, 'gradflux_threads', 0) and nthreads is None and
+        getattr(be, 'gradflux_maxctas', 2) >= 2 and
+        fits(LD) == 1 and fits(LD // 2) >= 2):
+        SPLIT = 2
+
+    class _Half:
+        """The backend as the kernel sees its (half-width) blocks."""
+        def __init__(self, be, c):
+            self._be, self.soasz, self.csubsz = be, c, c
+
+        def __getattr__(self, k):
+            return getattr(self._be, k)
+
+    csub = gcsub // SPLIT
+    LD = nv*csub
+    gbe, be = be, (_Half(be, csub) if SPLIT > 1 else be)
 
     # Columns per work item: one 16-byte access
     NC = 16 // isz
@@ -182,7 +231,6 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     comps = 'xyzw'[:NC]
     vec = {(8, 2): 'double2', (4, 4): 'float4'}[isz, NC]
 
-    linear = 'linear' in tplargs['ktype']
     affine = bool(affine and linear)
 
     # Occupancy plan: as many CTAs per SM as the shared-memory footprint
@@ -203,7 +251,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     # (the second starts once the first has finished its first phase 1),
     # so the FP64-bound flux phase of one overlaps the shared-memory-bound
     # line phases of the other.
-    NG = getattr(be, 'gradflux_groups', 1)
+    NG = 1 if gather else getattr(be, 'gradflux_groups', 1)
     if (NG < 1 or csub % (NG*NC) or be.soasz != csub or nthreads % (32*NG)
             or (nthreads // NG) % (csub // NG)):
         NG = 1
@@ -223,7 +271,10 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             ('NVERTS', tplargs.get('nverts', 0)), ('NEED_RCPDJAC', 1),
             ('LD', LD), ('NTHREADS', nthreads), ('NROUNDS', nrounds),
             ('ROWB', ROWB), ('NCGH', NCGH), ('NLG', NLG), ('NLINES', nl),
-            ('NG', NG), ('GT', GT), ('H', H), ('CPV', CPV)]
+            ('NG', NG), ('GT', GT), ('H', H), ('CPV', CPV),
+            ('NGP', nf*csub), ('NGR', -(-nf*csub // nthreads)),
+            ('SPLIT', SPLIT), ('GC_SUB', gcsub), ('GLD', GLD),
+            ('GROWB', GLD*isz), ('CH16', csub*isz // 16)]
     defs += ph.physics_defines(tplargs['c'], tplargs.get('visc_corr', 'none'),
                                True)
 
@@ -244,7 +295,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     if rowcls is not None and max(rowcls) < 16:
         cls = [int(c) for c in rowcls]
         fm_arg = ',\n         const int* __restrict__ fmask'
-        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + bq);'
+        fm_load = 'const unsigned fm = (unsigned) __ldg(fmask + rb);'
     else:
         cls, fm_arg, fm_load = None, '', ''
 
@@ -278,16 +329,28 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     }}''')
     desc = ''.join(desc)
 
-    def unpack(d, r, ends=False, masks=False):
+    def unpack(d, r, ends=False, masks=False, glob=False):
         """Row offsets (bytes, this item's columns included) of work item
         ``(d, r)``: ``lb`` first solution point, ``lm``/``lp`` its flux
-        points; ``wm``/``wp`` whether those rows are needed."""
+        points; ``wm``/``wp`` whether those rows are needed; ``glob``: the
+        same rows in the storage layout (``glb``, ``glm``, ``glp``)."""
         L = [f'    unsigned qx = dx{d}_{r}, qy = dy{d}_{r};',
              '    OPAQUE(qx); OPAQUE(qy);',
              '    const int lb = (int) (qx & 0xffffu)*ROWB + cb;']
         if ends:
             L += ['    const int lm = (int) (qx >> 16)*ROWB + cb, '
                   'lp = (int) (qy & 0xffffu)*ROWB + cb;']
+        if glob:
+            # (this item's columns in the storage layout; the half block's
+            # own offset rides on the block pointers)
+            L += ['    int cq = cb; OPAQUE(cq);',
+                  f'    const int cbg = cq + (cq / (C_SUB*{isz}))'
+                  f'*((GC_SUB - C_SUB)*{isz});']
+        if glob and ends:
+            L += ['    const int glm = (int) (qx >> 16)*GROWB + cbg, '
+                  'glp = (int) (qy & 0xffffu)*GROWB + cbg;']
+        elif glob:
+            L += ['    const int glb = (int) (qx & 0xffffu)*GROWB + cbg;']
         if masks and cls:
             L += ['    const bool wm = (fm >> ((qy >> 16) & 0xffu)) & 1u, '
                   'wp = (fm >> (qy >> 24)) & 1u;']
@@ -312,27 +375,50 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             out.append(f'{indent}{dst}.{k} = {e or "FP(0.0)"};')
         return out
 
+    # Software pipelining of the line phases: the loads of work item k + 1
+    # are written ahead of the arithmetic and the stores of item k.  The
+    # compiler cannot make that move itself -- it has to assume that a
+    # store into G may alias the next item's loads -- and without it a warp
+    # alternates between waiting for shared memory and using the FP64
+    # pipe (SASS of r02c: LDS x7, DFMA x70, STS x5 per direction).
+    swp = getattr(be, 'gradflux_swp', True)
+
+    def pipelined(items):
+        """``items``: (condition, declarations, load lines, compute lines,
+        lines every thread runs ahead of the compute step -- a barrier);
+        the loads leave their values in the declared variables."""
+        L = [l for it in items for l in it[1]]
+        for k, (c, dcl, lds, cmp, pre) in enumerate(items):
+            if k == 0 or not swp:
+                L += [f'if ({c})', '{'] + lds + ['}']
+            if swp and k + 1 < len(items):
+                L += [f'if ({items[k + 1][0]})', '{'] + items[k + 1][2] + ['}']
+            L += pre + [f'if ({c})', '{'] + cmp + ['}']
+        return '\n        '.join(L)
+
     # -- phase 1: G[d] = Dg u + Lg (c-, c+) along the lines of d -------------
     p1 = []
     for d in range(nd):
         sb = st['stride'][d]*ROWB
         for r in range(R):
-            L = [f'if (on{d}_{r})', '{'] + unpack(d, r, ends=True)
+            t = f'{d}_{r}'
+            dcl = ['fpvec_t ' + ', '.join(f'x{t}_{i}' for i in range(n1)) +
+                   f', cm{t}, cp{t};']
+            lds = unpack(d, r, ends=True)
             for i in range(n1):
-                L.append(f'    const fpvec_t x{i} = '
-                         f'{ld("Ub", f"lb + {i*sb}")};')
-            L.append(f'    const fpvec_t cm = {ld("Cb", "lm")};')
-            L.append(f'    const fpvec_t cp = {ld("Cb", "lp")};')
-            L.append('    fpvec_t o;')
+                lds.append(f'    x{t}_{i} = {ld("Ub", f"lb + {i*sb}")};')
+            lds += [f'    cm{t} = {ld("Cb", "lm")};',
+                    f'    cp{t} = {ld("Cb", "lp")};']
+            cmp = unpack(d, r) + ['    fpvec_t o;']
             for i in range(n1):
-                terms = [(st['Dg'][d][i, j], f'x{j}') for j in range(n1)]
-                terms += [(st['Lg'][d][i, 0], 'cm'), (st['Lg'][d][i, 1], 'cp')]
-                L += lincomb('o', terms, '    ')
-                L.append(f'    {stv("Gb", f"{d*nu*ROWB + i*sb} + lb")}'
-                         ' = o;')
-            L.append('}')
-            p1.append('\n        '.join(L))
-    p1 = '\n        '.join(p1)
+                terms = [(st['Dg'][d][i, j], f'x{t}_{j}') for j in range(n1)]
+                terms += [(st['Lg'][d][i, 0], f'cm{t}'),
+                          (st['Lg'][d][i, 1], f'cp{t}')]
+                cmp += lincomb('o', terms, '    ')
+                cmp.append(
+                    f'    {stv("Gb", f"{d*nu*ROWB + i*sb} + lb")} = o;')
+            p1.append((f'on{d}_{r}', dcl, lds, cmp, []))
+    p1 = pipelined(p1)
 
     # -- phase 3: gradients at the flux points -> HBM -------------------------
     # Lines of direction a end on the two faces normal to a; all ndims
@@ -342,14 +428,14 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     metric_load = f'''
         // Constant metric of the {NC} elements this item's columns belong to
         // (QS was filled by the first threads of the block)
-        fpdtype_t sP[{NC}][NDIMS][NDIMS], rjP[{NC}];
+        // scaled by 1/|J|
+        fpdtype_t sP[{NC}][NDIMS][NDIMS];
         UNROLL for (int k = 0; k < {NC}; k++)
         {{
-            const fpdtype_t *q = QS + (e0 + k)*(NDIMS*NDIMS + 1);
+            const fpdtype_t *q = QS + (e0 + k)*QSTRIDE + NDIMS*NDIMS + 1;
             UNROLL for (int i = 0; i < NDIMS; i++)
                 UNROLL for (int j = 0; j < NDIMS; j++)
                     sP[k][i][j] = q[i*NDIMS + j];
-            rjP[k] = q[NDIMS*NDIMS];
         }}'''
     late = getattr(be, 'gradflux_metric_late', False)
     p3 = []
@@ -357,96 +443,113 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         sb = st['stride'][a]*ROWB
         for r in range(R):
             L = ([f'if (on{a}_{r})', '{'] +
-                 unpack(a, r, ends=True, masks=True))
-            L += ['    if (wm | wp)', '    {']
-            for d in range(nd):
-                L.append(f'        fpvec_t tm{d}, tp{d};')
-                L.append('        {')
-                for i in range(n1):
-                    L.append(f'            const fpvec_t g{i} = '
-                             f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
-                L += lincomb(f'tm{d}', [(st['lm'][a][i], f'g{i}')
-                                        for i in range(n1)], '            ')
-                L += lincomb(f'tp{d}', [(st['lp'][a][i], f'g{i}')
-                                        for i in range(n1)], '            ')
-                L.append('        }')
+                 unpack(a, r, ends=True, masks=True, glob=True))
+            # One body per set of live ends: with a one-sided LDG flux a
+            # line usually has one live end, and the interpolation to the
+            # other one is not formed either
+            for cond, ends in (('wm & wp', 'mp'), ('wm', 'm'), ('wp', 'p')):
+                kw = 'if' if ends == 'mp' else 'else if'
+                L += [f'    {kw} ({cond})', '    {']
+                for d in range(nd):
+                    L.append('        fpvec_t ' + ', '.join(
+                        f't{e}{d}' for e in ends) + ';')
+                    L.append('        {')
+                    for i in range(n1):
+                        L.append(
+                            f'            const fpvec_t g{i} = '
+                            f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
+                    for e in ends:
+                        L += lincomb(f't{e}{d}',
+                                     [(st['l' + e][a][i], f'g{i}')
+                                      for i in range(n1)], '            ')
+                    L.append('        }')
 
-            if affine and late:
-                # (the metric is fetched after the interpolation, so that
-                # its registers do not limit the loads in flight above)
-                L.append(metric_load)
-            for w, t, lf in (('wm', 'tm', 'lm'), ('wp', 'tp', 'lp')):
-                L += [f'        if ({w})', '        {',
-                      f'            char *vo = vfp + {lf};']
-                for dp in range(nd):
-                    if affine:
-                        L.append('            { fpvec_t o;')
-                        for ki, k in enumerate(comps):
-                            e = None
-                            for d in range(nd):
-                                e = (f'sP[{ki}][{d}][{dp}]*{t}{d}.{k}'
-                                     if e is None else
-                                     f'fma(sP[{ki}][{d}][{dp}], {t}{d}.{k}, '
-                                     f'{e})')
-                            L.append(f'            o.{k} = rjP[{ki}]*({e});')
-                        L.append(f'            {stv("vo", dp*nf*ROWB)} = o; '
-                                 '}')
-                    else:
-                        L.append(f'            {stv("vo", dp*nf*ROWB)} = '
-                                 f'{t}{dp};')
-                L.append('        }')
-            L += ['    }', '}']
+                if affine and late:
+                    # (the metric is fetched after the interpolation, so
+                    # that its registers do not limit the loads in flight)
+                    L.append(metric_load)
+                for e in ends:
+                    t = f't{e}'
+                    L += ['        {', f'            char *vo = vfp + gl{e};']
+                    for dp in range(nd):
+                        if affine:
+                            L.append('            { fpvec_t o;')
+                            for ki, k in enumerate(comps):
+                                ex = None
+                                for d in range(nd):
+                                    ex = (f'sP[{ki}][{d}][{dp}]*{t}{d}.{k}'
+                                          if ex is None else
+                                          f'fma(sP[{ki}][{d}][{dp}], '
+                                          f'{t}{d}.{k}, {ex})')
+                                L.append(f'            o.{k} = {ex};')
+                            L.append(f'            {stv("vo", dp*nf*GLD*isz)}'
+                                     ' = o; }')
+                        else:
+                            L.append(f'            {stv("vo", dp*nf*GLD*isz)} = '
+                                     f'{t}{dp};')
+                    L.append('        }')
+                L.append('    }')
+            L.append('}')
             p3.append('\n        '.join(L))
     p3 = '\n        '.join(p3)
 
     # -- phase 5: divergence --------------------------------------------------
     # in-place line transforms for all but the last direction ...
-    p5a = []
+    def p5_loads(a, r):
+        t = f'{a}_{r}'
+        sb = st['stride'][a]*ROWB
+        dcl = ['fpvec_t ' + ', '.join(f'f{t}_{i}' for i in range(n1)) +
+               ';']
+        lds = unpack(a, r)
+        for i in range(n1):
+            lds.append(f'    f{t}_{i} = '
+                       f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb")};')
+        return dcl, lds
+
+    p5 = []
     for a in range(nd - 1):
         sb = st['stride'][a]*ROWB
         for r in range(R):
-            L = [f'if (on{a}_{r})', '{'] + unpack(a, r)
+            t = f'{a}_{r}'
+            dcl, lds = p5_loads(a, r)
+            cmp = unpack(a, r) + ['    fpvec_t o;']
             for i in range(n1):
-                L.append(f'    const fpvec_t x{i} = '
-                         f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb")};')
-            L.append('    fpvec_t o;')
-            for i in range(n1):
-                L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
-                                   for j in range(n1)], '    ')
-                L.append(f'    {stv("Gb", f"{a*nu*ROWB + i*sb} + lb")}'
-                         ' = o;')
-            L.append('}')
-            p5a.append('\n        '.join(L))
-    p5a = '\n        '.join(p5a)
+                cmp += lincomb('o', [(st['Dt'][a][i, j], f'f{t}_{j}')
+                                     for j in range(n1)], '    ')
+                cmp.append(
+                    f'    {stv("Gb", f"{a*nu*ROWB + i*sb} + lb")} = o;')
+            p5.append((f'on{a}_{r}', dcl, lds, cmp, []))
 
     # ... the last one in registers, summed with the others on the way out
+    # (its own flux component is not touched by the transforms above and
+    # is fetched ahead of the barrier that separates the two steps)
     a = nd - 1
     sb = st['stride'][a]*ROWB
-    p5b = []
     for r in range(R):
-        L = [f'if (on{a}_{r})', '{'] + unpack(a, r)
+        t = f'{a}_{r}'
+        dcl, lds = p5_loads(a, r)
+        cmp = unpack(a, r, glob=True) + ['    fpvec_t o;']
+        sbg = st['stride'][a]*GLD*isz
         for i in range(n1):
-            L.append(f'    const fpvec_t x{i} = '
-                     f'{ld("Gb", f"{a*nu*ROWB + i*sb} + lb")};')
-        L.append('    fpvec_t o;')
-        for i in range(n1):
-            L += lincomb('o', [(st['Dt'][a][i, j], f'x{j}')
-                               for j in range(n1)], '    ')
+            cmp += lincomb('o', [(st['Dt'][a][i, j], f'f{t}_{j}')
+                                 for j in range(n1)], '    ')
             for d in range(nd - 1):
-                L.append(f'    {{ const fpvec_t y = '
-                         f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
-                L.append('      ' + ' '.join(f'o.{k} += y.{k};'
-                                             for k in comps) + ' }')
-            L.append(f'    {stv("fop", f"{i*sb} + lb")} = o;')
-        L.append('}')
-        p5b.append('\n        '.join(L))
-    p5b = '\n        '.join(p5b)
+                cmp.append(f'    {{ const fpvec_t y = '
+                           f'{ld("Gb", f"{d*nu*ROWB + i*sb} + lb")};')
+                cmp.append('      ' + ' '.join(f'o.{k} += y.{k};'
+                                               for k in comps) + ' }')
+            cmp.append(f'    {stv("fop", f"{i*sbg} + glb")} = o;')
+        p5.append((f'on{a}_{r}', dcl, lds, cmp,
+                   ['GSYNC();'] if (r == 0 and nd > 1) else []))
+    p5 = pipelined(p5)
 
     # -- metric terms of the work items' columns (affine) ---------------------
     if affine:
         metric_p3 = '' if late else metric_load
         p2 = ''
-        p4_xform = 'transform_grad(g, s, rcpdjac_v);'
+        # (1/|J| rides on the viscosity: the viscous flux is linear in g)
+        p4_xform = 'transform_grad(g, s, FP(1.0));'
+        p4_visc = 'viscous_flux_add_sc(ureg[r], g, ft, rcpdjac_v);'
     else:
         metric_p3 = ''
         p2 = f'''
@@ -471,9 +574,12 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         GSYNC();
 '''
         p4_xform = '(void) rcpdjac_v;'
+        p4_visc = 'viscous_flux_add(ureg[r], g, ft);'
 
     geo_words = geo['geo_words']
     smem = ((nu + nf + nd*nu)*LD + geo_words)*isz + 64
+    if gather:
+        smem += nf*csub*4
     if smem > 227*1024:
         raise NotFusable(f'needs {smem} bytes of shared memory')
 
@@ -483,7 +589,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         hold = '''
     // The second group starts once the first has finished a phase of its
     // first block (one thread polls, the rest wait on the group barrier)
-    if (grp > 0 && (long long) blockIdx.x < nblocks)
+    if (grp > 0 && (long long) blockIdx.x < nblk)
     {
         if (gtid == 0)
             flag_wait(flag);
@@ -491,7 +597,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     }
 '''
         release = ('if (it == 0 && grp == 0 && gtid == 0) flag_set(flag);')
-        issue = '''if (gtid == 0 && nxt < nblocks)
+        issue = '''if (gtid == 0 && nxt < nblk)
         {
             // the group that arrives last starts the copy
             if (atomicAdd(cnt, 1) == NG - 1)
@@ -503,15 +609,117 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     else:
         gsync = '#define GSYNC() __syncthreads()'
         hold, release = '', ''
-        issue = '''if (tid == 0 && nxt < nblocks)
+        issue = '''if (tid == 0 && nxt < nblk)
             fetch(nxt, it + 1);'''
     rel1 = release if stagger == 1 else ''
     rel3 = release if stagger != 1 else ''
 
+    from pyfr_b200.kernels.mul import _cpasync_src
+
+    split = SPLIT > 1
+    nb_expr = 'nblocks*SPLIT' if split else 'nblocks'
+    cpsrc = _cpasync_src if (gather or split) else ''
+
+    if gather:
+        g_arg = (',\n         const int* __restrict__ gidx,'
+                 '\n         const fpdtype_t* __restrict__ sfp')
+        g_lambdas = f'''
+    // Common solution by gather: this thread's points of a block (point =
+    // flux-point row x element) and where each comes from.  The indices
+    // of the next block are parked in shared memory a phase ahead of the
+    // copies that need them (each thread reads back what it copied itself)
+    auto gidx_load = [&](long long b)
+    {{
+        const long long rbn = b / SPLIT;
+        const int hf = (int) (b % SPLIT);
+        UNROLL for (int r = 0; r < NGR; r++)
+        {{
+            const int p = tid + r*NTHREADS;
+            if (p < NGP)
+                cp_async<4>(GIX + p, gidx + rbn*(NFPTS*GC_SUB)
+                            + (p / C_SUB)*GC_SUB + hf*C_SUB + p % C_SUB);
+        }}
+    }};
+    auto gather = [&](long long b)
+    {{
+        const long long rbn = b / SPLIT;
+        const int hf = (int) (b % SPLIT);
+        cp_async_wait_all();
+        UNROLL for (int r = 0; r < NGR; r++)
+        {{
+            const int p = tid + r*NTHREADS;
+            if (p < NGP)
+            {{
+                const int row = p / C_SUB, e = p % C_SUB, gi = GIX[p];
+                const fpdtype_t *from = (gi >= 0) ? sfp + gi
+                    : ucomm + rbn*ucomm_bsz + row*GLD + hf*C_SUB + e;
+                fpdtype_t *to = C + row*LD + e;
+                UNROLL for (int v = 0; v < NVARS; v++)
+                    cp_async<{isz}>(to + v*C_SUB, from + v*GC_SUB);
+            }}
+        }}
+    }};'''
+        # (the indices of the next block are fetched a phase ahead of the
+        # copies that need them)
+        g_top = 'if (nxt < nblk) gidx_load(nxt);'
+        g_issue = 'if (nxt < nblk) gather(nxt);'
+    else:
+        g_arg = g_lambdas = g_top = g_issue = ''
+
+    if gather or split:
+        g_first = ('''
+    if (blk < nblk)
+    {''' + ('''
+        gidx_load(blk);
+        gather(blk);''' if gather else '') + ('''
+        fetch(blk, 0);''' if split else '') + '''
+    }
+    cp_async_wait_all();
+    __syncthreads();''')
+        g_wait = 'cp_async_wait_all();'
+    else:
+        g_first = g_wait = ''
+
+    if split:
+        # Half blocks: 16-byte runs of the storage rows, one asynchronous
+        # copy each, issued by all threads
+        def strided(dst, srcp, bsz, nrows):
+            return f'''
+        {{
+            const fpdtype_t *from = {srcp} + rbn*{bsz} + hf*C_SUB;
+            for (int i = tid; i < ({nrows})*CH16; i += NTHREADS)
+                cp_async16({dst} + (i / CH16)*C_SUB + (i % CH16)*{16 // isz},
+                           from + (i / CH16)*GC_SUB + (i % CH16)*{16 // isz});
+        }}'''
+
+        fetch_body = ('const long long rbn = b / SPLIT;\n        '
+                      'const int hf = (int) (b % SPLIT);'
+                      + strided('U', 'u', 'u_bsz', 'NPTS*NVARS')
+                      + ('' if gather else
+                         strided('C', 'ucomm', 'ucomm_bsz', 'NFPTS*NVARS'))
+                      + strided('(VSB + (n & 1)*V_WORDS)', 'verts',
+                                'verts_bsz', 'NVERTS*NDIMS'))
+        first_fetch = ''
+        issue = '''if (nxt < nblk)
+            fetch(nxt, it + 1);'''
+        wait_tma = ''
+    else:
+        c_fetch = '' if gather else (
+            '''tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
+                    &bars[0]);''')
+        fetch_body = f'''mbar_expect_tx(&bars[0], ({'U_WORDS' if gather else 'U_WORDS + C_WORDS'})*sizeof(fpdtype_t)
+                                 {geo['geo_bytes']});
+        tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
+        {c_fetch}
+        {geo['geo_fetch']}'''
+        first_fetch = '''if (tid == 0 && blk < nblk)
+        fetch(blk, 0);'''
+        wait_tma = 'mbar_wait(&bars[0], it & 1);'
+
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
                           be.soasz, be.csubsz, defs)}
 typedef {vec} fpvec_t;
-{_pipeline_src}
+{_pipeline_src}{cpsrc}
 {ph.flux_src}
 {ph.visc_src}
 {ph.geom_src}
@@ -535,7 +743,7 @@ gradflux(int nblocks, int neles,
          const fpdtype_t* ucomm, long long ucomm_bsz,
          fpdtype_t* vf, long long vf_bsz,
          fpdtype_t* __restrict__ fout, long long fout_bsz,
-         {geo['gargs']}{fm_arg})
+         {geo['gargs']}{fm_arg}{g_arg})
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
@@ -545,7 +753,8 @@ gradflux(int nblocks, int neles,
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         G + G_WORDS + {geo_words});
     int *cnt = reinterpret_cast<int *>(bars + 1), *flag = cnt + 1;
-    (void) flag;
+    int *GIX = cnt + 2;
+    (void) flag; (void) GIX;
 
     char *Ub = reinterpret_cast<char *>(U);
     char *Cb = reinterpret_cast<char *>(C);
@@ -577,29 +786,31 @@ gradflux(int nblocks, int neles,
 
     auto fetch = [&](long long b, unsigned n)
     {{
-        mbar_expect_tx(&bars[0], (U_WORDS + C_WORDS)*sizeof(fpdtype_t)
-                                 {geo['geo_bytes']});
-        tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
-        tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
-                    &bars[0]);
-        {geo['geo_fetch']}
+        {fetch_body}
     }};
+{g_lambdas}
 
+    // (half) blocks of this launch
+    const long long nblk = {nb_expr};
     long long blk = blockIdx.x;
-    if (tid == 0 && blk < nblocks)
-        fetch(blk, 0);
+    {first_fetch}
+{g_first}
 {hold}
-    for (unsigned it = 0; blk < nblocks; blk += gridDim.x, it++)
+    for (unsigned it = 0; blk < nblk; blk += gridDim.x, it++)
     {{
         // (block pointers are formed from the block number every time:
         // kept as induction variables they cost a dozen registers)
         long long bq = blk;
         OPAQUE64(bq);
         const long long nxt = bq + gridDim.x;
-        char *vfp = reinterpret_cast<char *>(vf + bq*vf_bsz);
-        char *fop = reinterpret_cast<char *>(fout + bq*fout_bsz);
+        // storage block and which half of its columns
+        const long long rb = bq / SPLIT;
+        const long long hoff = (bq % SPLIT)*C_SUB;
+        char *vfp = reinterpret_cast<char *>(vf + rb*vf_bsz + hoff);
+        char *fop = reinterpret_cast<char *>(fout + rb*fout_bsz + hoff);
 
-        mbar_wait(&bars[0], it & 1);
+        {wait_tma}
+        {g_top}
         {geo['geo_blk']}
         {fm_load}
 {geo['geo_elem']}
@@ -626,6 +837,7 @@ gradflux(int nblocks, int neles,
         // here the next block's copies are started behind the remaining
         // phases
         {issue}
+        {g_issue}
 {p2}
         // ---- phase 3: gradients at the flux points -> HBM ---------------
         {{
@@ -653,7 +865,7 @@ gradflux(int nblocks, int neles,
 
                 fpdtype_t ft[NDIMS][NVARS], fo[NDIMS][NVARS], pr, vel[NDIMS];
                 inviscid_flux(ureg[r], ft, pr, vel);
-                viscous_flux_add(ureg[r], g, ft);
+                {p4_visc}
                 transform_flux(ft, s, fo);
 
                 UNROLL for (int d = 0; d < NDIMS; d++)
@@ -664,9 +876,8 @@ gradflux(int nblocks, int neles,
         GSYNC();
 
         // ---- phase 5: divergence along the lines, summed -> HBM ----------
-        {p5a}
-        {'GSYNC();' if nd > 1 else ''}
-        {p5b}
+        {p5}
+        {g_wait}
         GSYNC();
     }}
 }}
@@ -674,6 +885,7 @@ gradflux(int nblocks, int neles,
     if nctas*(smem + 1024) > 227*1024:
         nctas = 1
     meta = dict(nthreads=nthreads, smem=smem, nctas=nctas, ngroups=NG,
-                words_per_block=(2*nu + nf + nd*nf)*LD, tensor=True)
+                words_per_block=(2*nu + nf + nd*nf)*GLD, tensor=True,
+                gather=gather, gather_points=nf*gcsub, split=SPLIT)
 
     return src, 'gradflux', meta

@@ -189,8 +189,17 @@ class B200Graph(base.Graph):
             self.program = fusion.batch_launches(be, self.program)
 
     def _commit(self):
-        self._fuse()
+        import weakref
 
+        self._fuse()
+        self._plan()
+
+        # (the fusion pass of the next graph may still fold a kernel of
+        # this one into its own -- ``fusion.conu_fold_plan`` -- as long as
+        # this graph has not run)
+        self.backend.last_committed = weakref.ref(self)
+
+    def _plan(self):
         # All exchanges of a graph go out as one NCCL group, issued once
         # the last pack kernel has been enqueued
         reqs = [r for what, r in self.program if what == 'xchg']
@@ -252,6 +261,7 @@ class B200Graph(base.Graph):
     def run(self, stream=None):
         be, rt = self.backend, self.backend.rt
         stream = stream or be.stream
+        self.started = True
 
         # Run-time scalars (t, dt) reach the kernels through device memory
         be.rtscal.flush(stream)

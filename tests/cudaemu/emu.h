@@ -186,6 +186,20 @@ static inline void tma_load_1d(void *dst, const void *src, unsigned bytes,
         b->completed.fetch_add(1, std::memory_order_release);
 }
 
+// ---- per-thread asynchronous copies (executed at once) ---------------------------
+template <int N>
+static inline void cp_async(void *dst, const void *src)
+{
+    std::memcpy(dst, src, N);
+}
+
+static inline void cp_async16(void *dst, const void *src)
+{
+    std::memcpy(dst, src, 16);
+}
+
+static inline void cp_async_wait_all() {}
+
 // ---- launcher -----------------------------------------------------------------
 template <class F>
 static void emu_launch(F &&body, unsigned gx, unsigned gy, unsigned gz,

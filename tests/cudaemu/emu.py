@@ -46,9 +46,9 @@ extern "C" void emu_entry(void **args, unsigned gx, unsigned gy, unsigned gz,
 
 
 def translate(src):
-    from pyfr_b200.kernels.mul import _pipeline_src
+    from pyfr_b200.kernels.mul import _cpasync_src, _pipeline_src
 
-    src = src.replace(_pipeline_src, '')
+    src = src.replace(_pipeline_src, '').replace(_cpasync_src, '')
     src = src.replace('asm volatile("fence.mbarrier_init.release.cluster;" '
                       '::: "memory");', '')
     src = re.sub(r'extern __shared__[^;]*;', '', src)

@@ -71,21 +71,21 @@ def _kinds(sysm):
     (dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
     # intconu over pairs of points (128-bit accesses where both addresses
     # of a side are adjacent): one-sided, central and left-biased LDG
-    (dict(order=2, warp=0.1), {'conu-pairs': 1}, 'intconu'),
+    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0}, 'intconu'),
     (dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {'conu-pairs': 1},
      'intconu'),
-    (dict(order=2, beta=-0.5, curved=0.5, warp=0.1), {'conu-pairs': 1},
-     'intconu'),
+    (dict(order=2, beta=-0.5, curved=0.5, warp=0.1),
+     {'conu-pairs': 1, 'conu-fold': 0}, 'intconu'),
     (dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0}, 'intconu'),
-    (dict(order=3), {'conu-pairs': 1, 'n-soa': 4}, 'intconu'),
+    (dict(order=3), {'conu-pairs': 1, 'n-soa': 4, 'conu-fold': 0}, 'intconu'),
     # ... with the interface points in true address order (most pairs
     # then take the 128-bit path)
-    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address'},
-     'intconu'),
+    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address',
+                               'conu-fold': 0}, 'intconu'),
     (dict(order=3, rsolver='hllc', beta=0.0), {'conu-pairs': 1,
                                                'inters-order': 'address'},
      'intconu'),
-    (dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1,
+    (dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0,
                                           'inters-order': 'address'},
      'intconu'),
     (dict(order=4), {'inters-order': 'address'}, 'gradflux'),
@@ -101,8 +101,15 @@ def _kinds(sysm):
      'gradflux'),
     (dict(order=2, warp=0.1), {'dead-rows': 0}, 'gradflux'),
     (dict(order=1), {}, 'gradflux'),
-    # the benchmark's kernel variants (p = 4, 512 threads, 220 KB smem)
+    # the benchmark's kernel variants (p = 4): common solution gathered by
+    # the element kernel, half blocks (the default); each switched off
     (dict(order=4), {}, 'gradflux'),
+    (dict(order=4), {'conu-fold': 0}, 'intconu'),
+    (dict(order=4), {'gradflux-split': 0}, 'gradflux'),
+    (dict(order=4, beta=-0.5, warp=0.1), {'conu-fold': 0,
+                                          'gradflux-split': 0}, 'intconu'),
+    (dict(order=4, beta=0.0, warp=0.1), {}, 'intconu'),
+    (dict(order=4, beta=-0.5, curved=0.5, warp=0.1), {}, 'gradflux'),
     (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),
 ], ids=str)
 def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
@@ -124,8 +131,9 @@ def test_navier_stokes_rhs_through_generated_kernels(emulated, kw, opts,
     for g in sysm.rhs_graphs(0, 1):
         for w, k in g.plan:
             if w == 'kernel' and getattr(k, 'kind', None) == 'gradflux':
-                old = any(o.startswith('gradflux-') and
-                          o != 'gradflux-threads' for o in opts)
+                old = any(o.startswith('gradflux-') and o not in
+                          ('gradflux-threads', 'gradflux-split')
+                          for o in opts)
                 assert k.info['tensor'] == (not old), opts
 
 
@@ -361,7 +369,7 @@ def test_bench_script_end_to_end(emulated, monkeypatch, capsys):
                 'clocks', 'cpu_baseline'):
         assert key in line, key
 
-    assert line['launches_per_step'] == 5 and line['gpu_launches'] == 15
+    assert line['launches_per_step'] == 4 and line['gpu_launches'] == 12
     assert line['e2e']['h2d_bytes_per_step'] == 27*5*8*8
     assert set(line['roofline']) >= {'bound', 'achieved', 'peak', 'unit',
                                      'frac', 'traffic'}
@@ -391,7 +399,7 @@ def test_bench_script_with_opt_in_variants(emulated, monkeypatch, capsys,
     runpy.run_path(os.path.join(root, 'bench.py'), run_name='__main__')
 
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert line['value'] > 0 and line['launches_per_step'] == 5
+    assert line['value'] > 0 and line['launches_per_step'] == 4
     with open(kt) as f:
         kern = json.load(f)['kernels']
     assert any(k.endswith('gradflux') for k in kern)

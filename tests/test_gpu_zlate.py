@@ -351,6 +351,9 @@ def test_vectorised_gradflux_phases_match_oracle(built, case, n, kw, opts):
 # the measured alternatives of DESIGN.md section 3 beside them)
 VARIANT_REPORT = [
     ('default', []),
+    ('intconu as its own launch', ['conu-fold=0']),
+    ('gradflux on whole blocks', ['gradflux-split=0']),
+    ('start of round 2 (r02c)', ['conu-fold=0', 'gradflux-split=0']),
     ('table-driven gradflux', ['gradflux-tensor=0']),
     ('host order of interface points', ['kernel-order=host']),
     ('round-1 path', ['gradflux-tensor=0', 'kernel-order=host']),

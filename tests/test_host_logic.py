@@ -281,12 +281,58 @@ def _dry_plan(case, n, opts={}, nparts=1, **kw):
                 for g in s.rhs_graphs(0, 1)]
 
 
-def test_b200_ns_rhs_is_five_launches(built):
+def test_b200_ns_rhs_is_four_launches(built):
+    """disu; the element kernel (which gathers the common solution itself:
+    the interior intconu of the first graph is folded into it); the common
+    flux; the correction with negdivconf."""
     be, plan = _dry_plan('tgv', 2, order=4)
+    kinds = [[k for w, k in g] for g in plan]
+
+    assert kinds == [['mul'], ['gradflux', None], ['mul+negdivconf']]
+
+    # without the fold: five, intconu storing both sides (no copy_fpts)
+    be, plan = _dry_plan('tgv', 2, {'conu-fold': 0}, order=4)
     kinds = [[k for w, k in g] for g in plan]
 
     assert kinds == [['mul', 'intconu'], ['gradflux', None],
                      ['mul+negdivconf']]
+
+    # a central LDG flux averages the two traces: nothing to fold
+    be, plan = _dry_plan('tgv', 2, order=4, beta=0.0)
+    assert [k for w, k in plan[0]] == ['mul', 'intconu']
+
+
+def test_conu_fold_gather_indices(built):
+    """The index table the folded element kernel gathers through: every
+    flux point of every element names the entry of scal_fpts that the
+    reference's intconu would have copied into it -- for ldg-beta = +1/2
+    the right-hand trace of its interface."""
+    from pyfr_b200.backend import B200Backend
+
+    for beta in (0.5, -0.5):
+        cfg, box = cases.make('tgv', (3, 2, 2), order=2, beta=beta)
+        be = B200Backend(cfg, dry=True)
+        s = get_system(be, box.local_mesh(), cfg, 2)
+        g0, g1, g2 = s.rhs_graphs(0, 1)
+
+        conu, = g0.folded
+        gf, = [k for w, k in g1.plan if w == 'kernel' and k.kind == 'gradflux']
+        assert gf.info['gather'] and conu.kind == 'intconu'
+
+        i = conu.info
+        S = i['ulin']._mats[0]
+        gidx = gf.info['gidx'].get().ravel()
+
+        # every point is covered exactly once (periodic mesh: no
+        # boundaries; the padding elements of the last block read their
+        # own entries), sources are the views of the side beta selects
+        gidx = gidx.reshape(S.nblocks, S.nrow, be.csubsz)
+        live = np.arange(S.nblocks*be.csubsz).reshape(-1, be.csubsz) < 12
+        assert (gidx[live[:, None, :].repeat(S.nrow, 1)] >= 0).all()
+        assert (gidx[~live[:, None, :].repeat(S.nrow, 1)] == -1).all()
+        src = (i['urin'] if beta > 0 else i['ulin']).mapping.get()[0]
+        src = src - S.offset // S.itemsize
+        assert sorted(gidx[gidx >= 0]) == sorted(np.concatenate([src, src]))
 
 
 def test_b200_unfused_plan_keeps_reference_decomposition(built):
@@ -341,7 +387,10 @@ def test_b200_dead_gradient_rows(built, beta, dead):
 
     nu, nf, LD, nb = 27, 54, 5*be.csubsz, -(-27 // be.csubsz)
     full = (2*nu + nf + 3*nf)*LD*nb*8
-    assert gf.traffic == (full - 3*(nf // 2)*LD*nb*8 if dead else full)
+    # (folded common solution: + one 32-bit index per flux point)
+    idx = nf*be.csubsz*nb*4 if gf.info['gather'] else 0
+    assert gf.info['gather'] == dead
+    assert gf.traffic == (full - 3*(nf // 2)*LD*nb*8 if dead else full) + idx
 
 
 @pytest.mark.parametrize('rs', ['rusanov', 'hllc'])
@@ -401,12 +450,21 @@ def test_b200_boundary_plan(built):
                                  {'ylo': 'no-slp-adia-wall',
                                   'yhi': 'char-riem-inv'}, order=2)
     s = get_system(B200Backend(cfg, dry=True), box.local_mesh(), cfg, 2)
+    graphs = s.rhs_graphs(0, 1)
     kinds = [[getattr(k, 'kind', None) for w, k in g.plan if w == 'kernel']
-             for g in s.rhs_graphs(0, 1)]
+             for g in graphs]
 
-    assert kinds == [['mul', 'intconu', 'bcconu', 'bcconu'],
+    # (the interior intconu is folded into gradflux, which takes the
+    # boundary points' common values from where bcconu stored them)
+    assert kinds == [['mul', 'bcconu', 'bcconu'],
                      ['gradflux', None, 'bccflux', 'bccflux'],
                      ['mul+negdivconf']]
+
+    gf = graphs[1].plan[0][1]
+    gidx = gf.info['gidx'].get().reshape(3, 54, 8)
+    nbc = 2*3*2*9                      # faces on ylo + yhi, points per face
+    npad = 6*54                        # 18 elements in three blocks of 8
+    assert (gidx < 0).sum() == nbc + npad
 
 
 def test_unknown_boundary_type_is_refused():
@@ -467,6 +525,7 @@ def test_address_order_of_interface_points(case, n, kw):
     for order in ('reference', 'address'):
         cfg, box = cases.make(case, n, **kw)
         cfg.set('backend-b200', 'inters-order', order)
+        cfg.set('backend-b200', 'conu-fold', 0)
         be = B200Backend(cfg, dry=True)
         sysm = get_system(be, box.local_mesh(), cfg, 2)
         conu, = [k for g in sysm.rhs_graphs(0, 1) for w, k in g.plan
@@ -519,7 +578,8 @@ def test_interface_kernels_order_their_points_privately():
     sees no difference."""
     maps = {}
     for order in ('host', 'address'):
-        be, sysm = _dry_system('tgv', (4, 3, 3), {'kernel-order': order},
+        be, sysm = _dry_system('tgv', (4, 3, 3), {'kernel-order': order,
+                                                  'conu-fold': 0},
                                order=2, warp=0.1)
         conu, = [k for k in _plan_kernels(sysm) if k.kind == 'intconu']
         v = conu.info['ulin']
