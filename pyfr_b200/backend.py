@@ -195,12 +195,18 @@ class B200Backend(base.BaseBackend):
         # interior common solution (|ldg-beta| = 1/2) gathered by the
         # element kernel: no intconu launch (fusion.conu_fold_plan)
         self.conu_fold = cfg.getbool(sect, 'conu-fold', True)
+        # ... whole flux-point rows by bulk copy where their points come
+        # from one row of the trace matrix
+        self.gather_rows = cfg.getbool(sect, 'gather-rows', True)
         # element kernel on half blocks, two CTAs per SM, where a whole
         # block fills the shared memory (tensor-product kernel)
         # (measured a loss with per-thread copies in place of the bulk
         # copy: 0.275 -> 0.281 ms at 32^3, r02n; off)
         self.gradflux_split = cfg.getbool(sect, 'gradflux-split', False)
         self.last_committed = None
+        # partitioned meshes: the element kernel split into boundary and
+        # interior blocks, the latter behind the exchange of the traces
+        self.gradflux_overlap = cfg.getbool(sect, 'gradflux-overlap', True)
 
         # Compute stream, communication stream and fork/join events
         self.stream = rt.new_ptr(rt.stream_create)

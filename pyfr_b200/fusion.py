@@ -162,8 +162,15 @@ def conu_fold_plan(be, C):
         return None
 
     # On a partitioned mesh intconu is what the exchange of the traces
-    # (issued by the same graph) overlaps with: it stays
-    if any(w == 'xchg' for w, o in g.program):
+    # (issued by the same graph) overlaps with.  It can still go if the
+    # element kernel takes its place: split into the blocks that touch a
+    # partition boundary -- they need the halo, ``mpiconu`` stores their
+    # common values in the present graph -- and the rest, which moves into
+    # the earlier graph behind the exchange (``bnd`` below)
+    overlap = any(w == 'xchg' for w, o in g.program)
+    cur = getattr(be, '_fusing', None)
+    if overlap and (not getattr(be, 'gradflux_overlap', True) or
+                    cur is None):
         return None
 
     ks = [k for w, k in g.program
@@ -216,13 +223,49 @@ def conu_fold_plan(be, C):
 
         gidx[blk, row*csub + e] = src
 
-    return dict(graph=g, kernel=k, sfp=S, gidx=gidx)
+    # Rows whose csub points come from one row of the trace matrix, in
+    # order: a single contiguous run (column 0 of a row, csub entries per
+    # variable as in the destination).  rowd[block, row] = its offset, or
+    # -1; rowd[block, nf] = how many such rows the block has
+    g3 = gidx.reshape(nblocks, nf, csub)
+    whole = ((g3[:, :, :1] >= 0) & (g3[:, :, :1] % LD == 0) &
+             (g3 == g3[:, :, :1] + np.arange(csub))).all(axis=2)
+    rowd = np.where(whole, g3[:, :, 0], -1).astype(np.int32)
+    rowd = np.concatenate([rowd, whole.sum(axis=1, dtype=np.int32)[:, None]],
+                          axis=1)
+
+    bnd = None
+    if overlap:
+        mk = [o for w, o in cur.program
+              if w == 'kernel' and getattr(o, 'kind', None) == 'mpiconu']
+        if not mk:
+            return None
+
+        bnd = np.zeros(nblocks, dtype=bool)
+        for o in mk:
+            v = o.info['ulout']
+            v = getattr(v, 'view', v)
+            d = v.mapping.get()[0].astype(np.int64) - VF.offset // isz
+            if len(v._mats) != 1 or _root(v._mats[0]) is not VF or \
+               (len(d) and (d.min() < 0 or d.max() >= VF.blocksz*nblocks)):
+                return None
+            bnd[d // VF.blocksz] = True
+
+        # (worth it only if most of the kernel can run behind the exchange)
+        if bnd.mean() > 0.5:
+            return None
+
+    return dict(graph=g, kernel=k, sfp=S, gidx=gidx, rowd=rowd, whole=whole,
+                bnd=bnd)
 
 
-def apply_conu_fold(plan):
-    """Drops the folded ``intconu`` from the graph that held it."""
+def apply_conu_fold(plan, moved=()):
+    """Drops the folded ``intconu`` from the graph that held it; ``moved``:
+    kernels of the present graph that run at the end of that one instead
+    (behind its exchange)."""
     g, k = plan['graph'], plan['kernel']
     g.program = [(w, o) for w, o in g.program if o is not k]
+    g.program += [('kernel', m) for m in moved]
     g._plan()
     g.folded = getattr(g, 'folded', []) + [k]
 
@@ -286,7 +329,10 @@ def fuse_gradflux(be, kerns, subs):
     # The common solution gathered by the element kernel itself (all
     # regions of the element type or none)
     fold = conu_fold_plan(be, C) if be.gradflux_tensor else None
-    fold_gidx = None
+    fold_gidx = fold_rowd = None
+    moved = []
+    if fold is not None and fold['bnd'] is not None and len(g4) != 1:
+        fold = None
 
     # Dead-store elimination on vect_fpts
     rneed = row_need_classes(be, VF, nf, VF.nblocks) if be.dead_rows else None
@@ -317,7 +363,8 @@ def fuse_gradflux(be, kerns, subs):
                 src, name, meta = ktensor.gradflux_tp_source(
                     be, ops, ti['tplargs'], pts, LD,
                     rowcls=None if rneed is None else rneed[0], affine=affine,
-                    gather=fold is not None
+                    gather=fold is not None,
+                    blist=fold is not None and fold['bnd'] is not None
                 )
             except kfused.NotFusable:
                 src = None
@@ -357,13 +404,22 @@ def fuse_gradflux(be, kerns, subs):
         words = meta['words_per_block']*nblocks
         if fold is not None:
             if fold_gidx is None:
-                fold_gidx = be.const_matrix(fold['gidx'].reshape(1, -1),
+                gi = fold['gidx']
+                if meta['gather_rows']:
+                    # points fetched with their whole row
+                    gi = np.where(np.repeat(fold['whole'], be.csubsz, axis=1),
+                                  -2, gi).astype(np.int32)
+                fold_gidx = be.const_matrix(gi.reshape(1, -1),
+                                            dtype=np.int32, tags={'noblock'})
+                fold_rowd = be.const_matrix(fold['rowd'].reshape(1, -1),
                                             dtype=np.int32, tags={'noblock'})
             ngp = meta['gather_points']
             gargs = [('p', fold_gidx.data + b0*ngp*4),
                      ('p', fold['sfp'].data)]
-            # (+ the index table, one 32-bit word per point)
-            words += nblocks*ngp*4 // isz
+            if meta['gather_rows']:
+                gargs.append(('p', fold_rowd.data + b0*(nf + 1)*4))
+            # (+ the index tables, one 32-bit word per point and per row)
+            words += nblocks*(ngp + nf + 1)*4 // isz
         else:
             gargs = []
         if rneed is not None:
@@ -380,7 +436,38 @@ def fuse_gradflux(be, kerns, subs):
 
         args += gargs
         if fold is not None:
-            geo = geo + [fold_gidx, fold['sfp']]
+            geo = geo + [fold_gidx, fold_rowd, fold['sfp']]
+
+        info = dict(replaces=kerns, dead_rows=rneed is not None,
+                    affine=affine, tensor=bool(meta.get('tensor')),
+                    gather=fold is not None, split=meta.get('split', 1),
+                    gidx=fold_gidx, rows=meta.get('gather_rows'),
+                    rowd=fold_rowd if fold is not None else None)
+
+        if fold is not None and fold['bnd'] is not None:
+            # Two launches over block lists, drawn dynamically: the blocks
+            # on a partition boundary (here) and the others (end of the
+            # earlier graph, behind its exchange)
+            for part, sel in (('interior', ~fold['bnd']),
+                              ('boundary', fold['bnd'])):
+                ids = np.flatnonzero(sel[b0:b0 + nblocks]).astype(np.int32)
+                if not len(ids):
+                    continue
+                bl = be.const_matrix(ids[None, :], dtype=np.int32,
+                                     tags={'noblock'})
+                sch = be.const_matrix(np.zeros((1, 2), dtype=np.int32),
+                                      dtype=np.int32, tags={'noblock'})
+                pargs = ([('i', len(ids))] + args[1:] +
+                         [('p', bl.data), ('p', sch.data)])
+                kern = B200Kernel(
+                    be, fn, (min(len(ids), be.sm_count*meta['nctas']), 1, 1),
+                    (meta['nthreads'], 1, 1), meta['smem'], pargs,
+                    mats=[U, C, VF, FOUT, G, bl, sch] + geo, misc=[meta],
+                    traffic=words*isz*len(ids)//nblocks, kind='gradflux',
+                    info=dict(info, part=part, nblocks=len(ids))
+                )
+                (moved if part == 'interior' else out).append(kern)
+            continue
 
         # (a kernel working on half blocks walks twice as many)
         ngrid = min(nblocks*meta.get('split', 1), be.sm_count*meta['nctas'])
@@ -388,15 +475,14 @@ def fuse_gradflux(be, kerns, subs):
             be, fn, (ngrid, 1, 1),
             (meta['nthreads'], 1, 1), meta['smem'], args,
             mats=[U, C, VF, FOUT, G] + geo, misc=[meta],
-            traffic=words*isz, kind='gradflux',
-            info=dict(replaces=kerns, dead_rows=rneed is not None,
-                      affine=affine, tensor=bool(meta.get('tensor')),
-                      gather=fold is not None, split=meta.get('split', 1),
-                      gidx=fold_gidx)
+            traffic=words*isz, kind='gradflux', info=info
         ))
 
     if fold is not None:
-        apply_conu_fold(fold)
+        if fold['bnd'] is not None and not out:
+            # (no block touches a partition boundary: keep one launch here)
+            out, moved = moved, []
+        apply_conu_fold(fold, moved)
 
     return out
 

@@ -161,7 +161,7 @@ def tp_structure(ops, nd, tol=1e-12):
 
 
 def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
-                       affine=False, gather=False):
+                       affine=False, gather=False, blist=False):
     """Source of the sum-factorised fused kernel; arguments and return
     value as ``fused.gradflux_source``.
 
@@ -175,7 +175,15 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     partition boundary) has stored the common value (index < 0) -- with
     per-thread asynchronous copies straight into shared memory.
 
-    Half blocks (``gradflux-split``, automatic): where a whole element
+    ``blist``: the launch works through a *list* of element blocks
+    (``blist[i]``, ``nblocks`` entries) handed out dynamically -- a CTA
+    draws the position of its next block from a device counter two
+    iterations ahead.  Used where the element kernel is split into the
+    blocks that touch a partition boundary and the rest, the latter
+    running next to the halo exchange whose NCCL kernel holds some SMs for
+    part of the time: CTAs that start late simply draw fewer blocks.
+
+    Half blocks (``gradflux-split``, opt-in): where a whole element
     block fills an SM's shared memory (hexahedra, p = 4, fp64: 208 KB) the
     kernel works on half blocks instead -- the columns of ``C_SUB/2``
     elements, two co-resident CTAs of half the threads per SM -- so that
@@ -579,7 +587,8 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     geo_words = geo['geo_words']
     smem = ((nu + nf + nd*nu)*LD + geo_words)*isz + 64
     if gather:
-        smem += nf*csub*4
+        smem += (nf*csub + nf + 4)*4
+    smem += 16
     if smem > 227*1024:
         raise NotFusable(f'needs {smem} bytes of shared memory')
 
@@ -597,7 +606,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     }
 '''
         release = ('if (it == 0 && grp == 0 && gtid == 0) flag_set(flag);')
-        issue = '''if (gtid == 0 && nxt < nblk)
+        issue = '''if (gtid == 0 && more)
         {
             // the group that arrives last starts the copy
             if (atomicAdd(cnt, 1) == NG - 1)
@@ -609,25 +618,84 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     else:
         gsync = '#define GSYNC() __syncthreads()'
         hold, release = '', ''
-        issue = '''if (tid == 0 && nxt < nblk)
+        issue = '''if (tid == 0 && more)
             fetch(nxt, it + 1);'''
     rel1 = release if stagger == 1 else ''
     rel3 = release if stagger != 1 else ''
 
     from pyfr_b200.kernels.mul import _cpasync_src
 
+    if blist:
+        if SPLIT > 1 or NG > 1:
+            raise NotFusable('block lists: whole blocks, one warp group')
+        d_arg = (',\n         const int* __restrict__ blist,'
+                 '\n         int* __restrict__ sched')
+        # NB[k & 1]: the block of iteration k, drawn during iteration k - 2
+        # (ticket at the top, block number after the first barrier, stored
+        # after the third: no step waits for the one before)
+        dyn_first = '''
+    long long cur = 0;
+    int tk = 0, bid = 0;
+    if (blk < nblk)
+        cur = __ldg(blist + blk);
+    if (tid == 0)
+    {
+        tk = (int) gridDim.x + atomicAdd(sched, 1);
+        NB[1] = (tk < nblk) ? __ldg(blist + tk) : -1;
+    }
+    __syncthreads();'''
+        dyn_top = '''const long long nxt = NB[(it + 1) & 1];
+        const bool more = nxt >= 0;
+        if (tid == 0)
+            tk = (int) gridDim.x + atomicAdd(sched, 1);'''
+        dyn_p1 = '''if (tid == 0)
+            bid = (tk < nblk) ? __ldg(blist + tk) : -1;'''
+        dyn_p3 = '''if (tid == 0)
+            NB[it & 1] = bid;'''
+        dyn_next = '''if (!more)
+            break;
+        cur = nxt;'''
+        # ... the last CTA out re-arms the counters for the next launch
+        dyn_last = '''
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicAdd(sched + 1, 1) == (int) gridDim.x - 1)
+        {
+            sched[0] = 0; sched[1] = 0;
+            __threadfence();
+        }
+    }'''
+        blkid = '#define BLOCK_ID(i) ((long long) __ldg(blist + (i)))'
+    else:
+        d_arg = dyn_first = dyn_p1 = dyn_p3 = dyn_last = ''
+        dyn_top = '''const long long nxt = bq + gridDim.x;
+        const bool more = nxt < nblk;'''
+        dyn_next = 'blk = nxt;'
+        blkid = '#define BLOCK_ID(i) ((long long) (i))'
+
     split = SPLIT > 1
     nb_expr = 'nblocks*SPLIT' if split else 'nblocks'
     cpsrc = _cpasync_src if (gather or split) else ''
 
+    # Whole rows by bulk copy: where the csub points of a flux-point row
+    # take their values from one row of ``sfp`` (structured numbering:
+    # every face but those whose neighbours sit one element further on)
+    # the row is one contiguous run and a single TMA copy fetches it
+    rows = (gather and not split and nf < nthreads and
+            getattr(be, 'gather_rows', True))
+
     if gather:
         g_arg = (',\n         const int* __restrict__ gidx,'
-                 '\n         const fpdtype_t* __restrict__ sfp')
+                 '\n         const fpdtype_t* __restrict__ sfp'
+                 + (',\n         const int* __restrict__ growd'
+                    if rows else ''))
         g_lambdas = f'''
     // Common solution by gather: this thread's points of a block (point =
-    // flux-point row x element) and where each comes from.  The indices
-    // of the next block are parked in shared memory a phase ahead of the
-    // copies that need them (each thread reads back what it copied itself)
+    // flux-point row x element) and where each comes from ({"-2: fetched with its whole row; " if rows else ""}-1: the
+    // block's own ucomm entry).  The indices of the next block are parked
+    // in shared memory a phase ahead of the copies that need them (each
+    // thread reads back what it copied itself)
     auto gidx_load = [&](long long b)
     {{
         const long long rbn = b / SPLIT;
@@ -639,16 +707,26 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                 cp_async<4>(GIX + p, gidx + rbn*(NFPTS*GC_SUB)
                             + (p / C_SUB)*GC_SUB + hf*C_SUB + p % C_SUB);
         }}
+        {"""if (tid < NFPTS)
+            cp_async<4>(ROWD + tid, growd + b*(NFPTS + 1) + tid);
+        if (tid == 0)
+            cp_async<4>(ROWD + NFPTS, growd + b*(NFPTS + 1) + NFPTS);""" if rows else ""}
     }};
-    auto gather = [&](long long b)
+    auto gather = [&](long long b, unsigned n)
     {{
         const long long rbn = b / SPLIT;
         const int hf = (int) (b % SPLIT);
         cp_async_wait_all();
+        {"""// (the bulk copies of u, the vertices and ROWD[NFPTS] whole rows
+        // complete on one mbarrier)
+        if (tid == 0)
+            fetch(b, n, ROWD[NFPTS]);
+        if (tid < NFPTS && ROWD[tid] >= 0)
+            tma_load_1d(C + tid*LD, sfp + ROWD[tid], ROWB, &bars[0]);""" if rows else ""}
         UNROLL for (int r = 0; r < NGR; r++)
         {{
             const int p = tid + r*NTHREADS;
-            if (p < NGP)
+            if (p < NGP && GIX[p] != -2)
             {{
                 const int row = p / C_SUB, e = p % C_SUB, gi = GIX[p];
                 const fpdtype_t *from = (gi >= 0) ? sfp + gi
@@ -661,8 +739,8 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     }};'''
         # (the indices of the next block are fetched a phase ahead of the
         # copies that need them)
-        g_top = 'if (nxt < nblk) gidx_load(nxt);'
-        g_issue = 'if (nxt < nblk) gather(nxt);'
+        g_top = 'if (more) gidx_load(nxt);'
+        g_issue = 'if (more) gather(nxt, it + 1);'
     else:
         g_arg = g_lambdas = g_top = g_issue = ''
 
@@ -670,9 +748,9 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         g_first = ('''
     if (blk < nblk)
     {''' + ('''
-        gidx_load(blk);
-        gather(blk);''' if gather else '') + ('''
-        fetch(blk, 0);''' if split else '') + '''
+        gidx_load(BLOCK_ID(blk));
+        gather(BLOCK_ID(blk), 0);''' if gather else '') + ('''
+        fetch(BLOCK_ID(blk), 0);''' if split else '') + '''
     }
     cp_async_wait_all();
     __syncthreads();''')
@@ -700,7 +778,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                       + strided('(VSB + (n & 1)*V_WORDS)', 'verts',
                                 'verts_bsz', 'NVERTS*NDIMS'))
         first_fetch = ''
-        issue = '''if (nxt < nblk)
+        issue = '''if (more)
             fetch(nxt, it + 1);'''
         wait_tma = ''
     else:
@@ -708,12 +786,14 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             '''tma_load_1d(C, ucomm + b*ucomm_bsz, C_WORDS*sizeof(fpdtype_t),
                     &bars[0]);''')
         fetch_body = f'''mbar_expect_tx(&bars[0], ({'U_WORDS' if gather else 'U_WORDS + C_WORDS'})*sizeof(fpdtype_t)
-                                 {geo['geo_bytes']});
+                                 {geo['geo_bytes']} + nrows*ROWB);
         tma_load_1d(U, u + b*u_bsz, U_WORDS*sizeof(fpdtype_t), &bars[0]);
         {c_fetch}
         {geo['geo_fetch']}'''
-        first_fetch = '''if (tid == 0 && blk < nblk)
-        fetch(blk, 0);'''
+        first_fetch = '' if rows else '''if (tid == 0 && blk < nblk)
+        fetch(BLOCK_ID(blk), 0);'''
+        if rows:
+            issue = ''
         wait_tma = 'mbar_wait(&bars[0], it & 1);'
 
     src = f'''{ph.prologue(be.fpdtype.__name__, be.ixdtype.__name__,
@@ -727,6 +807,7 @@ typedef {vec} fpvec_t;
 {tabsrc}
 {K.decl()}
 
+{blkid}
 #define U_WORDS (NPTS*LD)
 #define C_WORDS (NFPTS*LD)
 #define G_WORDS (NDIMS*NPTS*LD)
@@ -743,7 +824,7 @@ gradflux(int nblocks, int neles,
          const fpdtype_t* ucomm, long long ucomm_bsz,
          fpdtype_t* vf, long long vf_bsz,
          fpdtype_t* __restrict__ fout, long long fout_bsz,
-         {geo['gargs']}{fm_arg}{g_arg})
+         {geo['gargs']}{fm_arg}{g_arg}{d_arg})
 {{
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fpdtype_t *U = reinterpret_cast<fpdtype_t *>(smem_raw);
@@ -753,8 +834,8 @@ gradflux(int nblocks, int neles,
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         G + G_WORDS + {geo_words});
     int *cnt = reinterpret_cast<int *>(bars + 1), *flag = cnt + 1;
-    int *GIX = cnt + 2;
-    (void) flag; (void) GIX;
+    int *NB = cnt + 2, *GIX = NB + 2, *ROWD = GIX + NGP;
+    (void) flag; (void) GIX; (void) ROWD; (void) NB;
 
     char *Ub = reinterpret_cast<char *>(U);
     char *Cb = reinterpret_cast<char *>(C);
@@ -784,7 +865,7 @@ gradflux(int nblocks, int neles,
     }}
     __syncthreads();
 
-    auto fetch = [&](long long b, unsigned n)
+    auto fetch = [&](long long b, unsigned n, int nrows = 0)
     {{
         {fetch_body}
     }};
@@ -793,16 +874,17 @@ gradflux(int nblocks, int neles,
     // (half) blocks of this launch
     const long long nblk = {nb_expr};
     long long blk = blockIdx.x;
+{dyn_first}
     {first_fetch}
 {g_first}
 {hold}
-    for (unsigned it = 0; blk < nblk; blk += gridDim.x, it++)
+    for (unsigned it = 0; blk < nblk; it++)
     {{
         // (block pointers are formed from the block number every time:
         // kept as induction variables they cost a dozen registers)
-        long long bq = blk;
+        long long bq = {'blk' if not blist else 'cur'};
         OPAQUE64(bq);
-        const long long nxt = bq + gridDim.x;
+        {dyn_top}
         // storage block and which half of its columns
         const long long rb = bq / SPLIT;
         const long long hoff = (bq % SPLIT)*C_SUB;
@@ -838,6 +920,7 @@ gradflux(int nblocks, int neles,
         // phases
         {issue}
         {g_issue}
+        {dyn_p1}
 {p2}
         // ---- phase 3: gradients at the flux points -> HBM ---------------
         {{
@@ -846,6 +929,7 @@ gradflux(int nblocks, int neles,
         }}
         GSYNC();
         {rel3}
+        {dyn_p3}
 
         // ---- phase 4: transformed flux (in place over the gradient) -----
 {geo['geo_post']}
@@ -879,13 +963,16 @@ gradflux(int nblocks, int neles,
         {p5}
         {g_wait}
         GSYNC();
+        {dyn_next}
     }}
+{dyn_last}
 }}
 '''
     if nctas*(smem + 1024) > 227*1024:
         nctas = 1
     meta = dict(nthreads=nthreads, smem=smem, nctas=nctas, ngroups=NG,
                 words_per_block=(2*nu + nf + nd*nf)*GLD, tensor=True,
-                gather=gather, gather_points=nf*gcsub, split=SPLIT)
+                gather=gather, gather_points=nf*gcsub, split=SPLIT,
+                gather_rows=bool(rows), blist=bool(blist))
 
     return src, 'gradflux', meta

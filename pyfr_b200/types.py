@@ -161,6 +161,10 @@ class B200Graph(base.Graph):
         if not be.fuse:
             return
 
+        # (the graph being planned, for rewrites that look at its other
+        # kernels: fusion.conu_fold_plan)
+        be._fusing = self
+
         for kerns, subs in getattr(self, '_fgroups', []):
             new = fusion.fuse_group(be, kerns, subs)
             if not new and kerns and \

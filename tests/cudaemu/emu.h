@@ -167,7 +167,11 @@ static inline void mbar_init(unsigned long long *bar, unsigned n)
 
 static inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
-    reinterpret_cast<EmuMbar *>(bar)->pending.fetch_add(bytes);
+    // (copies issued by other threads may have completed already: the
+    // byte count runs negative until the expectation arrives)
+    EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    if (b->pending.fetch_add(bytes) + bytes == 0)
+        b->completed.fetch_add(1, std::memory_order_release);
 }
 
 static inline void mbar_wait(unsigned long long *bar, unsigned parity)

@@ -309,8 +309,9 @@ def test_conu_fold_gather_indices(built):
     the right-hand trace of its interface."""
     from pyfr_b200.backend import B200Backend
 
-    for beta in (0.5, -0.5):
+    for beta, rows in ((0.5, 0), (-0.5, 0), (0.5, 1)):
         cfg, box = cases.make('tgv', (3, 2, 2), order=2, beta=beta)
+        cfg.set('backend-b200', 'gather-rows', rows)
         be = B200Backend(cfg, dry=True)
         s = get_system(be, box.local_mesh(), cfg, 2)
         g0, g1, g2 = s.rhs_graphs(0, 1)
@@ -321,17 +322,31 @@ def test_conu_fold_gather_indices(built):
 
         i = conu.info
         S = i['ulin']._mats[0]
-        gidx = gf.info['gidx'].get().ravel()
+        csub, nf, nb = be.csubsz, S.nrow, S.nblocks
+        gidx = gf.info['gidx'].get().reshape(nb, nf, csub)
+        src = (i['urin'] if beta > 0 else i['ulin']).mapping.get()[0]
+        src = src - S.offset // S.itemsize
+
+        if rows:
+            # Whole rows (their points marked -2) go by one bulk copy from
+            # rowd[block, row]: put the points back and the table must be
+            # the per-point one
+            rowd = gf.info['rowd'].get().reshape(nb, nf + 1)
+            whole = rowd[:, :nf] >= 0
+            assert whole.any() and not whole.all()
+            assert np.array_equal(whole.sum(axis=1), rowd[:, nf])
+            assert np.array_equal((gidx == -2).all(axis=2), whole)
+            assert np.array_equal((gidx == -2).any(axis=2), whole)
+            assert (rowd[:, :nf][whole] % S.leaddim == 0).all()
+            gidx = np.where(whole[:, :, None],
+                            rowd[:, :nf, None] + np.arange(csub), gidx)
 
         # every point is covered exactly once (periodic mesh: no
         # boundaries; the padding elements of the last block read their
         # own entries), sources are the views of the side beta selects
-        gidx = gidx.reshape(S.nblocks, S.nrow, be.csubsz)
-        live = np.arange(S.nblocks*be.csubsz).reshape(-1, be.csubsz) < 12
-        assert (gidx[live[:, None, :].repeat(S.nrow, 1)] >= 0).all()
-        assert (gidx[~live[:, None, :].repeat(S.nrow, 1)] == -1).all()
-        src = (i['urin'] if beta > 0 else i['ulin']).mapping.get()[0]
-        src = src - S.offset // S.itemsize
+        live = np.arange(nb*csub).reshape(-1, csub) < 12
+        live = live[:, None, :].repeat(nf, 1)
+        assert (gidx[live] >= 0).all() and (gidx[~live] == -1).all()
         assert sorted(gidx[gidx >= 0]) == sorted(np.concatenate([src, src]))
 
 
@@ -388,7 +403,7 @@ def test_b200_dead_gradient_rows(built, beta, dead):
     nu, nf, LD, nb = 27, 54, 5*be.csubsz, -(-27 // be.csubsz)
     full = (2*nu + nf + 3*nf)*LD*nb*8
     # (folded common solution: + one 32-bit index per flux point)
-    idx = nf*be.csubsz*nb*4 if gf.info['gather'] else 0
+    idx = (nf*be.csubsz + nf + 1)*nb*4 if gf.info['gather'] else 0
     assert gf.info['gather'] == dead
     assert gf.traffic == (full - 3*(nf // 2)*LD*nb*8 if dead else full) + idx
 
@@ -464,7 +479,7 @@ def test_b200_boundary_plan(built):
     gidx = gf.info['gidx'].get().reshape(3, 54, 8)
     nbc = 2*3*2*9                      # faces on ylo + yhi, points per face
     npad = 6*54                        # 18 elements in three blocks of 8
-    assert (gidx < 0).sum() == nbc + npad
+    assert (gidx == -1).sum() == nbc + npad
 
 
 def test_unknown_boundary_type_is_refused():
