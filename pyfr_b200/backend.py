@@ -101,7 +101,9 @@ class B200Backend(base.BaseBackend):
             raise RuntimeError('The b200 backend targets sm_100a only; found '
                                f'compute capability {info["cc"]}')
 
-        self.sm_count = info['sm_count']
+        # (persistent kernels launch one CTA, or CTA pair, per SM; `sm-count`
+        # restricts them to fewer -- a test and tuning knob)
+        self.sm_count = cfg.getint(sect, 'sm-count', info['sm_count'])
         self.smem_budget = min(info['smem_optin'], 227*1024) - 8*1024
 
         # Storage layout: 64-byte SoA rows (two 32-byte sectors), one SoA

@@ -251,8 +251,10 @@ def conu_fold_plan(be, C):
                 return None
             bnd[d // VF.blocksz] = True
 
-        # (worth it only if most of the kernel can run behind the exchange)
-        if bnd.mean() > 0.5:
+        # (worth it only if most of the kernel can run behind the exchange;
+        # the boundary launch takes the range of blocks up to the last one
+        # on a partition boundary)
+        if (np.flatnonzero(bnd).max() + 1) > 0.5*nblocks:
             return None
 
     return dict(graph=g, kernel=k, sfp=S, gidx=gidx, rowd=rowd, whole=whole,
@@ -445,26 +447,44 @@ def fuse_gradflux(be, kerns, subs):
                     rowd=fold_rowd if fold is not None else None)
 
         if fold is not None and fold['bnd'] is not None:
-            # Two launches over block lists, drawn dynamically: the blocks
-            # on a partition boundary (here) and the others (end of the
-            # earlier graph, behind its exchange)
-            for part, sel in (('interior', ~fold['bnd']),
-                              ('boundary', fold['bnd'])):
-                ids = np.flatnonzero(sel[b0:b0 + nblocks]).astype(np.int32)
-                if not len(ids):
+            # Two launches over block ranges, blocks drawn dynamically:
+            # [0, nbb) holds every block on a partition boundary (those
+            # elements come first in a partition, ``pyfr/partitioners/
+            # base.py:286-290``) and runs here; the rest runs at the end of
+            # the earlier graph, behind its exchange
+            nbb = int(np.flatnonzero(fold['bnd'][b0:b0 + nblocks]).max()) + 1
+            for part, lo, hi in (('interior', nbb, nblocks),
+                                 ('boundary', 0, nbb)):
+                if hi <= lo:
                     continue
-                bl = be.const_matrix(ids[None, :], dtype=np.int32,
-                                     tags={'noblock'})
                 sch = be.const_matrix(np.zeros((1, 2), dtype=np.int32),
                                       dtype=np.int32, tags={'noblock'})
-                pargs = ([('i', len(ids))] + args[1:] +
-                         [('p', bl.data), ('p', sch.data)])
+
+                # block-indexed arguments start at block lo
+                pargs, step = [('i', hi - lo),
+                               ('i', neles - lo*be.csubsz)], None
+                for (c, v), nxt in zip(args[2:], args[3:] + [(None, 0)]):
+                    if c == 'p' and nxt[0] == 'l':
+                        v += lo*nxt[1]*isz
+                    pargs.append((c, v))
+                # (fmask, gidx, growd: one entry / NGP / nf + 1 per block)
+                tail = []
+                if rneed is not None:
+                    tail.append(('p', fm.data + lo*4))
+                tail.append(('p', gargs[0][1] + lo*ngp*4))
+                tail.append(gargs[1])
+                if meta['gather_rows']:
+                    tail.append(('p', gargs[2][1] + lo*(nf + 1)*4))
+                pargs = pargs[:len(pargs) - len(tail)] + tail
+                pargs.append(('p', sch.data))
+
                 kern = B200Kernel(
-                    be, fn, (min(len(ids), be.sm_count*meta['nctas']), 1, 1),
+                    be, fn, (min(-(-(hi - lo) // meta['chunk']),
+                                 be.sm_count*meta['nctas']), 1, 1),
                     (meta['nthreads'], 1, 1), meta['smem'], pargs,
-                    mats=[U, C, VF, FOUT, G, bl, sch] + geo, misc=[meta],
-                    traffic=words*isz*len(ids)//nblocks, kind='gradflux',
-                    info=dict(info, part=part, nblocks=len(ids))
+                    mats=[U, C, VF, FOUT, G, sch] + geo, misc=[meta],
+                    traffic=words*isz*(hi - lo)//nblocks, kind='gradflux',
+                    info=dict(info, part=part, nblocks=hi - lo)
                 )
                 (moved if part == 'interior' else out).append(kern)
             continue

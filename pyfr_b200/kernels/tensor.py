@@ -175,13 +175,13 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     partition boundary) has stored the common value (index < 0) -- with
     per-thread asynchronous copies straight into shared memory.
 
-    ``blist``: the launch works through a *list* of element blocks
-    (``blist[i]``, ``nblocks`` entries) handed out dynamically -- a CTA
-    draws the position of its next block from a device counter two
-    iterations ahead.  Used where the element kernel is split into the
-    blocks that touch a partition boundary and the rest, the latter
-    running next to the halo exchange whose NCCL kernel holds some SMs for
-    part of the time: CTAs that start late simply draw fewer blocks.
+    ``blist``: the blocks of the launch are handed out dynamically -- a
+    CTA draws its next block from a device counter (``sched``) two
+    iterations ahead, the last CTA to finish re-arms the counter.  Used
+    where the element kernel is split into the blocks that touch a
+    partition boundary and the rest, the latter running next to the halo
+    exchange whose NCCL kernel holds some SMs for part of the time: CTAs
+    that start late simply draw fewer blocks.
 
     Half blocks (``gradflux-split``, opt-in): where a whole element
     block fills an SM's shared memory (hexahedra, p = 4, fp64: 208 KB) the
@@ -627,34 +627,43 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
 
     if blist:
         if SPLIT > 1 or NG > 1:
-            raise NotFusable('block lists: whole blocks, one warp group')
-        d_arg = (',\n         const int* __restrict__ blist,'
-                 '\n         int* __restrict__ sched')
-        # NB[k & 1]: the block of iteration k, drawn during iteration k - 2
-        # (ticket at the top, block number after the first barrier, stored
-        # after the third: no step waits for the one before)
+            raise NotFusable('dynamic blocks: whole blocks, one warp group')
+        d_arg = ',\n         int* __restrict__ sched'
+        # Blocks are drawn in chunks of DCH consecutive ones: chunk c of
+        # the first gridDim.x belongs to CTA c, further chunks go to
+        # whoever asks first.  NB[k & 1] holds the block of iteration k,
+        # found during iteration k - 2; the ticket is drawn at the top of
+        # that iteration and first touched after its first barrier (the
+        # compiler parks it in local memory at once -- the kernel is at
+        # its register limit -- which stalls warp 0 for the atomic's round
+        # trip: 10 % of the kernel with one ticket per block, r02p2; hence
+        # the chunks)
+        DCH = 4
+        defs.append(('DCH', DCH))
         dyn_first = '''
-    long long cur = 0;
-    int tk = 0, bid = 0;
-    if (blk < nblk)
-        cur = __ldg(blist + blk);
+    int tk = 0;
+    blk = (long long) blockIdx.x*DCH;
     if (tid == 0)
     {
-        tk = (int) gridDim.x + atomicAdd(sched, 1);
-        NB[1] = (tk < nblk) ? __ldg(blist + tk) : -1;
+        long long b1 = blk + 1;
+        if (DCH == 1)
+            b1 = (long long) (atomicAdd(sched, 1) + (int) gridDim.x)*DCH;
+        NB[1] = (b1 < nblk) ? (int) b1 : -1;
     }
     __syncthreads();'''
-        dyn_top = '''const long long nxt = NB[(it + 1) & 1];
+        dyn_top = '''const int nxt = NB[(it + 1) & 1];
         const bool more = nxt >= 0;
-        if (tid == 0)
-            tk = (int) gridDim.x + atomicAdd(sched, 1);'''
+        const bool draw = more && (nxt + 1) % DCH == 0;
+        if (tid == 0 && draw)
+            tk = atomicAdd(sched, 1);'''
         dyn_p1 = '''if (tid == 0)
-            bid = (tk < nblk) ? __ldg(blist + tk) : -1;'''
-        dyn_p3 = '''if (tid == 0)
-            NB[it & 1] = bid;'''
-        dyn_next = '''if (!more)
-            break;
-        cur = nxt;'''
+        {
+            long long b2 = draw ? (long long) (tk + (int) gridDim.x)*DCH
+                                : nxt + 1;
+            NB[it & 1] = (more && b2 < nblk) ? (int) b2 : -1;
+        }'''
+        dyn_p3 = ''
+        dyn_next = 'blk = more ? nxt : nblk;'
         # ... the last CTA out re-arms the counters for the next launch
         dyn_last = '''
     if (tid == 0)
@@ -666,13 +675,12 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
             __threadfence();
         }
     }'''
-        blkid = '#define BLOCK_ID(i) ((long long) __ldg(blist + (i)))'
     else:
         d_arg = dyn_first = dyn_p1 = dyn_p3 = dyn_last = ''
         dyn_top = '''const long long nxt = bq + gridDim.x;
         const bool more = nxt < nblk;'''
         dyn_next = 'blk = nxt;'
-        blkid = '#define BLOCK_ID(i) ((long long) (i))'
+    blkid = '#define BLOCK_ID(i) ((long long) (i))'
 
     split = SPLIT > 1
     nb_expr = 'nblocks*SPLIT' if split else 'nblocks'
@@ -882,7 +890,7 @@ gradflux(int nblocks, int neles,
     {{
         // (block pointers are formed from the block number every time:
         // kept as induction variables they cost a dozen registers)
-        long long bq = {'blk' if not blist else 'cur'};
+        long long bq = blk;
         OPAQUE64(bq);
         {dyn_top}
         // storage block and which half of its columns
@@ -973,6 +981,7 @@ gradflux(int nblocks, int neles,
     meta = dict(nthreads=nthreads, smem=smem, nctas=nctas, ngroups=NG,
                 words_per_block=(2*nu + nf + nd*nf)*GLD, tensor=True,
                 gather=gather, gather_points=nf*gcsub, split=SPLIT,
-                gather_rows=bool(rows), blist=bool(blist))
+                gather_rows=bool(rows), blist=bool(blist),
+                chunk=DCH if blist else 1)
 
     return src, 'gradflux', meta

@@ -53,6 +53,11 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 // ---- atomics / bit casts -------------------------------------------------------
 static std::mutex emu_atomic_mutex;
 
+static inline void __threadfence()
+{
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+}
+
 template <class T> static inline T atomicAdd(T *p, T v)
 {
     std::lock_guard<std::mutex> lk(emu_atomic_mutex);

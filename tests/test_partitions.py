@@ -66,6 +66,11 @@ CASES = [
      dict(order=3, beta=0.0, rsolver='hllc')),
     ('tgv', (5, 4, 3), 'conn_hex_periodic_3parts',
      dict(order=2, beta=-0.5, warp=0.1)),
+    # long enough in x for element blocks without a partition-boundary
+    # face: the element kernel runs as an interior launch (first graph,
+    # behind the exchange of the traces) and a boundary launch
+    ('tgv', (64, 2, 2), _brick((2, 1, 1)), dict(order=2, warp=0.05)),
+    ('tgv', (64, 2, 2), _brick((2, 1, 1)), dict(order=2, beta=-0.5)),
     ('vortex', 12, _brick((2, 1)), dict(order=3)),
     ('vortex', 12, _brick((2, 2)), dict(order=2, rsolver='hllc')),
 ]
@@ -117,6 +122,11 @@ def test_partitioned_rhs_matches_partitioned_oracle(substrate, case, n, part,
     vparts = _fixture_parts(part) if isinstance(part, str) else part(box)
     nparts = int(vparts.max()) + 1
 
+    if n == (64, 2, 2):
+        # fewer CTAs than chunks of blocks: the interior launch hands out
+        # blocks dynamically (and must re-arm its counter for the replay)
+        opts['sm-count'] = 3
+
     world, systems = _b200_systems(case, n, vparts, nparts, kw, opts)
 
     # Twice: the second evaluation replays the captured graphs and finds
@@ -147,6 +157,16 @@ def test_partitioned_rhs_matches_partitioned_oracle(substrate, case, n, part,
         # (pack: once for the solution, once for the gradients)
         assert kinds.count('mpicflux') <= 2 and kinds.count('pack') <= 2
         assert kinds.count('mpiconu') <= 2
+
+        if n == (64, 2, 2):
+            g0, g1, _ = s.rhs_graphs(0, 1)
+            parts = [[k.info.get('part') for w, k in g.plan
+                      if w == 'kernel' and k.kind == 'gradflux']
+                     for g in (g0, g1)]
+            assert parts == [['interior'], ['boundary']]
+            assert 'intconu' not in kinds
+            # ... which follows the exchange of its graph
+            assert [w for w, k in g0.plan][-2:] == ['xchg', 'kernel']
 
     # The partitioned discretisation differs from the single-partition one
     # exactly when the LDG flux is one-sided (a check that the test would
