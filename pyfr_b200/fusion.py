@@ -157,6 +157,11 @@ def conu_fold_plan(be, C):
     if not getattr(be, 'conu_fold', True):
         return None
 
+    # (a flux-point row of one variable must be worth a copy: 16-byte rows
+    # -- fp32 at n-soa = 4 -- were a loss, p = 6: 10.8 + 2.2 -> 16.3 ms, r02q)
+    if be.csubsz*C.itemsize < 32:
+        return None
+
     g = be.last_committed() if getattr(be, 'last_committed', None) else None
     if g is None or getattr(g, 'started', False):
         return None
@@ -579,7 +584,11 @@ def fuse_tdivtconf_negdivconf(be, kerns, subs):
     else:
         src, name, meta = kmul.mul_source(
             be, im['A'], LD, im['alpha'], im['beta'],
-            smem_budget=be.smem_budget, rowgroups=be.mul_rowgroups or 8,
+            # (eight row groups where the blocks are a full warp wide; on
+            # narrow blocks they cost the second CTA per SM: p = 6 fp32 at
+            # n-soa = 4, 4.4 -> 9.5 ms, r02q)
+            smem_budget=be.smem_budget,
+            rowgroups=be.mul_rowgroups or (8 if LD >= 32 else 4),
             negdiv_nvars=nv, rk=rk
         )
         ngrid = min(nblocks, be.sm_count*meta['nctas'])

@@ -389,7 +389,11 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     # store into G may alias the next item's loads -- and without it a warp
     # alternates between waiting for shared memory and using the FP64
     # pipe (SASS of r02c: LDS x7, DFMA x70, STS x5 per direction).
-    swp = getattr(be, 'gradflux_swp', True)
+    # (only where the loads of two work items fit the register file: at
+    # p = 6 in fp32 -- nine float4 per item, three rounds -- the pipelined
+    # form spills 112 bytes and runs 14.5 instead of 10.8 ms, r02s)
+    swp = (getattr(be, 'gradflux_swp', True) and R == 1 and
+           (n1 + 2)*NC*isz // 4 <= 28)
 
     def pipelined(items):
         """``items``: (condition, declarations, load lines, compute lines,
@@ -744,10 +748,16 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
                     cp_async<{isz}>(to + v*C_SUB, from + v*GC_SUB);
             }}
         }}
+        {"""// this thread's index slots are free again: the indices of the
+        // block after b go in now, a whole iteration ahead of their use
+        // (ncu r02q: fetched one phase ahead, 5 % of the kernel's stall
+        // samples were this wait)
+        if (b + gridDim.x < (long long) nblocks*SPLIT)
+            gidx_load(b + gridDim.x);""" if not blist else ""}
     }};'''
-        # (the indices of the next block are fetched a phase ahead of the
-        # copies that need them)
-        g_top = 'if (more) gidx_load(nxt);'
+        # (dynamic blocks: the block after the next one is not known yet;
+        # its indices are fetched at the top of the next iteration)
+        g_top = 'if (more) gidx_load(nxt);' if blist else ''
         g_issue = 'if (more) gather(nxt, it + 1);'
     else:
         g_arg = g_lambdas = g_top = g_issue = ''
