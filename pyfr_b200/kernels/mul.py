@@ -139,6 +139,14 @@ __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
+
+// ... or, without waiting: one arrival on an mbarrier once they have (the
+// barrier's count includes these arrivals: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
 '''
 
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -163,11 +164,19 @@ static_assert(sizeof(EmuMbar) == 8, "mbarrier slot");
 
 static inline unsigned smem_u32(const void *p) { return 0; }
 
+// Arrivals a phase expects beyond the one that carries the byte count
+// (``mbar_init(bar, 1 + k)``: k threads signal the completion of their
+// cp.async copies); modelled as k further bytes
+static std::mutex emu_mbar_mutex;
+static std::map<const void *, unsigned> emu_mbar_extra;
+
 static inline void mbar_init(unsigned long long *bar, unsigned n)
 {
     EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
     b->completed.store(0);
     b->pending.store(0);
+    std::lock_guard<std::mutex> lk(emu_mbar_mutex);
+    emu_mbar_extra[bar] = n - 1;
 }
 
 static inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
@@ -175,6 +184,10 @@ static inline void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
     // (copies issued by other threads may have completed already: the
     // byte count runs negative until the expectation arrives)
     EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    {
+        std::lock_guard<std::mutex> lk(emu_mbar_mutex);
+        bytes += emu_mbar_extra[bar];
+    }
     if (b->pending.fetch_add(bytes) + bytes == 0)
         b->completed.fetch_add(1, std::memory_order_release);
 }
@@ -208,6 +221,18 @@ static inline void cp_async16(void *dst, const void *src)
 }
 
 static inline void cp_async_wait_all() {}
+
+// All of this thread's copies so far have landed (they are executed at
+// once here): one arrival on the barrier
+static inline void cp_async_mbar_arrive(unsigned long long *bar);
+
+
+static inline void cp_async_mbar_arrive(unsigned long long *bar)
+{
+    EmuMbar *b = reinterpret_cast<EmuMbar *>(bar);
+    if (b->pending.fetch_sub(1) == 1)
+        b->completed.fetch_add(1, std::memory_order_release);
+}
 
 // ---- launcher -----------------------------------------------------------------
 template <class F>
