@@ -371,7 +371,7 @@ def fuse_gradflux(be, kerns, subs):
                     be, ops, ti['tplargs'], pts, LD,
                     rowcls=None if rneed is None else rneed[0], affine=affine,
                     gather=fold is not None,
-                    blist=fold is not None and fold['bnd'] is not None
+                    dynamic=fold is not None and fold['bnd'] is not None
                 )
             except kfused.NotFusable:
                 src = None

@@ -161,7 +161,7 @@ def tp_structure(ops, nd, tol=1e-12):
 
 
 def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
-                       affine=False, gather=False, blist=False):
+                       affine=False, gather=False, dynamic=False):
     """Source of the sum-factorised fused kernel; arguments and return
     value as ``fused.gradflux_source``.
 
@@ -175,7 +175,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     partition boundary) has stored the common value (index < 0) -- with
     per-thread asynchronous copies straight into shared memory.
 
-    ``blist``: the blocks of the launch are handed out dynamically -- a
+    ``dynamic``: the blocks of the launch are handed out dynamically -- a
     CTA draws its next block from a device counter (``sched``) two
     iterations ahead, the last CTA to finish re-arms the counter.  Used
     where the element kernel is split into the blocks that touch a
@@ -629,7 +629,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
 
     from pyfr_b200.kernels.mul import _cpasync_src
 
-    if blist:
+    if dynamic:
         if SPLIT > 1 or NG > 1:
             raise NotFusable('dynamic blocks: whole blocks, one warp group')
         d_arg = ',\n         int* __restrict__ sched'
@@ -730,8 +730,8 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     {{
         const long long rbn = b / SPLIT;
         const int hf = (int) (b % SPLIT);
-        {"// (the indices were part of the previous block's barrier phase)" if onbar and not blist else ""}
-        {"if (n == 0)" if onbar and not blist else ""}
+        {"// (the indices were part of the previous block's barrier phase)" if onbar and not dynamic else ""}
+        {"if (n == 0)" if onbar and not dynamic else ""}
         cp_async_wait_all();
         {"""// (the bulk copies of u, the vertices and ROWD[NFPTS] whole rows
         // complete on one mbarrier)
@@ -757,7 +757,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
         // (ncu r02q: fetched one phase ahead, 5 % of the kernel's stall
         // samples were this wait)
         if (b + gridDim.x < (long long) nblocks*SPLIT)
-            gidx_load(b + gridDim.x);""" if not blist else ""}
+            gidx_load(b + gridDim.x);""" if not dynamic else ""}
         {"""// ... and once this thread's copies have landed they count as one
         // arrival on the block's barrier: nobody waits for them but the
         // threads that wait for the block (the cp.async.wait_all that stood
@@ -766,7 +766,7 @@ def gradflux_tp_source(be, ops, tplargs, pts, LD, nthreads=None, rowcls=None,
     }};'''
         # (dynamic blocks: the block after the next one is not known yet;
         # its indices are fetched at the top of the next iteration)
-        g_top = 'if (more) gidx_load(nxt);' if blist else ''
+        g_top = 'if (more) gidx_load(nxt);' if dynamic else ''
         g_issue = 'if (more) gather(nxt, it + 1);'
     else:
         g_arg = g_lambdas = g_top = g_issue = ''
@@ -1000,7 +1000,7 @@ gradflux(int nblocks, int neles,
     meta = dict(nthreads=nthreads, smem=smem, nctas=nctas, ngroups=NG,
                 words_per_block=(2*nu + nf + nd*nf)*GLD, tensor=True,
                 gather=gather, gather_points=nf*gcsub, split=SPLIT,
-                gather_rows=bool(rows), blist=bool(blist),
-                chunk=DCH if blist else 1)
+                gather_rows=bool(rows), dynamic=bool(dynamic),
+                chunk=DCH if dynamic else 1)
 
     return src, 'gradflux', meta
