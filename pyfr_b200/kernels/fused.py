@@ -602,8 +602,17 @@ def geometry_source(be, tplargs, pts, nthreads, affine=False, who=None):
             const fpdtype_t (&s)[NDIMS][NDIMS] = sA;
             const fpdtype_t rcpdjac_v = rjA;
 '''
-            npt_words, q_words = 2, 2*(nd*nd + 1)*csub
-            gsrc = f'#define QSTRIDE {2*(nd*nd + 1)}\n' + gsrc
+            # Per-element stride of QS: the elements of a block are read
+            # side by side with 16-byte loads, so consecutive elements
+            # must start four banks apart modulo a permutation -- in fp64
+            # a stride of 2 (mod 4) doubles (20 put elements e and e + 4
+            # on the same banks: 29 M excess wavefronts, 8 % of the
+            # kernel's shared-memory traffic, ncu r02s)
+            qst = 2*(nd*nd + 1)
+            while isz == 8 and qst % 4 != 2:
+                qst += 2
+            npt_words, q_words = 2, qst*csub
+            gsrc = f'#define QSTRIDE {qst}\n' + gsrc
         elif mj is not None:
             # Per element: Q[q][i] = sum_n W[d][k][n] V[n][i] for every
             # (d, monomial k) with a non-zero coefficient; per point: the
