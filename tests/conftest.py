@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200)')
+    config.addinivalue_line(
+        'markers', 'slow: CPU-model cases of opt-in kernel variants that are '
+        'not defaults (measured alternatives of round 1); run with '
+        'PYFR_B200_SLOW=1')
 
 
 def pytest_collection_modifyitems(config, items):
@@ -17,6 +21,12 @@ def pytest_collection_modifyitems(config, items):
     skipped (with the runtime's own message) rather than failed, so a plain
     ``pytest tests`` is green wherever it runs.  A library that is missing
     or fails to load is *not* a reason to skip."""
+    if not os.environ.get('PYFR_B200_SLOW'):
+        skip = pytest.mark.skip(reason='opt-in variant: PYFR_B200_SLOW=1')
+        for it in items:
+            if it.get_closest_marker('slow'):
+                it.add_marker(skip)
+
     gpu = [it for it in items if it.get_closest_marker('gpu')]
     if not gpu:
         return

@@ -61,33 +61,46 @@ def _kinds(sysm):
     (dict(order=2, warp=0.1), {'fusion': 0}, 'tflux'),
     (dict(order=2, warp=0.1), {'dead-rows': 0, 'gradflux-monojac': 0},
      'gradflux'),
-    (dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux'),
+    pytest.param(dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux',
+                 marks=pytest.mark.slow),
     (dict(order=3), {'n-soa': 4}, 'gradflux'),
     # two adjacent columns per work item (16-byte accesses)
-    (dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
-    (dict(order=3, beta=0.0), {'gradflux-vec2': 'p3'}, 'gradflux'),
-    (dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
-                               'gradflux-planes': 1}, 'gradflux'),
-    (dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
+    pytest.param(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=3, beta=0.0), {'gradflux-vec2': 'p3'}, 'gradflux',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
+                               'gradflux-planes': 1}, 'gradflux',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux',
+                 marks=pytest.mark.slow),
     # intconu over pairs of points (128-bit accesses where both addresses
     # of a side are adjacent): one-sided, central and left-biased LDG
-    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0}, 'intconu'),
-    (dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {'conu-pairs': 1},
-     'intconu'),
-    (dict(order=2, beta=-0.5, curved=0.5, warp=0.1),
-     {'conu-pairs': 1, 'conu-fold': 0}, 'intconu'),
-    (dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0}, 'intconu'),
-    (dict(order=3), {'conu-pairs': 1, 'n-soa': 4, 'conu-fold': 0}, 'intconu'),
+    pytest.param(dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0}, 'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {'conu-pairs': 1},
+     'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=2, beta=-0.5, curved=0.5, warp=0.1),
+     {'conu-pairs': 1, 'conu-fold': 0}, 'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0}, 'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=3), {'conu-pairs': 1, 'n-soa': 4, 'conu-fold': 0}, 'intconu',
+                 marks=pytest.mark.slow),
     # ... with the interface points in true address order (most pairs
     # then take the 128-bit path)
-    (dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address',
-                               'conu-fold': 0}, 'intconu'),
-    (dict(order=3, rsolver='hllc', beta=0.0), {'conu-pairs': 1,
+    pytest.param(dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address',
+                               'conu-fold': 0}, 'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=3, rsolver='hllc', beta=0.0), {'conu-pairs': 1,
                                                'inters-order': 'address'},
-     'intconu'),
-    (dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0,
+     'intconu',
+                 marks=pytest.mark.slow),
+    pytest.param(dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0,
                                           'inters-order': 'address'},
-     'intconu'),
+     'intconu',
+                 marks=pytest.mark.slow),
     (dict(order=4), {'inters-order': 'address'}, 'gradflux'),
     # the table-driven fused kernel (what non-tensor-product elements and
     # hexes with gradflux-tensor = 0 take)
@@ -101,13 +114,15 @@ def _kinds(sysm):
      'gradflux'),
     (dict(order=2, warp=0.1), {'dead-rows': 0}, 'gradflux'),
     (dict(order=1), {}, 'gradflux'),
-    # the benchmark's kernel variants (p = 4): common solution gathered by
-    # the element kernel, half blocks (the default); each switched off
+    # the benchmark's kernel (p = 4): common solution gathered by the
+    # element kernel (whole rows by bulk copy, the rest point by point);
+    # the fold and the row copies switched off; the opt-in half-block form
     (dict(order=4), {}, 'gradflux'),
     (dict(order=4), {'conu-fold': 0}, 'intconu'),
-    (dict(order=4), {'gradflux-split': 0}, 'gradflux'),
+    (dict(order=4), {'gather-rows': 0}, 'gradflux'),
+    (dict(order=4), {'gradflux-split': 1}, 'gradflux'),
     (dict(order=4, beta=-0.5, warp=0.1), {'conu-fold': 0,
-                                          'gradflux-split': 0}, 'intconu'),
+                                          'gradflux-split': 1}, 'intconu'),
     (dict(order=4, beta=0.0, warp=0.1), {}, 'intconu'),
     (dict(order=4, beta=-0.5, curved=0.5, warp=0.1), {}, 'gradflux'),
     (dict(order=4, warp=0.1, rsolver='hllc'), {}, 'gradflux'),
@@ -142,6 +157,7 @@ def _vec2_cases():
     return VEC2_CASES
 
 
+@pytest.mark.slow
 @pytest.mark.parametrize('case,n,kw,opts', _vec2_cases(), ids=str)
 def test_vectorised_gradflux_device_cases(emulated, case, n, kw, opts):
     """The device parity cases of the gradflux-vec2 variants
@@ -647,6 +663,7 @@ def test_mixed_element_types(emulated, pattern, n, kw, nfused):
     assert kinds.count('fluxdiv') + kinds.count('gradflux') == nfused
 
 
+@pytest.mark.slow
 def test_dense_operators_from_constant_table(emulated):
     """mul-const-table: operators with many distinct coefficients (tets,
     pyramids) read them from __constant__ memory instead of literals."""
