@@ -155,8 +155,6 @@ class B200Graph(base.Graph):
         self._fgroups = getattr(self, '_fgroups', []) + [(kerns, subs)]
 
     def _fuse(self):
-        from pyfr_b200 import fusion
-
         be = self.backend
         if not be.fuse:
             return
@@ -164,6 +162,13 @@ class B200Graph(base.Graph):
         # (the graph being planned, for rewrites that look at its other
         # kernels: fusion.conu_fold_plan)
         be._fusing = self
+        try:
+            self._fuse_groups(be)
+        finally:
+            be._fusing = None
+
+    def _fuse_groups(self, be):
+        from pyfr_b200 import fusion
 
         for kerns, subs in getattr(self, '_fgroups', []):
             new = fusion.fuse_group(be, kerns, subs)

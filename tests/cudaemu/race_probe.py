@@ -50,7 +50,14 @@ runs = [('tgv', (3, 2, 2), dict(order=2, warp=0.1), {}),
         ('tgv', (3, 2, 2), dict(order=2, warp=0.1), {'gradflux-tensor': 0}),
         ('tgv', 2, dict(order=4), {'gradflux-groups': 2}),
         ('tgv', (3, 2, 2), dict(order=3), {'n-soa': 4}),
-        ('tgv', 2, dict(order=2, precision='single'), {})]
+        ('tgv', 2, dict(order=2, precision='single'), {}),
+        # persistent loops of several blocks per CTA: the gathered common
+        # solution (bulk-copied rows, per-thread copies, indices fetched an
+        # iteration ahead, all completing on the block's mbarrier); the
+        # per-point form; the opt-in half-block kernel
+        ('tgv', (9, 3, 2), dict(order=2, warp=0.1), {'sm-count': 2}),
+        ('tgv', (9, 3, 2), dict(order=2), {'sm-count': 2, 'gather-rows': 0}),
+        ('tgv', 2, dict(order=4), {'gradflux-split': 1})]
 if '--drop-barrier' in sys.argv:
     runs = runs[:1]
 
@@ -71,6 +78,28 @@ if '--drop-barrier' not in sys.argv:
         cfg.set('backend-b200', 'graphs', 'false')
         s = get_system(B200Backend(cfg), box.local_mesh(), cfg, 2)
         s.rhs(0.0, 0, 1)
+
+    # Two partitions on one device: the element kernel as an interior
+    # launch (blocks drawn dynamically from a device counter) and a
+    # partition-boundary launch
+    from pyfr_b200.comm import LoopbackWorld
+
+    world, systems = LoopbackWorld(2), []
+    for r in range(2):
+        cfg, box = cases.make('tgv', (64, 2, 2), order=2)
+        cfg.set('backend-b200', 'graphs', 'false')
+        cfg.set('backend-b200', 'sm-count', 3)
+        comm = world.peer(r)
+        be = B200Backend(cfg, comm=comm)
+        comm.rt = be.rt
+        vparts = box.brick_partition((2, 1, 1))
+        systems.append(get_system(be, box.local_mesh(vparts, r), cfg, 2,
+                                  comm=comm))
+    for _ in range(2):
+        world.run_lockstep(systems, 0.0, 0, 1)
+    assert any(k.info.get('part') == 'interior'
+               for w, k in systems[0].rhs_graphs(0, 1)[0].plan
+               if w == 'kernel' and getattr(k, 'info', None))
 
     # Shared-memory tree reduction + atomics (error norm), rkvdh2 stages
     from pyfr_b200.host.integrator import PIController, RK45Stepper
