@@ -2,8 +2,10 @@
 
 Counterpart of ``pyfr/backends/cuda/kernels/axnpby.mako:4-44``: the same
 ``a0 == 0`` (overwrite, ``x0`` never read) and general paths, but written as
-a flat grid-stride sweep over the whole allocation with 128-bit accesses
--- every bank shares one blocked layout, so no index arithmetic is needed.
+a flat grid-stride sweep over the whole allocation -- every bank shares one
+blocked layout, so no index arithmetic is needed -- with coalesced
+element-wide accesses, four independent iterations of a thread in flight
+(``#pragma unroll``); an HBM-streaming kernel, not on the RHS path.
 """
 
 from pyfr_b200.kernels import physics as ph
