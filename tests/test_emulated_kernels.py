@@ -53,6 +53,11 @@ def _kinds(sysm):
             for w, k in g.plan if w == 'kernel']
 
 
+def _slow(*case):
+    """An opt-in kernel variant that is not a default (PYFR_B200_SLOW=1)"""
+    return pytest.param(*case, marks=pytest.mark.slow)
+
+
 @pytest.mark.parametrize('kw,opts,expect', [
     (dict(order=2, warp=0.1), {}, 'gradflux'),
     (dict(order=2), {}, 'gradflux'),                           # affine path
@@ -61,46 +66,35 @@ def _kinds(sysm):
     (dict(order=2, warp=0.1), {'fusion': 0}, 'tflux'),
     (dict(order=2, warp=0.1), {'dead-rows': 0, 'gradflux-monojac': 0},
      'gradflux'),
-    pytest.param(dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux',
-                 marks=pytest.mark.slow),
+    _slow(dict(order=2, warp=0.1), {'gradflux-planes': 1}, 'gradflux'),
     (dict(order=3), {'n-soa': 4}, 'gradflux'),
     # two adjacent columns per work item (16-byte accesses)
-    pytest.param(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=3, beta=0.0), {'gradflux-vec2': 'p3'}, 'gradflux',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
-                               'gradflux-planes': 1}, 'gradflux',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux',
-                 marks=pytest.mark.slow),
+    _slow(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
+    _slow(dict(order=3, beta=0.0), {'gradflux-vec2': 'p3'}, 'gradflux'),
+    _slow(dict(order=2, warp=0.1), {'gradflux-vec2': 'p1,p3,p5',
+                                    'gradflux-planes': 1}, 'gradflux'),
+    _slow(dict(order=4), {'gradflux-vec2': 'p1,p3,p5'}, 'gradflux'),
     # intconu over pairs of points (128-bit accesses where both addresses
     # of a side are adjacent): one-sided, central and left-biased LDG
-    pytest.param(dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0}, 'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=3, rsolver='hllc', beta=0.0, warp=0.1), {'conu-pairs': 1},
-     'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=2, beta=-0.5, curved=0.5, warp=0.1),
-     {'conu-pairs': 1, 'conu-fold': 0}, 'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0}, 'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=3), {'conu-pairs': 1, 'n-soa': 4, 'conu-fold': 0}, 'intconu',
-                 marks=pytest.mark.slow),
+    _slow(dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0},
+          'intconu'),
+    _slow(dict(order=3, rsolver='hllc', beta=0.0, warp=0.1),
+          {'conu-pairs': 1}, 'intconu'),
+    _slow(dict(order=2, beta=-0.5, curved=0.5, warp=0.1),
+          {'conu-pairs': 1, 'conu-fold': 0}, 'intconu'),
+    _slow(dict(order=2, beta=0.25), {'conu-pairs': 1, 'fusion': 0},
+          'intconu'),
+    _slow(dict(order=3), {'conu-pairs': 1, 'n-soa': 4, 'conu-fold': 0},
+          'intconu'),
     # ... with the interface points in true address order (most pairs
     # then take the 128-bit path)
-    pytest.param(dict(order=2, warp=0.1), {'conu-pairs': 1, 'inters-order': 'address',
-                               'conu-fold': 0}, 'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=3, rsolver='hllc', beta=0.0), {'conu-pairs': 1,
-                                               'inters-order': 'address'},
-     'intconu',
-                 marks=pytest.mark.slow),
-    pytest.param(dict(order=2, beta=-0.5, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0,
-                                          'inters-order': 'address'},
-     'intconu',
-                 marks=pytest.mark.slow),
+    _slow(dict(order=2, warp=0.1), {'conu-pairs': 1, 'conu-fold': 0,
+                                    'inters-order': 'address'}, 'intconu'),
+    _slow(dict(order=3, rsolver='hllc', beta=0.0),
+          {'conu-pairs': 1, 'inters-order': 'address'}, 'intconu'),
+    _slow(dict(order=2, beta=-0.5, warp=0.1),
+          {'conu-pairs': 1, 'conu-fold': 0, 'inters-order': 'address'},
+          'intconu'),
     (dict(order=4), {'inters-order': 'address'}, 'gradflux'),
     # the table-driven fused kernel (what non-tensor-product elements and
     # hexes with gradflux-tensor = 0 take)
